@@ -1,0 +1,126 @@
+/*
+ * s3d_b200.h -- C ABI of libs3d_b200.so: the sm_100a kernels behind the Simple3D-Former encoder hot path.
+ *
+ * The reference (VITA-Group/Simple3D-Former @ a6f74c8) has no FFI/plugin interface of its own: it is pure Python and the
+ * arithmetic lives in timm==0.3.2 / torch modules. Each entry point below therefore names the reference Python symbol
+ * whose arithmetic it replaces (file:line in the reference tree, or the timm-0.3.2 symbol for the encoder blocks).
+ * A maintainer binds these with ctypes; simple3d_former_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); the library never allocates, frees or
+ *     retains a pointer; work is enqueued on `stream` (a cudaStream_t passed as void*) and the call returns at once;
+ *   - return value: 0 = success; negative = S3D_ERR_* argument error (nothing was launched); positive = cudaError_t;
+ *   - no exceptions cross the ABI, no global state besides cached function attributes; re-entrant per stream;
+ *   - "bf16" buffers hold __nv_bfloat16; "f32" buffers float; index buffers int64_t (torch.long);
+ *   - row-major everywhere, leading dimensions in ELEMENTS.
+ */
+#ifndef S3D_B200_H_
+#define S3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3D_ABI_VERSION 1
+
+enum {
+  S3D_OK = 0,
+  S3D_ERR_BAD_SHAPE = -1,   /* non-positive / inconsistent sizes                         */
+  S3D_ERR_UNSUPPORTED = -2, /* valid but not implemented (e.g. head_dim not in 64/192/256) */
+  S3D_ERR_ALIGNMENT = -3,   /* pointer or leading dimension not 16-byte aligned           */
+  S3D_ERR_NULL = -4,        /* required pointer is NULL                                   */
+  S3D_ERR_DRIVER = -5,      /* cuTensorMapEncodeTiled unavailable / failed                */
+  S3D_ERR_WORKSPACE = -6    /* workspace too small                                        */
+};
+
+/* epilogues of s3d_gemm_bf16 */
+enum { S3D_EPI_NONE = 0, S3D_EPI_GELU = 1, S3D_EPI_DGELU = 2 };
+
+int s3d_abi_version(void);
+const char* s3d_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM (tcgen05 + TMEM + TMA):  D[M,N] = epilogue(alpha * A x B^T)
+ *   replaces nn.Linear inside timm-0.3.2 Attention.qkv / Attention.proj / Mlp.fc1 / Mlp.fc2,
+ *   nn.MultiheadAttention in_proj/out_proj and linear1/linear2 of the group_embed layer (vit_3d_2d_pretrain.py:381),
+ *   the Conv3d patchify as a GEMM (embed_layer_3d_modality.py:22-24,52-54), and all of their backward GEMMs.
+ *   A: a_mn_major == 0 -> [M,K] row-major (lda >= K);  == 1 -> stored [K,M] row-major (lda >= M)
+ *   B: b_mn_major == 0 -> [N,K] row-major (ldb >= K);  == 1 -> stored [K,N] row-major (ldb >= N)
+ *   epilogue order: v = alpha*acc; v += bias[n]; GELU: (aux_out = bf16(v)), v = gelu_erf(v);
+ *                   DGELU: v *= gelu_erf'(aux_in[m,n]); v += residual[m,n]; D = (out_fp32 ? v : bf16(v)).
+ *   residual may alias D (fp32 accumulate). batch > 1 runs `batch` independent problems with element strides.
+ * ------------------------------------------------------------------------------------------------------------- */
+int s3d_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldd,
+                  int a_mn_major, int b_mn_major, int out_fp32, float alpha, const float* bias, const float* residual,
+                  int64_t ldr, int epilogue, const void* aux_in, int64_t ld_aux_in, void* aux_out, int64_t ld_aux_out,
+                  int batch, int64_t batch_stride_a, int64_t batch_stride_b, int64_t batch_stride_d,
+                  int64_t batch_stride_r, int force_bn, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * LayerNorm (timm Block.norm1/norm2, VisionTransformer.norm: eps 1e-6, vit_3d_2d_pretrain.py:287; post-norm layers of
+ * nn.TransformerEncoderLayer: eps 1e-5). x f32 [T,D]; optional addend fuses "x + addend" (and writes it to sum_out).
+ * y_bf16 / y_f32 / mean / rstd may each be NULL. Backward adds `dres` (gradient through the residual branch) and can
+ * emit a bf16 copy of dx for the next GEMM; dgamma/dbeta are ACCUMULATED (caller zeroes them).
+ * ------------------------------------------------------------------------------------------------------------- */
+int s3d_layernorm_fwd(const float* x, const float* addend, float* sum_out, const float* gamma, const float* beta,
+                      void* y_bf16, float* y_f32, float* mean, float* rstd, int T, int D, float eps, void* stream);
+int s3d_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,
+                      const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                      int T, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Attention core (timm-0.3.2 Attention.forward: softmax(q k^T * scale) v; F.multi_head_attention_forward inside the
+ * group_embed layer). q/k/v/out addressed by element strides (batch, head, row) so both [B,N,3,H,dh] and the
+ * sequence-first [S,Nb,3E] layouts are read in place. head_dim in {64,192,256}. lse [B,H,N] f32 is written by fwd and
+ * read by bwd; delta [B,H,N] f32 is scratch for bwd. dq/dk/dv use the q/k/v strides, dout uses the out strides.
+ * ------------------------------------------------------------------------------------------------------------- */
+int s3d_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int head_dim,
+                 int64_t qkv_batch_stride, int64_t qkv_head_stride, int64_t qkv_row_stride, int64_t o_batch_stride,
+                 int64_t o_head_stride, int64_t o_row_stride, float scale, void* stream);
+int s3d_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                 float* delta, void* dq, void* dk, void* dv, int B, int H, int N, int head_dim,
+                 int64_t qkv_batch_stride, int64_t qkv_head_stride, int64_t qkv_row_stride, int64_t o_batch_stride,
+                 int64_t o_head_stride, int64_t o_row_stride, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Elementwise / data-movement helpers of the path
+ * ------------------------------------------------------------------------------------------------------------- */
+int s3d_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+/* out[c, r] = bf16(in[r, c]); in is f32 or bf16 [R,C] */
+int s3d_transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int C, int64_t ld_in, int64_t ld_out,
+                          void* stream);
+/* out[c] (+)= sum_t in[t, c]; Linear bias gradients */
+int s3d_colsum_bf16(const void* in, float* out, int T, int C, int64_t ld, int accumulate, void* stream);
+/* Conv3d(k = s = cell) operand: x f32 [B,1,V,V,V] -> P bf16 [B*p*p*(zsum?1:p), Kpad]; zsum sums the pz patches of a
+ * column first (VoxelEmbed's mean over dim 4, embed_layer_3d_modality.py:38). */
+int s3d_voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
+                           void* stream);
+/* torch.optim.Adam step (train_cls_voxel.py:195) over a flat f32 segment; refreshes the bf16 shadow; grad_scale folds
+ * the 1/world_size of the DDP gradient average (train_cls_voxel.py:154-165). */
+int s3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Point grouping (reference data/pointnet_util.py). xyz f32 [B,N,3], query f32 [B,S,3].
+ *   s3d_knn          : square_distance (:22-36) + argsort()[:, :, :K] (:119-120, :233-234; models/3DViT/model.py:23-24);
+ *                      idx int64 [B,S,K] ascending (distance, index); dist (optional) f32 [B,S,K].
+ *   s3d_ball_query   : query_ball_point (:76-96); radius_sq = float32(radius**2); idx int64 [B,S,nsample].
+ *   s3d_fps          : farthest_point_sample (:53-73) with the random start made explicit: start int64 [B].
+ *   s3d_gather_rows  : index_points (:39-50): out[b,m,:] = points[b, idx[b,m], :], points f32 [B,N,C], idx int64 [B,M].
+ *   s3d_scatter_add_rows: its backward (grad_points zeroed, then accumulated).
+ * ------------------------------------------------------------------------------------------------------------- */
+int s3d_knn(const float* xyz, const float* query, int64_t* idx, float* dist, int B, int N, int S, int K, void* stream);
+int s3d_ball_query(const float* xyz, const float* query, int64_t* idx, int B, int N, int S, float radius_sq,
+                   int nsample, void* stream);
+int s3d_fps(const float* xyz, const int64_t* start, int64_t* idx, int B, int N, int npoint, void* stream);
+int s3d_gather_rows(const float* points, const int64_t* idx, float* out, int B, int N, int M, int C, void* stream);
+int s3d_scatter_add_rows(const float* grad_out, const int64_t* idx, float* grad_points, int B, int N, int M, int C,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S3D_B200_H_ */

@@ -1,0 +1,289 @@
+"""ctypes binding of libs3d_b200.so (C ABI declared in include/s3d_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+PyTorch is used only to own device memory and streams; every pointer handed to the library is `tensor.data_ptr()`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs3d_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+# name -> (restype, argtypes); must list every symbol of include/s3d_b200.h (tests/test_abi.py checks this).
+_P = c_void_p
+SIGNATURES = {
+    "s3d_abi_version": (c_int, []),
+    "s3d_error_string": (c_char_p, [c_int]),
+    "s3d_gemm_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float,
+                              _P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_int64, c_int64, c_int64,
+                              c_int64, c_int, _P]),
+    "s3d_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
+    "s3d_layernorm_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "s3d_attn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64,
+                             c_int64, c_int64, c_float, _P]),
+    "s3d_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64,
+                             c_int64, c_int64, c_int64, c_int64, c_float, _P]),
+    "s3d_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "s3d_transpose_to_bf16": (c_int, [_P, c_int, _P, c_int, c_int, c_int64, c_int64, _P]),
+    "s3d_colsum_bf16": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, _P]),
+    "s3d_voxel_patch_gather": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s3d_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int,
+                              c_float, _P]),
+    "s3d_knn": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "s3d_ball_query": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P]),
+    "s3d_fps": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "s3d_gather_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "s3d_scatter_add_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+}
+
+_lib = None
+LAUNCHES = 0  # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libs3d_b200.so (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libs3d_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the sm_100a CUDA extension is mandatory; there is no CPU or PyTorch fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if _lib.s3d_abi_version() != 1:
+            raise RuntimeError("libs3d_b200.so ABI version mismatch")
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().s3d_error_string(code)
+        raise RuntimeError(f"{what} failed: {msg.decode() if msg else code} (code {code})")
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("simple3d_former_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def call(name: str, *args) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
+    check(getattr(lib(), name)(*args), name)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# thin tensor-level wrappers (shape checks + pointer extraction only)
+# ------------------------------------------------------------------------------------------------------------------
+EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, alpha=1.0, bias=None, residual=None,
+         epilogue=EPI_NONE, aux_in=None, aux_out=None, force_bn=0):
+    """D[M,N] = epi(alpha * A @ B^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn); 2-D or batched 3-D."""
+    _need_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    batched = a.dim() == 3
+    if batched:
+        assert b.dim() == 3 and a.shape[0] == b.shape[0]
+        batch = a.shape[0]
+        a2, b2 = a[0], b[0]
+    else:
+        batch = 1
+        a2, b2 = a, b
+    assert a2.stride(-1) == 1 and b2.stride(-1) == 1
+    if a_mn:
+        K, M = a2.shape
+    else:
+        M, K = a2.shape
+    if b_mn:
+        Kb, N = b2.shape
+    else:
+        N, Kb = b2.shape
+    assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
+    if out is None:
+        shape = (batch, M, N) if batched else (M, N)
+        out = torch.empty(shape, device=a.device, dtype=out_dtype)
+    o2 = out[0] if batched else out
+    assert o2.shape == (M, N) and o2.stride(-1) == 1
+    r2 = None
+    if residual is not None:
+        assert residual.dtype == torch.float32
+        r2 = residual[0] if batched else residual
+        assert r2.shape == (M, N) and r2.stride(-1) == 1
+    call("s3d_gemm_bf16", ptr(a), ptr(b), ptr(out), M, N, K, a2.stride(0), b2.stride(0), o2.stride(0), int(a_mn),
+         int(b_mn), int(out.dtype == torch.float32), float(alpha), ptr(bias), ptr(residual),
+         r2.stride(0) if r2 is not None else 0, epilogue, ptr(aux_in), aux_in.stride(0) if aux_in is not None else 0,
+         ptr(aux_out), aux_out.stride(0) if aux_out is not None else 0, batch,
+         a.stride(0) if batched else 0, b.stride(0) if batched else 0, out.stride(0) if batched else 0,
+         residual.stride(0) if (batched and residual is not None) else 0, force_bn, stream())
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, addend=None, want_sum=False, want_bf16=True, want_f32=False, want_stats=True):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    D = x.shape[-1]
+    T = x.numel() // D
+    y16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    y32 = torch.empty_like(x) if want_f32 else None
+    s = torch.empty_like(x) if (want_sum and addend is not None) else None
+    mean = torch.empty(T, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(T, device=x.device, dtype=torch.float32) if want_stats else None
+    if addend is not None:
+        assert addend.dtype == torch.float32 and addend.is_contiguous() and addend.shape == x.shape
+    call("s3d_layernorm_fwd", ptr(x), ptr(addend), ptr(s), ptr(gamma), ptr(beta), ptr(y16), ptr(y32), ptr(mean),
+         ptr(rstd), T, D, float(eps), stream())
+    return y16, y32, s, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, dres=None, want_bf16=False, dgamma=None, dbeta=None):
+    _need_cuda(dy, x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and dy.is_contiguous()
+    D = x.shape[-1]
+    T = x.numel() // D
+    dx = torch.empty_like(x)
+    dx16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    if dgamma is None:
+        dgamma = torch.zeros(D, device=x.device, dtype=torch.float32)
+        dbeta = torch.zeros(D, device=x.device, dtype=torch.float32)
+    call("s3d_layernorm_bwd", ptr(dy), int(dy.dtype == torch.bfloat16), ptr(x), ptr(gamma), ptr(mean), ptr(rstd),
+         ptr(dres), ptr(dx), ptr(dx16), ptr(dgamma), ptr(dbeta), T, D, stream())
+    return dx, dx16, dgamma, dbeta
+
+
+def attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale):
+    call("s3d_attn_fwd", ptr(q) if hasattr(q, "data_ptr") else q, ptr(k) if hasattr(k, "data_ptr") else k,
+         ptr(v) if hasattr(v, "data_ptr") else v, ptr(out), ptr(lse), B, H, N, dh, qs[0], qs[1], qs[2], os_[0], os_[1],
+         os_[2], float(scale), stream())
+
+
+def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, B, H, N, dh, qs, os_, scale):
+    call("s3d_attn_bwd", q, k, v, ptr(out), ptr(dout), ptr(lse), ptr(delta), dq, dk, dv, B, H, N, dh, qs[0], qs[1],
+         qs[2], os_[0], os_[1], os_[2], float(scale), stream())
+
+
+def cast_bf16(x, out=None):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    call("s3d_cast_f32_to_bf16", ptr(x), ptr(out), x.numel(), stream())
+    return out
+
+
+def transpose_bf16(x, out=None):
+    """out[C,R] = bf16(x[R,C]) for a 2-D f32/bf16 matrix."""
+    _need_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    if out is None:
+        out = torch.empty((C, R), device=x.device, dtype=torch.bfloat16)
+    call("s3d_transpose_to_bf16", ptr(x), int(x.dtype == torch.bfloat16), ptr(out), R, C, x.stride(0), out.stride(0),
+         stream())
+    return out
+
+
+def colsum(x, out=None, accumulate=False):
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    T, C = x.shape
+    if out is None:
+        out = torch.empty(C, device=x.device, dtype=torch.float32)
+        accumulate = False
+    call("s3d_colsum_bf16", ptr(x), ptr(out), T, C, x.stride(0), int(accumulate), stream())
+    return out
+
+
+def voxel_patch_gather(x, cell, patch, kpad, zsum):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5 and x.shape[1] == 1
+    B, _, V, _, _ = x.shape
+    rows = B * patch * patch * (1 if zsum else patch)
+    P = torch.empty((rows, kpad), device=x.device, dtype=torch.bfloat16)
+    call("s3d_voxel_patch_gather", ptr(x), ptr(P), B, V, cell, patch, kpad, int(zsum), stream())
+    return P
+
+
+def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    _need_cuda(p, g, m, v)
+    call("s3d_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), float(lr), float(beta1), float(beta2),
+         float(eps), float(weight_decay), int(step), float(grad_scale), stream())
+
+
+def knn(xyz, query, K, want_dist=False):
+    _need_cuda(xyz, query)
+    xyz = xyz.contiguous().float()
+    query = query.contiguous().float()
+    B, N, _ = xyz.shape
+    S = query.shape[1]
+    idx = torch.empty((B, S, K), device=xyz.device, dtype=torch.long)
+    dist = torch.empty((B, S, K), device=xyz.device, dtype=torch.float32) if want_dist else None
+    call("s3d_knn", ptr(xyz), ptr(query), ptr(idx), ptr(dist), B, N, S, K, stream())
+    return (idx, dist) if want_dist else idx
+
+
+def ball_query(radius_sq_f32, nsample, xyz, query):
+    _need_cuda(xyz, query)
+    xyz = xyz.contiguous().float()
+    query = query.contiguous().float()
+    B, N, _ = xyz.shape
+    S = query.shape[1]
+    idx = torch.empty((B, S, nsample), device=xyz.device, dtype=torch.long)
+    call("s3d_ball_query", ptr(xyz), ptr(query), ptr(idx), B, N, S, float(radius_sq_f32), nsample, stream())
+    return idx
+
+
+def fps(xyz, npoint, start):
+    _need_cuda(xyz, start)
+    xyz = xyz.contiguous().float()
+    B, N, _ = xyz.shape
+    start = start.contiguous().long()
+    idx = torch.empty((B, npoint), device=xyz.device, dtype=torch.long)
+    call("s3d_fps", ptr(xyz), ptr(start), ptr(idx), B, N, npoint, stream())
+    return idx
+
+
+def gather_rows(points, idx):
+    _need_cuda(points, idx)
+    B, N, C = points.shape
+    M = idx.numel() // B
+    out = torch.empty((B, M, C), device=points.device, dtype=torch.float32)
+    call("s3d_gather_rows", ptr(points), ptr(idx), ptr(out), B, N, M, C, stream())
+    return out
+
+
+def scatter_add_rows(grad_out, idx, N):
+    _need_cuda(grad_out, idx)
+    B, M, C = grad_out.shape
+    gp = torch.empty((B, N, C), device=grad_out.device, dtype=torch.float32)
+    call("s3d_scatter_add_rows", ptr(grad_out), ptr(idx), ptr(gp), B, N, M, C, stream())
+    return gp

@@ -1,0 +1,650 @@
+// Scaled-dot-product attention core, forward and backward, for every sequence shape on the hot path:
+//   timm-0.3.2 Attention.forward (q @ k^T * scale -> softmax -> @ v) with N in {15, 26, 197, 257, 513}, dh in {64, 256}
+//   nn.MultiheadAttention inside the group_embed TransformerEncoderLayer (vit_3d_2d_pretrain.py:381,479): S = 12544,
+//   dh = 192, sequence-first layout.
+// Flash-style: scores never touch HBM (the reference materialises [B,H,N,N] fp32), online softmax in fp32, bf16 operands.
+// Tensor-core path here is warp-level mma.sync.m16n8k16 with ldmatrix from XOR-swizzled shared memory; operands are
+// addressed through (batch, head, row) strides so the timm [B,N,3,H,dh] and the sequence-first [S,Nb,3E] layouts are
+// both consumed in place (no permute/contiguous copies).
+#include "kernels.h"
+
+namespace s3d {
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// smem tile of ROWS x DH bf16, 16-byte chunks XOR-swizzled by (row & 7): conflict-free ldmatrix in both orientations.
+template <int DH>
+__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
+  return base + (uint32_t)(((row * (DH / 8)) + (chunk ^ (row & 7))) << 4);
+}
+
+template <int DH, int ROWS>
+__device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g, long long row_stride, int r0, int N,
+                                          int tid, int nthr) {
+  constexpr int CH = DH / 8;
+  for (int i = tid; i < ROWS * CH; i += nthr) {
+    const int r = i / CH, c = i % CH;
+    const int gr = r0 + r;
+    const int cr = gr < N ? gr : N - 1;
+    cp_async16(tile_addr<DH>(sbase, r, c), g + (long long)cr * row_stride + c * 8, gr < N ? 16 : 0);
+  }
+}
+
+template <bool INDEP>
+__device__ __forceinline__ void group_sync() {
+  if (INDEP) __syncwarp(); else __syncthreads();
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ================================================================================================
+// Forward. CTA = NWARPS warps; each warp owns 16 query rows. INDEP: every warp works on its own (batch, head)
+// (tiny sequences, N <= 16), otherwise the CTA shares K/V tiles of one (batch, head).
+// ================================================================================================
+template <int DH, int NWARPS, int BKV, bool INDEP>
+__global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  constexpr int BQ = INDEP ? 16 : 16 * NWARPS;
+  constexpr int kQBytes = BQ * DH * 2;
+  constexpr int kKVBytes = BKV * DH * 2;
+  constexpr int NST = INDEP ? 1 : 2;                       // INDEP sequences fit one key tile: no ring needed
+  constexpr int kPerGroup = kQBytes + NST * 2 * kKVBytes;  // Q + NST stages x (K, V)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = INDEP ? lane : threadIdx.x;
+  constexpr int nthr = INDEP ? 32 : NWARPS * 32;
+  const int wq = INDEP ? 0 : warp;
+
+  long long bh;  // flattened (batch, head)
+  int q_tile;
+  if (INDEP) {
+    bh = (long long)blockIdx.x * NWARPS + warp;
+    q_tile = 0;
+    if (bh >= (long long)p.B * p.H) return;  // whole warp exits; only __syncwarp is used below
+  } else {
+    bh = (long long)blockIdx.z * p.H + blockIdx.y;
+    q_tile = blockIdx.x;
+  }
+  const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+  const uint32_t sbase = smem_u32(smem_attn) + (INDEP ? warp * kPerGroup : 0);
+  const uint32_t sQ = sbase;
+  const uint32_t sK0 = sbase + kQBytes;
+  const uint32_t sV0 = sK0 + kKVBytes;
+
+  const __nv_bfloat16* gq = p.q + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs;
+  const __nv_bfloat16* gk = p.k + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs;
+  const __nv_bfloat16* gv = p.v + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs;
+  const int q0 = q_tile * BQ;
+  const int nkt = (p.N + BKV - 1) / BKV;
+
+  load_tile<DH, BQ>(sQ, gq, p.qkv_rs, q0, p.N, tid, nthr);
+  load_tile<DH, BKV>(sK0, gk, p.qkv_rs, 0, p.N, tid, nthr);
+  load_tile<DH, BKV>(sV0, gv, p.qkv_rs, 0, p.N, tid, nthr);
+  cp_async_commit();
+
+  float o[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float sc = p.scale * kLog2e;
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int st = INDEP ? 0 : (kt & 1);
+    const uint32_t sK = sK0 + st * 2 * kKVBytes;
+    const uint32_t sV = sK + kKVBytes;
+    if (!INDEP && kt + 1 < nkt) {
+      const uint32_t nK = sK0 + (st ^ 1) * 2 * kKVBytes;
+      load_tile<DH, BKV>(nK, gk, p.qkv_rs, (kt + 1) * BKV, p.N, tid, nthr);
+      load_tile<DH, BKV>(nK + kKVBytes, gv, p.qkv_rs, (kt + 1) * BKV, p.N, tid, nthr);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    group_sync<INDEP>();
+
+    float s[BKV / 8][4];
+#pragma unroll
+    for (int i = 0; i < BKV / 8; ++i) { s[i][0] = 0.f; s[i][1] = 0.f; s[i][2] = 0.f; s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      ldsm_x4(tile_addr<DH>(sQ, wq * 16 + (lane & 15), ks * 2 + (lane >> 4)), a0, a1, a2, a3);
+#pragma unroll
+      for (int nt2 = 0; nt2 < BKV / 16; ++nt2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(tile_addr<DH>(sK, nt2 * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+        mma16816(s[2 * nt2], a0, a1, a2, a3, b0, b1);
+        mma16816(s[2 * nt2 + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    // mask keys beyond N, online softmax
+    const int key0 = kt * BKV + 2 * (lane & 3);
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < BKV / 8; ++nt) {
+      const int kidx = key0 + nt * 8;
+      if (kidx >= p.N) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (kidx + 1 >= p.N) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float al0 = exp2f((m0 - mn0) * sc), al1 = exp2f((m1 - mn1) * sc);
+    m0 = mn0; m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < BKV / 8; ++nt) {
+      s[nt][0] = exp2f((s[nt][0] - mn0) * sc);
+      s[nt][1] = exp2f((s[nt][1] - mn0) * sc);
+      s[nt][2] = exp2f((s[nt][2] - mn1) * sc);
+      s[nt][3] = exp2f((s[nt][3] - mn1) * sc);
+      rs0 += s[nt][0] + s[nt][1];
+      rs1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * al0 + rs0;
+    l1 = l1 * al1 + rs1;
+#pragma unroll
+    for (int i = 0; i < DH / 8; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
+    // O += P V
+#pragma unroll
+    for (int j = 0; j < BKV / 16; ++j) {
+      const uint32_t a0 = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+      const uint32_t a1 = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+      const uint32_t a2 = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      const uint32_t a3 = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+      for (int dt2 = 0; dt2 < DH / 16; ++dt2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(tile_addr<DH>(sV, j * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dt2 * 2 + (lane >> 4)), b0, b1, b2, b3);
+        mma16816(o[2 * dt2], a0, a1, a2, a3, b0, b1);
+        mma16816(o[2 * dt2 + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    group_sync<INDEP>();  // all reads of this stage done before it is refilled
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float il0 = 1.f / l0, il1 = 1.f / l1;
+  const int r0 = q0 + wq * 16 + (lane >> 2), r1 = r0 + 8;
+  __nv_bfloat16* go = p.out + (long long)b * p.o_bs + (long long)h * p.o_hs;
+#pragma unroll
+  for (int nt = 0; nt < DH / 8; ++nt) {
+    const int col = nt * 8 + 2 * (lane & 3);
+    if (r0 < p.N) *reinterpret_cast<uint32_t*>(go + (long long)r0 * p.o_rs + col) = pack_bf16x2(o[nt][0] * il0, o[nt][1] * il0);
+    if (r1 < p.N) *reinterpret_cast<uint32_t*>(go + (long long)r1 * p.o_rs + col) = pack_bf16x2(o[nt][2] * il1, o[nt][3] * il1);
+  }
+  if (p.lse != nullptr && (lane & 3) == 0) {
+    float* gl = p.lse + bh * p.N;
+    if (r0 < p.N) gl[r0] = m0 * p.scale + logf(l0);
+    if (r1 < p.N) gl[r1] = m1 * p.scale + logf(l1);
+  }
+}
+
+// ================================================================================================
+// Backward, part 0: delta[b,h,i] = sum_d dO[i,d] * O[i,d]   (one warp per row)
+// ================================================================================================
+__global__ void __launch_bounds__(256) attn_delta_kernel(const AttnParams p, int DH) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)p.B * p.H * p.N;
+  if (warp >= total) return;
+  const int i = (int)(warp % p.N);
+  const long long bh = warp / p.N;
+  const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+  const long long off = (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)i * p.o_rs;
+  float s = 0.f;
+  for (int d = lane * 2; d < DH; d += 64) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.o + off + d));
+    const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.dout + off + d));
+    s += a.x * g.x + a.y * g.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) p.delta[warp] = s;
+}
+
+// ================================================================================================
+// Backward, part 1: dQ. Each warp owns 16 query rows and sweeps the key tiles, recomputing P from lse.
+// ================================================================================================
+template <int DH, int NWARPS, int BKV, bool INDEP>
+__global__ void __launch_bounds__(NWARPS * 32) attn_bwd_dq_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  constexpr int BQ = INDEP ? 16 : 16 * NWARPS;
+  constexpr int kQBytes = BQ * DH * 2;
+  constexpr int kKVBytes = BKV * DH * 2;
+  constexpr int kPerGroup = 2 * kQBytes + 2 * kKVBytes;  // Q, dO, K, V (single stage)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = INDEP ? lane : threadIdx.x;
+  constexpr int nthr = INDEP ? 32 : NWARPS * 32;
+  const int wq = INDEP ? 0 : warp;
+  long long bh;
+  int q_tile;
+  if (INDEP) {
+    bh = (long long)blockIdx.x * NWARPS + warp;
+    q_tile = 0;
+    if (bh >= (long long)p.B * p.H) return;
+  } else {
+    bh = (long long)blockIdx.z * p.H + blockIdx.y;
+    q_tile = blockIdx.x;
+  }
+  const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+  const uint32_t sbase = smem_u32(smem_attn) + (INDEP ? warp * kPerGroup : 0);
+  const uint32_t sQ = sbase, sdO = sbase + kQBytes, sK = sbase + 2 * kQBytes, sV = sK + kKVBytes;
+  const long long qoff = (long long)b * p.qkv_bs + (long long)h * p.qkv_hs;
+  const long long ooff = (long long)b * p.o_bs + (long long)h * p.o_hs;
+  const int q0 = q_tile * BQ;
+  const int nkt = (p.N + BKV - 1) / BKV;
+
+  load_tile<DH, BQ>(sQ, p.q + qoff, p.qkv_rs, q0, p.N, tid, nthr);
+  load_tile<DH, BQ>(sdO, p.dout + ooff, p.o_rs, q0, p.N, tid, nthr);
+  cp_async_commit();
+
+  const int r0 = q0 + wq * 16 + (lane >> 2), r1 = r0 + 8;
+  const float* glse = p.lse + bh * p.N;
+  const float* gdel = p.delta + bh * p.N;
+  // padded query rows: lse = +inf makes P = 0
+  const float lse0 = r0 < p.N ? glse[r0] * kLog2e : INFINITY, lse1 = r1 < p.N ? glse[r1] * kLog2e : INFINITY;
+  const float del0 = r0 < p.N ? gdel[r0] : 0.f, del1 = r1 < p.N ? gdel[r1] : 0.f;
+  const float sc = p.scale * kLog2e;
+
+  float dq[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) { dq[i][0] = 0.f; dq[i][1] = 0.f; dq[i][2] = 0.f; dq[i][3] = 0.f; }
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    load_tile<DH, BKV>(sK, p.k + qoff, p.qkv_rs, kt * BKV, p.N, tid, nthr);
+    load_tile<DH, BKV>(sV, p.v + qoff, p.qkv_rs, kt * BKV, p.N, tid, nthr);
+    cp_async_commit();
+    cp_async_wait<0>();
+    group_sync<INDEP>();
+
+    float s[BKV / 8][4], dp[BKV / 8][4];
+#pragma unroll
+    for (int i = 0; i < BKV / 8; ++i) {
+      s[i][0] = 0.f; s[i][1] = 0.f; s[i][2] = 0.f; s[i][3] = 0.f;
+      dp[i][0] = 0.f; dp[i][1] = 0.f; dp[i][2] = 0.f; dp[i][3] = 0.f;
+    }
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) {
+      uint32_t a0, a1, a2, a3, g0, g1, g2, g3;
+      ldsm_x4(tile_addr<DH>(sQ, wq * 16 + (lane & 15), ks * 2 + (lane >> 4)), a0, a1, a2, a3);
+      ldsm_x4(tile_addr<DH>(sdO, wq * 16 + (lane & 15), ks * 2 + (lane >> 4)), g0, g1, g2, g3);
+#pragma unroll
+      for (int nt2 = 0; nt2 < BKV / 16; ++nt2) {
+        uint32_t b0, b1, b2, b3;
+        const int krow = nt2 * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int kch = ks * 2 + ((lane >> 3) & 1);
+        ldsm_x4(tile_addr<DH>(sK, krow, kch), b0, b1, b2, b3);
+        mma16816(s[2 * nt2], a0, a1, a2, a3, b0, b1);
+        mma16816(s[2 * nt2 + 1], a0, a1, a2, a3, b2, b3);
+        ldsm_x4(tile_addr<DH>(sV, krow, kch), b0, b1, b2, b3);
+        mma16816(dp[2 * nt2], g0, g1, g2, g3, b0, b1);
+        mma16816(dp[2 * nt2 + 1], g0, g1, g2, g3, b2, b3);
+      }
+    }
+    const int key0 = kt * BKV + 2 * (lane & 3);
+#pragma unroll
+    for (int nt = 0; nt < BKV / 8; ++nt) {
+      const int kidx = key0 + nt * 8;
+      const bool v0 = kidx < p.N, v1 = kidx + 1 < p.N;
+      const float p00 = v0 ? exp2f(s[nt][0] * sc - lse0) : 0.f;
+      const float p01 = v1 ? exp2f(s[nt][1] * sc - lse0) : 0.f;
+      const float p10 = v0 ? exp2f(s[nt][2] * sc - lse1) : 0.f;
+      const float p11 = v1 ? exp2f(s[nt][3] * sc - lse1) : 0.f;
+      s[nt][0] = p00 * (dp[nt][0] - del0);
+      s[nt][1] = p01 * (dp[nt][1] - del0);
+      s[nt][2] = p10 * (dp[nt][2] - del1);
+      s[nt][3] = p11 * (dp[nt][3] - del1);
+    }
+    // dQ += dS K
+#pragma unroll
+    for (int j = 0; j < BKV / 16; ++j) {
+      const uint32_t a0 = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+      const uint32_t a1 = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+      const uint32_t a2 = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      const uint32_t a3 = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+      for (int dt2 = 0; dt2 < DH / 16; ++dt2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(tile_addr<DH>(sK, j * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dt2 * 2 + (lane >> 4)), b0, b1, b2, b3);
+        mma16816(dq[2 * dt2], a0, a1, a2, a3, b0, b1);
+        mma16816(dq[2 * dt2 + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    group_sync<INDEP>();
+  }
+  __nv_bfloat16* gdq = p.dq + qoff;
+#pragma unroll
+  for (int nt = 0; nt < DH / 8; ++nt) {
+    const int col = nt * 8 + 2 * (lane & 3);
+    if (r0 < p.N) *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * p.qkv_rs + col) = pack_bf16x2(dq[nt][0] * p.scale, dq[nt][1] * p.scale);
+    if (r1 < p.N) *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * p.qkv_rs + col) = pack_bf16x2(dq[nt][2] * p.scale, dq[nt][3] * p.scale);
+  }
+}
+
+// ================================================================================================
+// Backward, part 2: dK, dV. Each warp owns 16 key rows and sweeps the query tiles with the transposed products
+// S^T = K Q^T and dP^T = V dO^T so P^T / dS^T land directly in A-operand registers. SPLIT > 1 divides the dh output
+// columns of the two accumulators across gridDim (register budget at dh = 192 / 256).
+// ================================================================================================
+template <int DH, int NWARPS, int BQ, int SPLIT, bool INDEP>
+__global__ void __launch_bounds__(NWARPS * 32) attn_bwd_dkv_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  constexpr int BKVT = INDEP ? 16 : 16 * NWARPS;
+  constexpr int DHS = DH / SPLIT;
+  constexpr int kKVBytes = BKVT * DH * 2;
+  constexpr int kQBytes = BQ * DH * 2;
+  constexpr int kPerGroup = 2 * kKVBytes + 2 * kQBytes + 2 * BQ * 4;  // K, V, Q, dO, lse, delta
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = INDEP ? lane : threadIdx.x;
+  constexpr int nthr = INDEP ? 32 : NWARPS * 32;
+  const int wk = INDEP ? 0 : warp;
+  long long bh;
+  int k_tile, split;
+  if (INDEP) {
+    const long long unit = (long long)blockIdx.x * NWARPS + warp;
+    bh = unit / SPLIT;
+    split = (int)(unit % SPLIT);
+    k_tile = 0;
+    if (bh >= (long long)p.B * p.H) return;
+  } else {
+    bh = (long long)blockIdx.z * p.H + blockIdx.y;
+    k_tile = blockIdx.x / SPLIT;
+    split = blockIdx.x % SPLIT;
+  }
+  const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+  uint8_t* sgen = smem_attn + (INDEP ? warp * kPerGroup : 0);
+  const uint32_t sbase = smem_u32(sgen);
+  const uint32_t sK = sbase, sV = sbase + kKVBytes, sQ = sV + kKVBytes, sdO = sQ + kQBytes;
+  float* s_lse = reinterpret_cast<float*>(sgen + 2 * kKVBytes + 2 * kQBytes);
+  float* s_del = s_lse + BQ;
+  const long long qoff = (long long)b * p.qkv_bs + (long long)h * p.qkv_hs;
+  const long long ooff = (long long)b * p.o_bs + (long long)h * p.o_hs;
+  const int k0 = k_tile * BKVT;
+  const int nqt = (p.N + BQ - 1) / BQ;
+  const float* glse = p.lse + bh * p.N;
+  const float* gdel = p.delta + bh * p.N;
+  const float sc = p.scale * kLog2e;
+
+  load_tile<DH, BKVT>(sK, p.k + qoff, p.qkv_rs, k0, p.N, tid, nthr);
+  load_tile<DH, BKVT>(sV, p.v + qoff, p.qkv_rs, k0, p.N, tid, nthr);
+  cp_async_commit();
+
+  float dk[DHS / 8][4], dv[DHS / 8][4];
+#pragma unroll
+  for (int i = 0; i < DHS / 8; ++i) {
+    dk[i][0] = 0.f; dk[i][1] = 0.f; dk[i][2] = 0.f; dk[i][3] = 0.f;
+    dv[i][0] = 0.f; dv[i][1] = 0.f; dv[i][2] = 0.f; dv[i][3] = 0.f;
+  }
+
+  for (int qt = 0; qt < nqt; ++qt) {
+    load_tile<DH, BQ>(sQ, p.q + qoff, p.qkv_rs, qt * BQ, p.N, tid, nthr);
+    load_tile<DH, BQ>(sdO, p.dout + ooff, p.o_rs, qt * BQ, p.N, tid, nthr);
+    cp_async_commit();
+    for (int i = tid; i < BQ; i += nthr) {
+      const int qi = qt * BQ + i;
+      s_lse[i] = qi < p.N ? glse[qi] * kLog2e : INFINITY;
+      s_del[i] = qi < p.N ? gdel[qi] : 0.f;
+    }
+    cp_async_wait<0>();
+    group_sync<INDEP>();
+
+    float st[BQ / 8][4], dpt[BQ / 8][4];
+#pragma unroll
+    for (int i = 0; i < BQ / 8; ++i) {
+      st[i][0] = 0.f; st[i][1] = 0.f; st[i][2] = 0.f; st[i][3] = 0.f;
+      dpt[i][0] = 0.f; dpt[i][1] = 0.f; dpt[i][2] = 0.f; dpt[i][3] = 0.f;
+    }
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) {
+      uint32_t a0, a1, a2, a3, g0, g1, g2, g3;
+      ldsm_x4(tile_addr<DH>(sK, wk * 16 + (lane & 15), ks * 2 + (lane >> 4)), a0, a1, a2, a3);
+      ldsm_x4(tile_addr<DH>(sV, wk * 16 + (lane & 15), ks * 2 + (lane >> 4)), g0, g1, g2, g3);
+#pragma unroll
+      for (int nt2 = 0; nt2 < BQ / 16; ++nt2) {
+        uint32_t b0, b1, b2, b3;
+        const int qrow = nt2 * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int qch = ks * 2 + ((lane >> 3) & 1);
+        ldsm_x4(tile_addr<DH>(sQ, qrow, qch), b0, b1, b2, b3);
+        mma16816(st[2 * nt2], a0, a1, a2, a3, b0, b1);
+        mma16816(st[2 * nt2 + 1], a0, a1, a2, a3, b2, b3);
+        ldsm_x4(tile_addr<DH>(sdO, qrow, qch), b0, b1, b2, b3);
+        mma16816(dpt[2 * nt2], g0, g1, g2, g3, b0, b1);
+        mma16816(dpt[2 * nt2 + 1], g0, g1, g2, g3, b2, b3);
+      }
+    }
+    // P^T and dS^T (rows = keys, columns = queries). Padded queries have lse = +inf -> P = 0.
+#pragma unroll
+    for (int nt = 0; nt < BQ / 8; ++nt) {
+      const int qc = nt * 8 + 2 * (lane & 3);
+      const float l0 = s_lse[qc], l1 = s_lse[qc + 1];
+      const float d0 = s_del[qc], d1 = s_del[qc + 1];
+      const float p00 = exp2f(st[nt][0] * sc - l0);
+      const float p01 = exp2f(st[nt][1] * sc - l1);
+      const float p10 = exp2f(st[nt][2] * sc - l0);
+      const float p11 = exp2f(st[nt][3] * sc - l1);
+      st[nt][0] = p00; st[nt][1] = p01; st[nt][2] = p10; st[nt][3] = p11;
+      dpt[nt][0] = p00 * (dpt[nt][0] - d0);
+      dpt[nt][1] = p01 * (dpt[nt][1] - d1);
+      dpt[nt][2] = p10 * (dpt[nt][2] - d0);
+      dpt[nt][3] = p11 * (dpt[nt][3] - d1);
+    }
+    // dV += P^T dO ; dK += dS^T Q   (B operands: [k = queries][n = dh] row-major -> ldmatrix.trans)
+#pragma unroll
+    for (int j = 0; j < BQ / 16; ++j) {
+      const uint32_t pa0 = pack_bf16x2(st[2 * j][0], st[2 * j][1]);
+      const uint32_t pa1 = pack_bf16x2(st[2 * j][2], st[2 * j][3]);
+      const uint32_t pa2 = pack_bf16x2(st[2 * j + 1][0], st[2 * j + 1][1]);
+      const uint32_t pa3 = pack_bf16x2(st[2 * j + 1][2], st[2 * j + 1][3]);
+      const uint32_t sa0 = pack_bf16x2(dpt[2 * j][0], dpt[2 * j][1]);
+      const uint32_t sa1 = pack_bf16x2(dpt[2 * j][2], dpt[2 * j][3]);
+      const uint32_t sa2 = pack_bf16x2(dpt[2 * j + 1][0], dpt[2 * j + 1][1]);
+      const uint32_t sa3 = pack_bf16x2(dpt[2 * j + 1][2], dpt[2 * j + 1][3]);
+      const int qrow = j * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+#pragma unroll
+      for (int dt2 = 0; dt2 < DHS / 16; ++dt2) {
+        uint32_t b0, b1, b2, b3;
+        const int ch = split * (DHS / 8) + dt2 * 2 + (lane >> 4);
+        ldsm_x4_t(tile_addr<DH>(sdO, qrow, ch), b0, b1, b2, b3);
+        mma16816(dv[2 * dt2], pa0, pa1, pa2, pa3, b0, b1);
+        mma16816(dv[2 * dt2 + 1], pa0, pa1, pa2, pa3, b2, b3);
+        ldsm_x4_t(tile_addr<DH>(sQ, qrow, ch), b0, b1, b2, b3);
+        mma16816(dk[2 * dt2], sa0, sa1, sa2, sa3, b0, b1);
+        mma16816(dk[2 * dt2 + 1], sa0, sa1, sa2, sa3, b2, b3);
+      }
+    }
+    group_sync<INDEP>();
+  }
+  const int r0 = k0 + wk * 16 + (lane >> 2), r1 = r0 + 8;
+  __nv_bfloat16* gdk = p.dk + qoff;
+  __nv_bfloat16* gdv = p.dv + qoff;
+#pragma unroll
+  for (int nt = 0; nt < DHS / 8; ++nt) {
+    const int col = split * DHS + nt * 8 + 2 * (lane & 3);
+    if (r0 < p.N) {
+      *reinterpret_cast<uint32_t*>(gdk + (long long)r0 * p.qkv_rs + col) = pack_bf16x2(dk[nt][0] * p.scale, dk[nt][1] * p.scale);
+      *reinterpret_cast<uint32_t*>(gdv + (long long)r0 * p.qkv_rs + col) = pack_bf16x2(dv[nt][0], dv[nt][1]);
+    }
+    if (r1 < p.N) {
+      *reinterpret_cast<uint32_t*>(gdk + (long long)r1 * p.qkv_rs + col) = pack_bf16x2(dk[nt][2] * p.scale, dk[nt][3] * p.scale);
+      *reinterpret_cast<uint32_t*>(gdv + (long long)r1 * p.qkv_rs + col) = pack_bf16x2(dv[nt][2], dv[nt][3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host dispatch
+// ------------------------------------------------------------------------------------------------
+static int check_attn(const AttnParams& p, int DH) {
+  if (p.B <= 0 || p.H <= 0 || p.N <= 0) return S3D_ERR_BAD_SHAPE;
+  if (DH != 64 && DH != 192 && DH != 256) return S3D_ERR_UNSUPPORTED;
+  if (p.qkv_rs % 8 || p.qkv_hs % 8 || p.qkv_bs % 8 || p.o_rs % 8 || p.o_hs % 8 || p.o_bs % 8) return S3D_ERR_ALIGNMENT;
+  return S3D_OK;
+}
+
+template <typename K>
+static int set_smem(K kern, int bytes) {
+  S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return S3D_OK;
+}
+
+template <int DH>
+static int attn_fwd_dh(const AttnParams& p, cudaStream_t stream) {
+  const long long BH = (long long)p.B * p.H;
+  if (p.N <= 16) {
+    constexpr int NW = 4, BKV = 16;
+    constexpr int smem = NW * (16 * DH * 2 + 2 * BKV * DH * 2);
+    auto kern = attn_fwd_kernel<DH, NW, BKV, true>;
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    kern<<<(unsigned)((BH + NW - 1) / NW), NW * 32, smem, stream>>>(p);
+  } else if (p.N <= 32) {
+    constexpr int NW = 2, BKV = 32;
+    constexpr int smem = 32 * DH * 2 + 4 * BKV * DH * 2;
+    auto kern = attn_fwd_kernel<DH, NW, BKV, false>;
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    if (p.B > 65535) return S3D_ERR_BAD_SHAPE;
+    kern<<<dim3(1, p.H, p.B), NW * 32, smem, stream>>>(p);
+  } else {
+    constexpr int NW = 4, BKV = (DH == 64) ? 64 : 32;
+    constexpr int smem = 64 * DH * 2 + 4 * BKV * DH * 2;
+    auto kern = attn_fwd_kernel<DH, NW, BKV, false>;
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    if (p.B > 65535) return S3D_ERR_BAD_SHAPE;
+    kern<<<dim3((p.N + 63) / 64, p.H, p.B), NW * 32, smem, stream>>>(p);
+  }
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+template <int DH>
+static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
+  const long long BH = (long long)p.B * p.H;
+  {
+    const long long rows = BH * p.N;
+    attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(p, DH);
+    S3D_LAUNCH_OK();
+  }
+  constexpr int SPLIT = (DH == 64) ? 1 : 2;
+  if (p.N <= 16) {
+    constexpr int NW = (DH == 64) ? 4 : 2, BKV = 16;
+    {
+      constexpr int smem = NW * (2 * 16 * DH * 2 + 2 * BKV * DH * 2);
+      auto kern = attn_bwd_dq_kernel<DH, NW, BKV, true>;
+      int rc = set_smem(kern, smem);
+      if (rc) return rc;
+      kern<<<(unsigned)((BH + NW - 1) / NW), NW * 32, smem, stream>>>(p);
+      S3D_LAUNCH_OK();
+    }
+    {
+      constexpr int BQ = 16;
+      constexpr int smem = NW * (2 * 16 * DH * 2 + 2 * BQ * DH * 2 + 2 * BQ * 4);
+      auto kern = attn_bwd_dkv_kernel<DH, NW, BQ, SPLIT, true>;
+      int rc = set_smem(kern, smem);
+      if (rc) return rc;
+      kern<<<(unsigned)((BH * SPLIT + NW - 1) / NW), NW * 32, smem, stream>>>(p);
+      S3D_LAUNCH_OK();
+    }
+  } else if (p.N <= 32) {
+    constexpr int NW = 2, BKV = 32;
+    if (p.B > 65535) return S3D_ERR_BAD_SHAPE;
+    {
+      constexpr int smem = 2 * 32 * DH * 2 + 2 * BKV * DH * 2;
+      auto kern = attn_bwd_dq_kernel<DH, NW, BKV, false>;
+      int rc = set_smem(kern, smem);
+      if (rc) return rc;
+      kern<<<dim3(1, p.H, p.B), NW * 32, smem, stream>>>(p);
+      S3D_LAUNCH_OK();
+    }
+    {
+      constexpr int BQ = 32;
+      constexpr int smem = 2 * 32 * DH * 2 + 2 * BQ * DH * 2 + 2 * BQ * 4;
+      auto kern = attn_bwd_dkv_kernel<DH, NW, BQ, SPLIT, false>;
+      int rc = set_smem(kern, smem);
+      if (rc) return rc;
+      kern<<<dim3(SPLIT, p.H, p.B), NW * 32, smem, stream>>>(p);
+      S3D_LAUNCH_OK();
+    }
+  } else {
+    constexpr int NW = 4;
+    if (p.B > 65535) return S3D_ERR_BAD_SHAPE;
+    {
+      constexpr int BKV = (DH == 64) ? 64 : 32;
+      constexpr int smem = 2 * 64 * DH * 2 + 2 * BKV * DH * 2;
+      auto kern = attn_bwd_dq_kernel<DH, NW, BKV, false>;
+      int rc = set_smem(kern, smem);
+      if (rc) return rc;
+      kern<<<dim3((p.N + 63) / 64, p.H, p.B), NW * 32, smem, stream>>>(p);
+      S3D_LAUNCH_OK();
+    }
+    {
+      constexpr int BQ = (DH == 64) ? 64 : 32;
+      constexpr int smem = 2 * 64 * DH * 2 + 2 * BQ * DH * 2 + 2 * BQ * 4;
+      auto kern = attn_bwd_dkv_kernel<DH, NW, BQ, SPLIT, false>;
+      int rc = set_smem(kern, smem);
+      if (rc) return rc;
+      kern<<<dim3(((p.N + 63) / 64) * SPLIT, p.H, p.B), NW * 32, smem, stream>>>(p);
+      S3D_LAUNCH_OK();
+    }
+  }
+  return S3D_OK;
+}
+
+int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream) {
+  int rc = check_attn(p, DH);
+  if (rc) return rc;
+  if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.out == nullptr) return S3D_ERR_NULL;
+  switch (DH) {
+    case 64: return attn_fwd_dh<64>(p, stream);
+    case 192: return attn_fwd_dh<192>(p, stream);
+    default: return attn_fwd_dh<256>(p, stream);
+  }
+}
+
+int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream) {
+  int rc = check_attn(p, DH);
+  if (rc) return rc;
+  if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.o == nullptr || p.dout == nullptr || p.dq == nullptr ||
+      p.dk == nullptr || p.dv == nullptr || p.lse == nullptr || p.delta == nullptr)
+    return S3D_ERR_NULL;
+  switch (DH) {
+    case 64: return attn_bwd_dh<64>(p, stream);
+    case 192: return attn_bwd_dh<192>(p, stream);
+    default: return attn_bwd_dh<256>(p, stream);
+  }
+}
+
+}  // namespace s3d

@@ -1,0 +1,81 @@
+// Internal declarations shared by the translation units of libs3d_b200.so (not part of the public ABI).
+#pragma once
+#include "common.cuh"
+
+namespace s3d {
+// gemm_tcgen05.cu
+enum : int { EPI_NONE = 0, EPI_GELU = 1, EPI_DGELU = 2 };
+struct GemmParams {
+  int M, N, K;
+  void* D;
+  long long ldd;
+  int out_fp32;
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  const __nv_bfloat16* aux_in;
+  long long ld_aux_in;
+  __nv_bfloat16* aux_out;
+  long long ld_aux_out;
+  int epilogue;
+  float alpha;
+  long long batch_stride_d, batch_stride_r;
+  int batched;
+  // UMMA smem-descriptor byte offsets (defaults: MN-major LBO 8192 / SBO 1024, K-major LBO 16 / SBO 1024);
+  // overridable through S3D_DBG_* environment variables for bring-up on new silicon.
+  unsigned mn_lbo, mn_sbo, k_lbo, k_sbo;
+};
+struct GemmArgs {
+  const void* A;
+  const void* B;
+  long long lda, ldb;
+  int a_mn, b_mn;
+  int batch;
+  long long batch_stride_a, batch_stride_b;
+  int force_bn;
+  GemmParams p;
+};
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+
+// norm_elementwise.cu
+int layernorm_fwd(const float* x, const float* addend, float* sum_out, const float* gamma, const float* beta,
+                  void* y_bf16, float* y_f32, float* mean, float* rstd, int T, int D, float eps, cudaStream_t stream);
+int layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,
+                  const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T,
+                  int D, cudaStream_t stream);
+int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
+int transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int C, long long ld_in, long long ld_out,
+                      cudaStream_t stream);
+int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accumulate, cudaStream_t stream);
+int voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
+                       cudaStream_t stream);
+int adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
+              float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);
+
+// attention_mma.cu
+struct AttnParams {
+  const __nv_bfloat16 *q, *k, *v;
+  const __nv_bfloat16 *o, *dout;
+  __nv_bfloat16* out;
+  __nv_bfloat16 *dq, *dk, *dv;
+  float* lse;
+  float* delta;
+  long long qkv_bs, qkv_hs, qkv_rs;
+  long long o_bs, o_hs, o_rs;
+  int B, H, N;
+  float scale;
+};
+int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream);
+int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream);
+
+// pointops.cu
+int knn(const float* xyz, const float* query, long long* idx, float* dist, int B, int N, int S, int K,
+        cudaStream_t stream);
+int ball_query(const float* xyz, const float* query, long long* idx, int B, int N, int S, float radius_sq, int nsample,
+               cudaStream_t stream);
+int fps(const float* xyz, const long long* start, long long* out, int B, int N, int npoint, cudaStream_t stream);
+int gather_rows(const float* points, const long long* idx, float* out, int B, int N, int M, int C,
+                cudaStream_t stream);
+int scatter_add_rows(const float* grad_out, const long long* idx, float* grad_points, int B, int N, int M, int C,
+                     cudaStream_t stream);
+}  // namespace s3d

@@ -1,0 +1,486 @@
+// HBM-bound kernels of the encoder hot path: LayerNorm forward/backward (timm Block.norm1/norm2, reference
+// vit_3d_2d_pretrain.py:287 eps=1e-6; nn.TransformerEncoderLayer norms eps=1e-5), fp32->bf16 weight shadowing,
+// bias-gradient column sums, voxel patch gather (Conv3d k=s=cell as a GEMM operand, embed_layer_3d_modality.py:22-24),
+// and the fused Adam step (train_cls_voxel.py:195). All are one-pass, 128-bit vectorised, grid sized to the SM count.
+#include "kernels.h"
+
+namespace s3d {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, the row lives in registers (D <= 1024, D % 4 == 0).
+// x fp32 [T,D] -> y (bf16 and/or fp32), mean/rstd fp32 [T]. Optional fused "x = a + b" prologue (post-norm layers).
+// ------------------------------------------------------------------------------------------------
+template <int VEC_ITERS>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ addend,
+                                                           float* __restrict__ sum_out,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
+                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                           int T, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D >> 2;
+  for (int row = warp; row < T; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    float4 v[VEC_ITERS];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        v[i] = xr[c];
+        if (addend != nullptr) {
+          const float4 a = reinterpret_cast<const float4*>(addend + (size_t)row * D)[c];
+          v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+          if (sum_out != nullptr) reinterpret_cast<float4*>(sum_out + (size_t)row * D)[c] = v[i];
+        }
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      } else {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    s = warp_sum(s);
+    const float mean = s / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / (float)D + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+        const float4 b = reinterpret_cast<const float4*>(beta)[c];
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (y_bf16 != nullptr) {
+          uint2 u;
+          u.x = pack_bf16x2(o.x, o.y);
+          u.y = pack_bf16x2(o.z, o.w);
+          reinterpret_cast<uint2*>(y_bf16 + (size_t)row * D)[c] = u;
+        }
+        if (y_f32 != nullptr) reinterpret_cast<float4*>(y_f32 + (size_t)row * D)[c] = o;
+      }
+    }
+  }
+}
+
+int layernorm_fwd(const float* x, const float* addend, float* sum_out, const float* gamma, const float* beta,
+                  void* y_bf16, float* y_f32, float* mean, float* rstd, int T, int D, float eps, cudaStream_t stream) {
+  if (T <= 0 || D <= 0 || D % 4 != 0 || D > 1024) return S3D_ERR_BAD_SHAPE;
+  if (x == nullptr || gamma == nullptr || beta == nullptr) return S3D_ERR_NULL;
+  const int warps_per_block = 8;
+  long long blocks = ((long long)T + warps_per_block - 1) / warps_per_block;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  const int iters = (D / 4 + 31) / 32;
+  auto yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+#define S3D_LN_FWD(I)                                                                                              \
+  layernorm_fwd_kernel<I><<<(int)blocks, warps_per_block * 32, 0, stream>>>(x, addend, sum_out, gamma, beta, yb, \
+                                                                            y_f32, mean, rstd, T, D, eps)
+  switch (iters) {
+    case 1: S3D_LN_FWD(1); break;
+    case 2: S3D_LN_FWD(2); break;
+    case 3: S3D_LN_FWD(3); break;
+    case 4: S3D_LN_FWD(4); break;
+    case 5: S3D_LN_FWD(5); break;
+    case 6: S3D_LN_FWD(6); break;
+    case 7: S3D_LN_FWD(7); break;
+    default: S3D_LN_FWD(8); break;
+  }
+#undef S3D_LN_FWD
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward. dy (bf16 or fp32) is the gradient w.r.t. the LN output; `dres` (optional, fp32) is the
+// gradient arriving through the residual branch and is added to dx. Writes dx fp32 and (optionally) a bf16 copy
+// that feeds the next tensor-core GEMM. dgamma/dbeta are accumulated with one atomicAdd per CTA per column.
+// ------------------------------------------------------------------------------------------------
+template <int VEC_ITERS, bool DY_BF16>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ mean_in,
+                                                           const float* __restrict__ rstd_in,
+                                                           const float* __restrict__ dres, float* __restrict__ dx,
+                                                           __nv_bfloat16* __restrict__ dx_bf16,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int T,
+                                                           int D) {
+  extern __shared__ float red[];  // [2][D]
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D >> 2;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+
+  float4 acc_g[VEC_ITERS], acc_b[VEC_ITERS];
+#pragma unroll
+  for (int i = 0; i < VEC_ITERS; ++i) {
+    acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = warp; row < T; row += nwarps) {
+    const float mean = mean_in[row];
+    const float rstd = rstd_in[row];
+    float4 xh[VEC_ITERS], gy[VEC_ITERS];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 xv = reinterpret_cast<const float4*>(x + (size_t)row * D)[c];
+        float4 dyv;
+        if (DY_BF16) {
+          const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + (size_t)row * D)[c];
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+          dyv = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+          dyv = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * D)[c];
+        }
+        const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        gy[i] = make_float4(dyv.x * g.x, dyv.y * g.y, dyv.z * g.z, dyv.w * g.w);
+        s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+        s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+        acc_g[i].x += dyv.x * xh[i].x; acc_g[i].y += dyv.y * xh[i].y;
+        acc_g[i].z += dyv.z * xh[i].z; acc_g[i].w += dyv.w * xh[i].w;
+        acc_b[i].x += dyv.x; acc_b[i].y += dyv.y; acc_b[i].z += dyv.z; acc_b[i].w += dyv.w;
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float4 o;
+        o.x = rstd * (gy[i].x - s1 - xh[i].x * s2);
+        o.y = rstd * (gy[i].y - s1 - xh[i].y * s2);
+        o.z = rstd * (gy[i].z - s1 - xh[i].z * s2);
+        o.w = rstd * (gy[i].w - s1 - xh[i].w * s2);
+        if (dres != nullptr) {
+          const float4 r = reinterpret_cast<const float4*>(dres + (size_t)row * D)[c];
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        reinterpret_cast<float4*>(dx + (size_t)row * D)[c] = o;
+        if (dx_bf16 != nullptr) {
+          uint2 u;
+          u.x = pack_bf16x2(o.x, o.y);
+          u.y = pack_bf16x2(o.z, o.w);
+          reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * D)[c] = u;
+        }
+      }
+    }
+  }
+  // CTA-level reduction of the parameter gradients, then one atomic per column per CTA.
+  if (dgamma != nullptr) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      if (w == warp_in_block) {
+#pragma unroll
+        for (int i = 0; i < VEC_ITERS; ++i) {
+          const int c = lane + 32 * i;
+          if (c < nvec) {
+            float* rg = red + 4 * c;
+            float* rb = red + D + 4 * c;
+            rg[0] += acc_g[i].x; rg[1] += acc_g[i].y; rg[2] += acc_g[i].z; rg[3] += acc_g[i].w;
+            rb[0] += acc_b[i].x; rb[1] += acc_b[i].y; rb[2] += acc_b[i].z; rb[3] += acc_b[i].w;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      atomicAdd(dgamma + i, red[i]);
+      atomicAdd(dbeta + i, red[D + i]);
+    }
+  }
+}
+
+int layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,
+                  const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T,
+                  int D, cudaStream_t stream) {
+  if (T <= 0 || D <= 0 || D % 4 != 0 || D > 1024) return S3D_ERR_BAD_SHAPE;
+  if (dy == nullptr || x == nullptr || gamma == nullptr || mean == nullptr || rstd == nullptr || dx == nullptr)
+    return S3D_ERR_NULL;
+  const int warps_per_block = 8;
+  long long blocks = ((long long)T + warps_per_block - 1) / warps_per_block;
+  const long long cap = (long long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  const int iters = (D / 4 + 31) / 32;
+  const size_t shmem = 2 * (size_t)D * sizeof(float);
+  auto dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+#define S3D_LN_BWD(I)                                                                                                 \
+  do {                                                                                                                \
+    if (dy_is_bf16)                                                                                                   \
+      layernorm_bwd_kernel<I, true><<<(int)blocks, warps_per_block * 32, shmem, stream>>>(dy, x, gamma, mean, rstd,  \
+                                                                                          dres, dx, dxb, dgamma,      \
+                                                                                          dbeta, T, D);               \
+    else                                                                                                              \
+      layernorm_bwd_kernel<I, false><<<(int)blocks, warps_per_block * 32, shmem, stream>>>(dy, x, gamma, mean, rstd, \
+                                                                                           dres, dx, dxb, dgamma,     \
+                                                                                           dbeta, T, D);              \
+  } while (0)
+  switch (iters) {
+    case 1: S3D_LN_BWD(1); break;
+    case 2: S3D_LN_BWD(2); break;
+    case 3: S3D_LN_BWD(3); break;
+    case 4: S3D_LN_BWD(4); break;
+    case 5: S3D_LN_BWD(5); break;
+    case 6: S3D_LN_BWD(6); break;
+    case 7: S3D_LN_BWD(7); break;
+    default: S3D_LN_BWD(8); break;
+  }
+#undef S3D_LN_BWD
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (weight shadow copies / activations), with optional transposed copy [C,R] of a [R,C] matrix.
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = u;
+  }
+}
+__global__ void cast_bf16_tail_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t start,
+                                      size_t n) {
+  const size_t i = start + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+
+int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
+  if (n <= 0) return S3D_ERR_BAD_SHAPE;
+  if (in == nullptr || out == nullptr) return S3D_ERR_NULL;
+  auto o = reinterpret_cast<__nv_bfloat16*>(out);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+  const size_t n4 = aligned ? (size_t)n / 4 : 0;
+  if (n4 > 0) {
+    size_t blocks = (n4 + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    cast_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, o, n4);
+    S3D_LAUNCH_OK();
+  }
+  const size_t done = n4 * 4;
+  if (done < (size_t)n) {
+    const size_t rem = (size_t)n - done;
+    cast_bf16_tail_kernel<<<(int)((rem + 255) / 256), 256, 0, stream>>>(in, o, done, (size_t)n);
+    S3D_LAUNCH_OK();
+  }
+  return S3D_OK;
+}
+
+// out[c, r] = bf16(in[r, c]);  32x32 smem tiles, coalesced on both sides.
+template <typename TIn>
+__global__ void transpose_to_bf16_kernel(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C,
+                                         long long ld_in, long long ld_out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[j][threadIdx.x] = (float)in[(size_t)r * ld_in + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[(size_t)c * ld_out + r] = __float2bfloat16(tile[threadIdx.x][j]);
+  }
+}
+
+int transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int C, long long ld_in, long long ld_out,
+                      cudaStream_t stream) {
+  if (R <= 0 || C <= 0) return S3D_ERR_BAD_SHAPE;
+  if (in == nullptr || out == nullptr) return S3D_ERR_NULL;
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  if (grid.y > 65535) return S3D_ERR_BAD_SHAPE;
+  if (in_is_bf16)
+    transpose_to_bf16_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                                        reinterpret_cast<__nv_bfloat16*>(out), R, C,
+                                                                        ld_in, ld_out);
+  else
+    transpose_to_bf16_kernel<float><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(in),
+                                                                reinterpret_cast<__nv_bfloat16*>(out), R, C, ld_in,
+                                                                ld_out);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums of a bf16 [T, C] matrix into fp32 [C] (Linear bias gradients). out must be zeroed by the caller
+// when accumulate == 0 is requested we zero it here. Each CTA covers 64 columns x a row slab; atomics per CTA.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
+                                                         int T, int C, long long ld, int rows_per_block) {
+  // blockDim = (32 column-pairs, 8 row lanes)
+  __shared__ float red[8][64];
+  const int c = blockIdx.x * 64 + threadIdx.x * 2;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(T, r_begin + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(in + (size_t)r * ld + c);
+      const float2 f = unpack_bf16x2(u);
+      s0 += f.x;
+      s1 += f.y;
+    }
+  }
+  red[threadIdx.y][threadIdx.x * 2] = s0;
+  red[threadIdx.y][threadIdx.x * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a += red[j][threadIdx.x * 2];
+      b += red[j][threadIdx.x * 2 + 1];
+    }
+    if (c < C) atomicAdd(out + c, a);
+    if (c + 1 < C) atomicAdd(out + c + 1, b);
+  }
+}
+
+int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accumulate, cudaStream_t stream) {
+  if (T <= 0 || C <= 0 || C % 2 != 0 || ld % 2 != 0) return S3D_ERR_BAD_SHAPE;
+  if (in == nullptr || out == nullptr) return S3D_ERR_NULL;
+  if (!accumulate) S3D_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, stream));
+  const int col_blocks = (C + 63) / 64;
+  int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+  if (row_blocks > (T + 63) / 64) row_blocks = (T + 63) / 64;
+  if (row_blocks < 1) row_blocks = 1;
+  const int rows_per_block = (T + row_blocks - 1) / row_blocks;
+  dim3 grid(col_blocks, row_blocks), block(32, 8);
+  colsum_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, T, C, ld,
+                                                 rows_per_block);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Voxel patch gather: x [B,1,V,V,V] fp32 -> P bf16 [B*p*p*(zsum?1:p), Kpad], K = c^3 (zero padded to Kpad).
+// Row order is (b, px, py, pz), column order (dx, dy, dz) = Conv3d weight [D,1,c,c,c] flattened, so the patchify
+// conv (embed_layer_3d_modality.py:22-24) is P @ W^T. With zsum=1 the pz patches of a column are summed first
+// (VoxelEmbed's mean over dim 4, :38, commutes with the linear map; the 1/p factor is applied in the GEMM epilogue).
+// Occupancy values are 0/1 so sums <= p are exact in bf16.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voxel_patch_gather_kernel(const float* __restrict__ x,
+                                                                __nv_bfloat16* __restrict__ P, int B, int V, int c,
+                                                                int p, int Kpad, int zsum) {
+  const int K = c * c * c;
+  const int pz_out = zsum ? 1 : p;
+  const long long rows = (long long)B * p * p * pz_out;
+  const int kp2 = Kpad >> 1;
+  const long long total = rows * kp2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / kp2;
+    const int k = (int)(i % kp2) * 2;
+    long long t = row;
+    const int pz = zsum ? 0 : (int)(t % p);
+    if (!zsum) t /= p;
+    const int py = (int)(t % p);
+    t /= p;
+    const int px = (int)(t % p);
+    const int b = (int)(t / p);
+    float v[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kk = k + e;
+      if (kk < K) {
+        const int dz = kk % c;
+        const int dy = (kk / c) % c;
+        const int dx = kk / (c * c);
+        const size_t base = (((size_t)b * V + (size_t)(px * c + dx)) * V + (size_t)(py * c + dy)) * V;
+        if (zsum) {
+          float s = 0.f;
+          for (int z = 0; z < p; ++z) s += x[base + (size_t)(z * c + dz)];
+          v[e] = s;
+        } else {
+          v[e] = x[base + (size_t)(pz * c + dz)];
+        }
+      }
+    }
+    *reinterpret_cast<uint32_t*>(P + row * Kpad + k) = pack_bf16x2(v[0], v[1]);
+  }
+}
+
+int voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
+                       cudaStream_t stream) {
+  if (B <= 0 || V <= 0 || cell <= 0 || patch <= 0 || patch * cell > V || Kpad < cell * cell * cell || Kpad % 8 != 0)
+    return S3D_ERR_BAD_SHAPE;
+  if (x == nullptr || P == nullptr) return S3D_ERR_NULL;
+  const long long rows = (long long)B * patch * patch * (zsum ? 1 : patch);
+  const long long total = rows * (Kpad / 2);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  voxel_patch_gather_kernel<<<(int)blocks, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(P), B, V, cell,
+                                                             patch, Kpad, zsum);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused Adam (torch.optim.Adam semantics, no amsgrad, L2 weight decay folded into the gradient) over a flat fp32
+// parameter segment; also refreshes the bf16 shadow copy used by the tensor-core GEMMs. grad_scale folds the
+// 1/world_size of the data-parallel gradient average into the same pass.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                  float* __restrict__ m, float* __restrict__ v,
+                                                  __nv_bfloat16* __restrict__ shadow, size_t n, float lr, float beta1,
+                                                  float beta2, float eps, float weight_decay, float bias_corr1,
+                                                  float bias_corr2_sqrt, float grad_scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    if (weight_decay != 0.f) gi += weight_decay * pi;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bias_corr2_sqrt + eps;
+    const float pn = pi - (lr / bias_corr1) * (mi / denom);
+    p[i] = pn;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16(pn);
+  }
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
+              float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream) {
+  if (n <= 0 || step <= 0) return S3D_ERR_BAD_SHAPE;
+  if (p == nullptr || g == nullptr || m == nullptr || v == nullptr) return S3D_ERR_NULL;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  adam_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), (size_t)n,
+                                               lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+}  // namespace s3d

@@ -1,0 +1,361 @@
+"""Bring-up probe: runs each kernel family against plain torch on the GPU and prints max errors.
+Every group runs in its own subprocess (a trapped kernel kills only its own CUDA context).
+
+    python tools/gpu_probe.py            # run all groups
+    python tools/gpu_probe.py gemm_k     # run one group in-process
+"""
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+GROUPS = ["gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
+
+
+def rel_err(a, b):
+    import torch
+    a = a.float()
+    b = b.float()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def report(name, err, tol):
+    print(f"  [{'PASS' if err <= tol else 'FAIL'}] {name}: rel_err={err:.3e} (tol {tol:g})", flush=True)
+
+
+def g_gemm_k():
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(0)
+    for (M, N, K) in [(128, 128, 64), (128, 256, 256), (256, 128, 512), (1664, 1152, 384), (1664, 384, 1536),
+                      (200, 192, 192), (333, 40, 72), (12608, 768, 3072)]:
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        b = torch.randn(N, K, device="cuda").bfloat16()
+        ref = a.float() @ b.float().t()
+        for bn in (64, 128, 256):
+            out = L.gemm(a, b, out_dtype=torch.float32, force_bn=bn)
+            torch.cuda.synchronize()
+            report(f"gemm K-major M{M} N{N} K{K} BN{bn}", rel_err(out, ref), 2e-3)
+        out = L.gemm(a, b)  # auto BN, bf16 out
+        torch.cuda.synchronize()
+        report(f"gemm K-major M{M} N{N} K{K} auto bf16", rel_err(out, ref), 1e-2)
+
+
+def g_gemm_mn():
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(1)
+    for (M, N, K) in [(128, 128, 64), (256, 256, 256), (1536, 384, 1664), (384, 384, 1000), (192, 576, 333 * 8)]:
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        b = torch.randn(N, K, device="cuda").bfloat16()
+        ref = a.float() @ b.float().t()
+        at = a.t().contiguous()  # [K, M]
+        bt = b.t().contiguous()  # [K, N]
+        for bn in (64, 128, 256):
+            o1 = L.gemm(at, b, a_mn=True, out_dtype=torch.float32, force_bn=bn)
+            o2 = L.gemm(a, bt, b_mn=True, out_dtype=torch.float32, force_bn=bn)
+            o3 = L.gemm(at, bt, a_mn=True, b_mn=True, out_dtype=torch.float32, force_bn=bn)
+            torch.cuda.synchronize()
+            report(f"gemm A-MN     M{M} N{N} K{K} BN{bn}", rel_err(o1, ref), 2e-3)
+            report(f"gemm B-MN     M{M} N{N} K{K} BN{bn}", rel_err(o2, ref), 2e-3)
+            report(f"gemm A-MN B-MN M{M} N{N} K{K} BN{bn}", rel_err(o3, ref), 2e-3)
+
+
+def g_gemm_epi():
+    import torch
+    import torch.nn.functional as F
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(2)
+    M, N, K = 1664, 1536, 384
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    acc = a.float() @ b.float().t()
+    out = L.gemm(a, b, bias=bias, out_dtype=torch.float32)
+    report("bias", rel_err(out, acc + bias), 2e-3)
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out = L.gemm(a, b, bias=bias, epilogue=L.EPI_GELU, aux_out=pre)
+    report("bias+gelu", rel_err(out, F.gelu(acc + bias)), 1e-2)
+    report("bias+gelu preact", rel_err(pre, acc + bias), 1e-2)
+    out = L.gemm(a, b, bias=bias, residual=res, out_dtype=torch.float32)
+    report("bias+residual", rel_err(out, acc + bias + res), 2e-3)
+    out = L.gemm(a, b, alpha=0.2, out_dtype=torch.float32)
+    report("alpha", rel_err(out, 0.2 * acc), 2e-3)
+    x = torch.randn(M, N, device="cuda").bfloat16()
+    xr = x.float().requires_grad_(True)
+    F.gelu(xr).sum().backward()
+    out = L.gemm(a, b, epilogue=L.EPI_DGELU, aux_in=x, out_dtype=torch.float32)
+    report("dgelu", rel_err(out, acc * xr.grad), 5e-3)
+    acc_buf = res.clone()
+    L.gemm(a, b, residual=acc_buf, out=acc_buf)
+    report("accumulate in place", rel_err(acc_buf, acc + res), 2e-3)
+    # N tail with vector epilogue disabled (N=40 head-like), M tail
+    M, N, K = 77, 40, 384
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out = L.gemm(a, b, bias=bias, out_dtype=torch.float32)
+    report("tails M77 N40", rel_err(out, a.float() @ b.float().t() + bias), 2e-3)
+
+
+def g_gemm_batched():
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(3)
+    Bn, M, N, K = 6, 300, 200, 192
+    a = torch.randn(Bn, M, K, device="cuda").bfloat16()
+    b = torch.randn(Bn, N, K, device="cuda").bfloat16()
+    out = L.gemm(a, b, out_dtype=torch.float32)
+    report("batched K-major", rel_err(out, torch.bmm(a.float(), b.float().transpose(1, 2))), 2e-3)
+    bt = b.transpose(1, 2).contiguous()
+    out = L.gemm(a, bt, b_mn=True, out_dtype=torch.float32)
+    report("batched B-MN", rel_err(out, torch.bmm(a.float(), b.float().transpose(1, 2))), 2e-3)
+
+
+def g_ln():
+    import torch
+    import torch.nn.functional as F
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(4)
+    for (T, D) in [(1664, 384), (1000, 768), (333, 192), (50, 1024)]:
+        x = torch.randn(T, D, device="cuda") * 2 + 0.5
+        g = torch.randn(D, device="cuda")
+        b = torch.randn(D, device="cuda")
+        y16, y32, _, mean, rstd = L.layernorm_fwd(x, g, b, 1e-6, want_f32=True)
+        ref = F.layer_norm(x, (D,), g, b, 1e-6)
+        report(f"ln fwd f32 T{T} D{D}", rel_err(y32, ref), 1e-5)
+        report(f"ln fwd bf16 T{T} D{D}", rel_err(y16, ref), 1e-2)
+        xr = x.clone().requires_grad_(True)
+        gr = g.clone().requires_grad_(True)
+        br = b.clone().requires_grad_(True)
+        dy = torch.randn(T, D, device="cuda")
+        dres = torch.randn(T, D, device="cuda")
+        F.layer_norm(xr, (D,), gr, br, 1e-6).backward(dy)
+        dx, dx16, dg, db = L.layernorm_bwd(dy, x, g, mean, rstd, dres=dres, want_bf16=True)
+        report(f"ln bwd dx T{T} D{D}", rel_err(dx, xr.grad + dres), 1e-4)
+        report(f"ln bwd dx16 T{T} D{D}", rel_err(dx16, xr.grad + dres), 1e-2)
+        report(f"ln bwd dgamma T{T} D{D}", rel_err(dg, gr.grad), 1e-4)
+        report(f"ln bwd dbeta T{T} D{D}", rel_err(db, br.grad), 1e-4)
+        dx, _, dg, db = L.layernorm_bwd(dy.bfloat16(), x, g, mean, rstd)
+        report(f"ln bwd (bf16 dy) dx T{T} D{D}", rel_err(dx, xr.grad), 1e-2)
+    x = torch.randn(100, 768, device="cuda")
+    a = torch.randn(100, 768, device="cuda")
+    g = torch.ones(768, device="cuda")
+    b = torch.zeros(768, device="cuda")
+    _, y32, s, _, _ = L.layernorm_fwd(x, g, b, 1e-5, addend=a, want_sum=True, want_f32=True)
+    report("ln fwd fused add", rel_err(y32, F.layer_norm(x + a, (768,), g, b, 1e-5)), 1e-5)
+    report("ln fwd fused add sum", rel_err(s, x + a), 1e-6)
+
+
+def _attn_ref(q, k, v, scale):
+    import torch
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    p = s.softmax(-1)
+    return p @ v.float(), torch.logsumexp(s, -1)
+
+
+def _attn_cases():
+    # (B, N, H, dh, layout)
+    return [(3, 15, 3, 256, "timm"), (130, 15, 3, 256, "timm"), (4, 26, 6, 64, "timm"), (2, 197, 3, 256, "timm"),
+            (2, 257, 3, 64, "timm"), (1, 513, 3, 64, "timm"), (2, 16, 3, 64, "timm"), (3, 15, 3, 64, "timm"),
+            (2, 700, 4, 192, "seqfirst"), (15, 392, 4, 192, "seqfirst")]
+
+
+def _make_qkv(B, N, H, dh, layout):
+    import torch
+    E = H * dh
+    if layout == "timm":
+        qkv = (torch.randn(B, N, 3, H, dh, device="cuda")).bfloat16()
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]  # [B,N,H,dh]
+        qs = (N * 3 * E, dh, 3 * E)
+        os_ = (N * E, dh, E)
+        out = torch.empty(B, N, H, dh, device="cuda", dtype=torch.bfloat16)
+        perm = lambda t: t.permute(0, 2, 1, 3)  # -> [B,H,N,dh]
+    else:  # sequence-first [S=N, Nb=B, 3E]
+        qkv = torch.randn(N, B, 3, H, dh, device="cuda").bfloat16()
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]  # [N,B,H,dh]
+        qs = (3 * E, dh, B * 3 * E)
+        os_ = (E, dh, B * E)
+        out = torch.empty(N, B, H, dh, device="cuda", dtype=torch.bfloat16)
+        perm = lambda t: t.permute(1, 2, 0, 3)
+    return qkv, q, k, v, qs, os_, out, perm
+
+
+def g_attn_fwd():
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(5)
+    for (B, N, H, dh, layout) in _attn_cases():
+        qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
+        lse = torch.empty(B, H, N, device="cuda")
+        scale = dh ** -0.5
+        L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale)
+        torch.cuda.synchronize()
+        ro, rl = _attn_ref(perm(q), perm(k), perm(v), scale)
+        report(f"attn fwd out B{B} N{N} H{H} dh{dh} {layout}", rel_err(perm(out), ro), 1.5e-2)
+        report(f"attn fwd lse B{B} N{N} H{H} dh{dh} {layout}", rel_err(lse, rl), 1e-3)
+
+
+def g_attn_bwd():
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(6)
+    for (B, N, H, dh, layout) in _attn_cases():
+        qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
+        lse = torch.empty(B, H, N, device="cuda")
+        delta = torch.empty(B, H, N, device="cuda")
+        scale = dh ** -0.5
+        L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale)
+        dout = torch.randn_like(out.float()).bfloat16()
+        dqkv = torch.zeros_like(qkv)
+        dq, dk, dv = dqkv.select(2, 0), dqkv.select(2, 1), dqkv.select(2, 2)
+        L.attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out, dout, lse, delta, dq.data_ptr(), dk.data_ptr(),
+                   dv.data_ptr(), B, H, N, dh, qs, os_, scale)
+        torch.cuda.synchronize()
+        qr = perm(q).float().detach().requires_grad_(True)
+        kr = perm(k).float().detach().requires_grad_(True)
+        vr = perm(v).float().detach().requires_grad_(True)
+        s = (qr @ kr.transpose(-1, -2)) * scale
+        (s.softmax(-1) @ vr).backward(perm(dout).float())
+        report(f"attn bwd dq B{B} N{N} H{H} dh{dh} {layout}", rel_err(perm(dq), qr.grad), 2e-2)
+        report(f"attn bwd dk B{B} N{N} H{H} dh{dh} {layout}", rel_err(perm(dk), kr.grad), 2e-2)
+        report(f"attn bwd dv B{B} N{N} H{H} dh{dh} {layout}", rel_err(perm(dv), vr.grad), 2e-2)
+
+
+def g_elementwise():
+    import torch
+    import torch.nn.functional as F
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(7)
+    x = torch.randn(1000, 333, device="cuda")
+    report("cast", rel_err(L.cast_bf16(x), x), 5e-3)
+    report("transpose f32", rel_err(L.transpose_bf16(x), x.t()), 5e-3)
+    report("transpose bf16", rel_err(L.transpose_bf16(x.bfloat16()), x.bfloat16().t()), 0)
+    y = torch.randn(5000, 384, device="cuda").bfloat16()
+    report("colsum", rel_err(L.colsum(y), y.float().sum(0)), 1e-5)
+    # voxel patch gather == conv3d
+    for (B, V, c, p, D, zsum) in [(4, 30, 6, 5, 384, True), (2, 128, 9, 14, 768, False), (2, 30, 6, 5, 384, False)]:
+        vox = (torch.rand(B, 1, V, V, V, device="cuda") < 0.1).float()
+        w = torch.randn(D, 1, c, c, c, device="cuda") * 0.05
+        bias = torch.randn(D, device="cuda")
+        K = c ** 3
+        kpad = (K + 63) // 64 * 64
+        P = L.voxel_patch_gather(vox, c, p, kpad, zsum)
+        wp = torch.zeros(D, kpad, device="cuda")
+        wp[:, :K] = w.reshape(D, K)
+        out = L.gemm(P, wp.bfloat16(), bias=bias, alpha=(1.0 / p) if zsum else 1.0, out_dtype=torch.float32)
+        ref = F.conv3d(vox, w.bfloat16().float(), bias, stride=c)
+        if zsum:
+            ref = ref.mean(4).flatten(2).transpose(1, 2).reshape(-1, D)
+        else:
+            ref = ref.flatten(2).transpose(1, 2).reshape(-1, D)
+        report(f"patchify V{V} c{c} p{p} zsum{zsum}", rel_err(out, ref), 2e-3)
+    # adam
+    p0 = torch.randn(10001, device="cuda")
+    g = torch.randn(10001, device="cuda")
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3)
+    m = torch.zeros_like(p0)
+    v = torch.zeros_like(p0)
+    pm = p0.clone()
+    sh = torch.empty(10001, device="cuda", dtype=torch.bfloat16)
+    for step in (1, 2, 3):
+        pr.grad = g.clone() * step
+        opt.step()
+        L.adam_step(pm, g * step, m, v, sh, 1e-3, 0.9, 0.999, 1e-8, 0.0, step)
+    report("adam 3 steps", rel_err(pm, pr.detach()), 1e-6)
+    report("adam shadow", rel_err(sh, pm), 5e-3)
+
+
+def g_points():
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(8)
+    for (B, N, S, K) in [(4, 1024, 1024, 16), (3, 1024, 256, 16), (2, 2048, 512, 16), (2, 300, 77, 3), (2, 5000, 100, 16)]:
+        xyz = torch.rand(B, N, 3, device="cuda") * 2 - 1
+        q = xyz[:, :S].contiguous() if S <= N else torch.rand(B, S, 3, device="cuda")
+        idx, dist = L.knn(xyz, q, K, want_dist=True)
+        xc, qc = xyz.cpu(), q.cpu()
+        d = torch.sum((qc[:, :, None] - xc[:, None]) ** 2, dim=-1)
+        ds, ref = d.sort(dim=-1, stable=True)
+        ok = torch.equal(idx.cpu(), ref[:, :, :K])
+        okd = torch.equal(dist.cpu(), ds[:, :, :K])
+        print(f"  [{'PASS' if ok and okd else 'FAIL'}] knn B{B} N{N} S{S} K{K}: idx exact={ok} dist exact={okd}", flush=True)
+        r2 = float(torch.tensor(0.2 ** 2, dtype=torch.float32))
+        bq = L.ball_query(r2, 16, xyz, q).cpu()
+        gi = torch.arange(N).view(1, 1, N).repeat(B, S, 1)
+        gi[d > 0.2 ** 2] = N
+        gi = gi.sort(dim=-1)[0][:, :, :16]
+        first = gi[:, :, 0:1].repeat(1, 1, 16)
+        gi[gi == N] = first[gi == N]
+        print(f"  [{'PASS' if torch.equal(bq, gi) else 'FAIL'}] ball_query B{B} N{N} S{S}", flush=True)
+    for (B, N, npoint) in [(4, 1024, 1024), (4, 1024, 256), (2, 2048, 512), (2, 3000, 64), (1, 8000, 32)]:
+        xyz = torch.rand(B, N, 3, device="cuda") * 2 - 1
+        start = torch.randint(0, N, (B,), device="cuda")
+        got = L.fps(xyz, npoint, start).cpu()
+        xc = xyz.cpu()
+        cent = torch.zeros(B, npoint, dtype=torch.long)
+        distance = torch.ones(B, N) * 1e10
+        far = start.cpu().clone()
+        bi = torch.arange(B)
+        for i in range(npoint):
+            cent[:, i] = far
+            c = xc[bi, far, :].view(B, 1, 3)
+            dd = torch.sum((xc - c) ** 2, -1)
+            distance = torch.min(distance, dd)
+            far = torch.max(distance, -1)[1]
+        print(f"  [{'PASS' if torch.equal(got, cent) else 'FAIL'}] fps B{B} N{N} npoint{npoint}", flush=True)
+    pts = torch.randn(3, 100, 51, device="cuda")
+    idx = torch.randint(0, 100, (3, 40, 16), device="cuda")
+    out = L.gather_rows(pts, idx)
+    ref = torch.gather(pts, 1, idx.reshape(3, -1)[..., None].expand(-1, -1, 51))
+    print(f"  [{'PASS' if torch.equal(out, ref) else 'FAIL'}] gather_rows", flush=True)
+    go = torch.randn(3, 640, 51, device="cuda")
+    gp = L.scatter_add_rows(go, idx, 100)
+    refg = torch.zeros(3, 100, 51, device="cuda").scatter_add_(1, idx.reshape(3, -1)[..., None].expand(-1, -1, 51), go)
+    report("scatter_add_rows", rel_err(gp, refg), 1e-5)
+
+
+def main():
+    if len(sys.argv) > 1:
+        name = sys.argv[1]
+        import torch
+        print(f"== {name} on {torch.cuda.get_device_name(0)}", flush=True)
+        globals()["g_" + name]()
+        torch.cuda.synchronize()
+        return
+    def run(g, env_extra=None):
+        t0 = time.time()
+        env = dict(os.environ)
+        env.update(env_extra or {})
+        out = ""
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), g], capture_output=True, text=True,
+                               timeout=300, env=env)
+            out = r.stdout
+            print(out, end="")
+            if r.returncode != 0:
+                out += "FAIL"
+                print(f"  [CRASH] group {g} rc={r.returncode}\n" + r.stderr[-1500:])
+        except subprocess.TimeoutExpired:
+            out += "FAIL"
+            print(f"  [TIMEOUT] group {g}")
+        print(f"  ({g} {env_extra or ''}: {time.time() - t0:.1f}s)", flush=True)
+        return out
+
+    for g in GROUPS:
+        out = run(g)
+        if "FAIL" in out and g == "gemm_mn":
+            # bring-up: try the alternative descriptor offset assignments for MN-major operands
+            for lbo, sbo in [(1024, 8192), (8192, 128), (128, 8192), (1024, 1024)]:
+                run(g, {"S3D_DBG_MN_LBO": str(lbo), "S3D_DBG_MN_SBO": str(sbo)})
+        if "FAIL" in out and g == "gemm_k":
+            for lbo, sbo in [(0, 1024), (1024, 1024), (16, 128)]:
+                run(g, {"S3D_DBG_K_LBO": str(lbo), "S3D_DBG_K_SBO": str(sbo)})
+
+
+if __name__ == "__main__":
+    main()
