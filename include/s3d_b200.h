@@ -36,7 +36,7 @@ enum {
 };
 
 /* epilogues of s3d_gemm_bf16 */
-enum { S3D_EPI_NONE = 0, S3D_EPI_GELU = 1, S3D_EPI_DGELU = 2 };
+enum { S3D_EPI_NONE = 0, S3D_EPI_GELU = 1, S3D_EPI_DGELU = 2, S3D_EPI_RELU = 3, S3D_EPI_DRELU = 4 };
 
 int s3d_abi_version(void);
 const char* s3d_error_string(int code);
@@ -49,7 +49,8 @@ const char* s3d_error_string(int code);
  *   A: a_mn_major == 0 -> [M,K] row-major (lda >= K);  == 1 -> stored [K,M] row-major (lda >= M)
  *   B: b_mn_major == 0 -> [N,K] row-major (ldb >= K);  == 1 -> stored [K,N] row-major (ldb >= N)
  *   epilogue order: v = alpha*acc; v += bias[n]; GELU: (aux_out = bf16(v)), v = gelu_erf(v);
- *                   DGELU: v *= gelu_erf'(aux_in[m,n]); v += residual[m,n]; D = (out_fp32 ? v : bf16(v)).
+ *                   DGELU: v *= gelu_erf'(aux_in[m,n]); RELU: v = max(v,0); DRELU: v = aux_in[m,n] > 0 ? v : 0;
+ *                   v += residual[m,n]; D = (out_fp32 ? v : bf16(v)).
  *   residual may alias D (fp32 accumulate). batch > 1 runs `batch` independent problems with element strides.
  * ------------------------------------------------------------------------------------------------------------- */
 int s3d_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldd,

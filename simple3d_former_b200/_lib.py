@@ -103,7 +103,7 @@ def call(name: str, *args) -> None:
 # ------------------------------------------------------------------------------------------------------------------
 # thin tensor-level wrappers (shape checks + pointer extraction only)
 # ------------------------------------------------------------------------------------------------------------------
-EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_DGELU, EPI_RELU, EPI_DRELU = 0, 1, 2, 3, 4
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, alpha=1.0, bias=None, residual=None,

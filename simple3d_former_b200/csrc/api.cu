@@ -31,7 +31,7 @@ int s3d_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
                   int64_t ldr, int epilogue, const void* aux_in, int64_t ld_aux_in, void* aux_out, int64_t ld_aux_out,
                   int batch, int64_t batch_stride_a, int64_t batch_stride_b, int64_t batch_stride_d,
                   int64_t batch_stride_r, int force_bn, void* stream) {
-  if (epilogue < S3D_EPI_NONE || epilogue > S3D_EPI_DGELU) return S3D_ERR_UNSUPPORTED;
+  if (epilogue < S3D_EPI_NONE || epilogue > S3D_EPI_DRELU) return S3D_ERR_UNSUPPORTED;
   if (batch < 1 || batch > 65535) return S3D_ERR_BAD_SHAPE;
   s3d::GemmArgs g;
   g.A = A;

@@ -231,6 +231,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         }
+        else if (p.epilogue == EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.epilogue == EPI_DRELU) {
+          // aux_in holds the post-ReLU activation: gradient passes where it is > 0
+          if (row_ok) {
+            const __nv_bfloat16* ai = p.aux_in + (long long)row * p.ld_aux_in + n;
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(ai + j);
+                float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+                f[j] = a0.x > 0.f ? f[j] : 0.f;
+                f[j + 1] = a0.y > 0.f ? f[j + 1] : 0.f;
+                f[j + 2] = a1.x > 0.f ? f[j + 2] : 0.f;
+                f[j + 3] = a1.y > 0.f ? f[j + 3] : 0.f;
+                f[j + 4] = a2.x > 0.f ? f[j + 4] : 0.f;
+                f[j + 5] = a2.y > 0.f ? f[j + 5] : 0.f;
+                f[j + 6] = a3.x > 0.f ? f[j + 6] : 0.f;
+                f[j + 7] = a3.y > 0.f ? f[j + 7] : 0.f;
+              }
+            } else {
+              for (int j = 0; j < 32 && n + j < p.N; ++j) f[j] = __bfloat162float(ai[j]) > 0.f ? f[j] : 0.f;
+            }
+          }
+        }
         if (row_ok) {
           if (p.residual != nullptr) {
             const float* r = p.residual + boff_r + (long long)row * p.ldr + n;
@@ -406,7 +432,7 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   const GemmParams& p = g.p;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return S3D_ERR_BAD_SHAPE;
   if (g.A == nullptr || g.B == nullptr || p.D == nullptr) return S3D_ERR_NULL;
-  if (p.epilogue == EPI_DGELU && p.aux_in == nullptr) return S3D_ERR_NULL;
+  if ((p.epilogue == EPI_DGELU || p.epilogue == EPI_DRELU) && p.aux_in == nullptr) return S3D_ERR_NULL;
   // vector epilogue accesses need 16-byte aligned rows
   const long long dmul = p.out_fp32 ? 4 : 8;
   if (p.ldd % dmul != 0 || (reinterpret_cast<uintptr_t>(p.D) & 15) != 0) return S3D_ERR_ALIGNMENT;

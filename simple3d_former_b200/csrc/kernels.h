@@ -4,7 +4,7 @@
 
 namespace s3d {
 // gemm_tcgen05.cu
-enum : int { EPI_NONE = 0, EPI_GELU = 1, EPI_DGELU = 2 };
+enum : int { EPI_NONE = 0, EPI_GELU = 1, EPI_DGELU = 2, EPI_RELU = 3, EPI_DRELU = 4 };
 struct GemmParams {
   int M, N, K;
   void* D;

@@ -1,0 +1,359 @@
+"""torch.autograd.Function wrappers that chain the C-ABI kernels into the fused pieces of the hot path.
+
+Numerics contract: bf16 storage for GEMM/attention operands, fp32 accumulation, fp32 residual stream, fp32 LayerNorm
+statistics and softmax, fp32 parameter gradients. PyTorch only allocates tensors and records the autograd graph here.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+_EPS_BLOCK = 1e-6
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# bf16 weight shadows
+# ----------------------------------------------------------------------------------------------------------------
+def shadow(p: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of an fp32 parameter (2-D+ weights are viewed as [out, -1]).
+
+    If a trainer manages a flat shadow buffer it sets `p._s3d_shadow` (kept fresh by the fused Adam kernel); otherwise
+    the copy is cached per parameter and refreshed when the parameter's version counter or storage changes."""
+    s = getattr(p, "_s3d_shadow", None)
+    if s is not None:
+        return s
+    key = (p._version, p.data_ptr())
+    cache = getattr(p, "_s3d_shadow_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    src = p.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    s16 = L.cast_bf16(src.float() if src.dtype != torch.float32 else src)
+    try:
+        p._s3d_shadow_cache = (key, s16)
+    except Exception:
+        pass
+    return s16
+
+
+def _w2d(w16: torch.Tensor) -> torch.Tensor:
+    return w16.reshape(w16.shape[0], -1)
+
+
+def _attn_strides_timm(N, H, dh):
+    E = H * dh
+    return (N * 3 * E, dh, 3 * E), (N * E, dh, E)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Linear: y = x W^T + b on the tensor cores (used by the stand-alone Attention / Mlp modules)
+# ----------------------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        K = x.shape[-1]
+        x16 = L.cast_bf16(x.reshape(-1, K).contiguous().float())
+        w16 = _w2d(shadow(weight))
+        y = L.gemm(x16, w16, bias=bias, out_dtype=torch.float32)
+        ctx.save_for_backward(x16, weight)
+        ctx.has_bias = bias is not None
+        ctx.in_shape = x.shape
+        return y.reshape(*x.shape[:-1], w16.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, weight = ctx.saved_tensors
+        w16 = _w2d(shadow(weight))
+        dy16 = L.cast_bf16(dy.reshape(-1, dy.shape[-1]).contiguous())
+        dx = L.gemm(dy16, w16, b_mn=True, out_dtype=torch.float32).reshape(ctx.in_shape)
+        dw = L.gemm(dy16, x16, a_mn=True, b_mn=True, out_dtype=torch.float32).reshape(weight.shape)
+        db = L.colsum(dy16) if ctx.has_bias else None
+        return dx, dw, db
+
+
+class MlpFn(torch.autograd.Function):
+    """timm Mlp.forward: fc2(GELU_erf(fc1(x))) with bias+GELU and bias epilogues fused into the two GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, fc1_w, fc1_b, fc2_w, fc2_b):
+        K = x.shape[-1]
+        x16 = L.cast_bf16(x.reshape(-1, K).contiguous().float())
+        w1, w2 = shadow(fc1_w), shadow(fc2_w)
+        pre = torch.empty((x16.shape[0], w1.shape[0]), device=x.device, dtype=torch.bfloat16)
+        a16 = L.gemm(x16, w1, bias=fc1_b, epilogue=L.EPI_GELU, aux_out=pre)
+        y = L.gemm(a16, w2, bias=fc2_b, out_dtype=torch.float32)
+        ctx.save_for_backward(x16, pre, a16, fc1_w, fc2_w)
+        ctx.meta = (x.shape, fc1_b is not None, fc2_b is not None)
+        return y.reshape(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, pre, a16, fc1_w, fc2_w = ctx.saved_tensors
+        in_shape, has_b1, has_b2 = ctx.meta
+        dy16 = L.cast_bf16(dy.reshape(-1, dy.shape[-1]).contiguous())
+        dfc2_w = L.gemm(dy16, a16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dfc2_b = L.colsum(dy16) if has_b2 else None
+        dpre = L.gemm(dy16, shadow(fc2_w), b_mn=True, epilogue=L.EPI_DGELU, aux_in=pre)
+        dfc1_w = L.gemm(dpre, x16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dfc1_b = L.colsum(dpre) if has_b1 else None
+        dx = L.gemm(dpre, shadow(fc1_w), b_mn=True, out_dtype=torch.float32).reshape(in_shape)
+        return dx, dfc1_w, dfc1_b, dfc2_w, dfc2_b
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Attention core on [B, N, 3, H, dh] bf16 (timm layout)
+# ----------------------------------------------------------------------------------------------------------------
+def _attn_core_fwd(qkv16, B, N, H, dh, scale):
+    E = H * dh
+    out = torch.empty((B, N, E), device=qkv16.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, N), device=qkv16.device, dtype=torch.float32)
+    qs, os_ = _attn_strides_timm(N, H, dh)
+    base = qkv16.data_ptr()
+    L.attn_fwd(base, base + 2 * E, base + 4 * E, out, lse, B, H, N, dh, qs, os_, scale)
+    return out, lse
+
+
+def _attn_core_bwd(qkv16, out16, dout16, lse, B, N, H, dh, scale):
+    E = H * dh
+    dqkv = torch.empty_like(qkv16)
+    delta = torch.empty_like(lse)
+    qs, os_ = _attn_strides_timm(N, H, dh)
+    base, dbase = qkv16.data_ptr(), dqkv.data_ptr()
+    L.attn_bwd(base, base + 2 * E, base + 4 * E, out16, dout16, lse, delta, dbase, dbase + 2 * E, dbase + 4 * E, B, H, N,
+               dh, qs, os_, scale)
+    return dqkv
+
+
+class AttentionFn(torch.autograd.Function):
+    """timm Attention.forward as one autograd node: qkv GEMM -> flash attention core -> proj GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, qkv_w, qkv_b, proj_w, proj_b, num_heads, scale):
+        B, N, C = x.shape
+        dh = C // num_heads
+        x16 = L.cast_bf16(x.reshape(B * N, C).contiguous())
+        qkv = L.gemm(x16, shadow(qkv_w), bias=qkv_b)
+        o16, lse = _attn_core_fwd(qkv, B, N, num_heads, dh, scale)
+        y = L.gemm(o16.view(B * N, C), shadow(proj_w), bias=proj_b, out_dtype=torch.float32)
+        ctx.save_for_backward(x16, qkv, o16, lse, qkv_w, proj_w)
+        ctx.meta = (B, N, C, num_heads, dh, scale, qkv_b is not None, proj_b is not None)
+        return y.view(B, N, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, qkv, o16, lse, qkv_w, proj_w = ctx.saved_tensors
+        B, N, C, H, dh, scale, has_qb, has_pb = ctx.meta
+        dy16 = L.cast_bf16(dy.reshape(B * N, C).contiguous())
+        dproj_w = L.gemm(dy16, o16.view(B * N, C), a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dproj_b = L.colsum(dy16) if has_pb else None
+        do16 = L.gemm(dy16, shadow(proj_w), b_mn=True)
+        dqkv = _attn_core_bwd(qkv, o16, do16.view(B, N, C), lse, B, N, H, dh, scale)
+        dqkv_w = L.gemm(dqkv, x16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dqkv_b = L.colsum(dqkv) if has_qb else None
+        dx = L.gemm(dqkv, shadow(qkv_w), b_mn=True, out_dtype=torch.float32).view(B, N, C)
+        return dx, dqkv_w, dqkv_b, dproj_w, dproj_b, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Whole encoder block (timm Block.forward, pre-norm): 7 kernels forward, 17 backward, one autograd node
+# ----------------------------------------------------------------------------------------------------------------
+class BlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, num_heads, scale,
+                eps1, eps2):
+        B, N, D = x.shape
+        T = B * N
+        dh = D // num_heads
+        x = x.contiguous()
+        x2 = x.view(T, D)
+        h16, _, _, mean1, rstd1 = L.layernorm_fwd(x2, n1w, n1b, eps1)
+        qkv = L.gemm(h16, shadow(qkv_w), bias=qkv_b)
+        o16, lse = _attn_core_fwd(qkv, B, N, num_heads, dh, scale)
+        x1 = L.gemm(o16.view(T, D), shadow(proj_w), bias=proj_b, residual=x2, out_dtype=torch.float32)
+        g16, _, _, mean2, rstd2 = L.layernorm_fwd(x1, n2w, n2b, eps2)
+        w1 = shadow(fc1_w)
+        pre = torch.empty((T, w1.shape[0]), device=x.device, dtype=torch.bfloat16)
+        a16 = L.gemm(g16, w1, bias=fc1_b, epilogue=L.EPI_GELU, aux_out=pre)
+        y = L.gemm(a16, shadow(fc2_w), bias=fc2_b, residual=x1, out_dtype=torch.float32)
+        ctx.save_for_backward(x2, mean1, rstd1, h16, qkv, o16, lse, x1, mean2, rstd2, g16, pre, a16, n1w, qkv_w, proj_w,
+                              n2w, fc1_w, fc2_w)
+        ctx.meta = (B, N, D, num_heads, dh, scale, qkv_b is not None, proj_b is not None, fc1_b is not None,
+                    fc2_b is not None)
+        return y.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2, mean1, rstd1, h16, qkv, o16, lse, x1, mean2, rstd2, g16, pre, a16, n1w, qkv_w, proj_w, n2w, fc1_w,
+         fc2_w) = ctx.saved_tensors
+        B, N, D, H, dh, scale, has_qb, has_pb, has_b1, has_b2 = ctx.meta
+        T = B * N
+        dy2 = dy.reshape(T, D).contiguous()
+        dy16 = L.cast_bf16(dy2)
+        # MLP
+        dfc2_w = L.gemm(dy16, a16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dfc2_b = L.colsum(dy16) if has_b2 else None
+        dpre = L.gemm(dy16, shadow(fc2_w), b_mn=True, epilogue=L.EPI_DGELU, aux_in=pre)
+        dfc1_w = L.gemm(dpre, g16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dfc1_b = L.colsum(dpre) if has_b1 else None
+        dg = L.gemm(dpre, shadow(fc1_w), b_mn=True)
+        dx1, dx1_16, dn2w, dn2b = L.layernorm_bwd(dg, x1, n2w, mean2, rstd2, dres=dy2, want_bf16=True)
+        # attention
+        dproj_w = L.gemm(dx1_16, o16.view(T, D), a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dproj_b = L.colsum(dx1_16) if has_pb else None
+        do16 = L.gemm(dx1_16, shadow(proj_w), b_mn=True)
+        dqkv = _attn_core_bwd(qkv, o16, do16.view(B, N, D), lse, B, N, H, dh, scale)
+        dqkv_w = L.gemm(dqkv, h16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dqkv_b = L.colsum(dqkv) if has_qb else None
+        dh_ = L.gemm(dqkv, shadow(qkv_w), b_mn=True)
+        dx, _, dn1w, dn1b = L.layernorm_bwd(dh_, x2, n1w, mean1, rstd1, dres=dx1)
+        return (dx.view(B, N, D), dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w,
+                dfc2_b, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# LayerNorm as its own node (VisionTransformer.norm on the fp32 residual stream)
+# ----------------------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).contiguous()
+        _, y, _, mean, rstd = L.layernorm_fwd(x2, weight, bias, eps, want_bf16=False, want_f32=True)
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        dy2 = dy.reshape(x2.shape).contiguous()
+        dx, _, dg, db = L.layernorm_bwd(dy2, x2, weight, mean, rstd)
+        return dx.view(dy.shape), dg, db, None
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Voxel patchify: Conv3d(1 -> D, k = s = cell) (+ mean over z) as gather + tensor-core GEMM, token-major output
+# ----------------------------------------------------------------------------------------------------------------
+class VoxelPatchifyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, cell, patch, zmean):
+        D = weight.shape[0]
+        K = cell ** 3
+        kpad = (K + 63) // 64 * 64
+        P = L.voxel_patch_gather(x.contiguous().float(), cell, patch, kpad, zmean)
+        w16 = _padded_conv_weight(weight, K, kpad)
+        alpha = 1.0 / patch if zmean else 1.0
+        tok = L.gemm(P, w16, bias=bias, alpha=alpha, out_dtype=torch.float32)  # [B*p*p(*p), D]
+        ctx.save_for_backward(P, weight)
+        ctx.meta = (K, kpad, alpha, bias is not None)
+        return tok.view(x.shape[0], -1, D)
+
+    @staticmethod
+    def backward(ctx, dtok):
+        P, weight = ctx.saved_tensors
+        K, kpad, alpha, has_bias = ctx.meta
+        D = weight.shape[0]
+        d16 = L.cast_bf16(dtok.reshape(-1, D).contiguous())
+        dw = L.gemm(d16, P, a_mn=True, b_mn=True, alpha=alpha, out_dtype=torch.float32)  # [D, kpad]
+        dw = dw[:, :K].reshape(weight.shape)
+        db = L.colsum(d16) if has_bias else None
+        return None, dw, db, None, None, None
+
+
+def _padded_conv_weight(weight, K, kpad):
+    """bf16 [D, kpad] view of the Conv3d weight [D,1,c,c,c], zero padded along K (cached per parameter version)."""
+    key = (weight._version, weight.data_ptr(), kpad)
+    cache = getattr(weight, "_s3d_pad_cache", None)
+    s = getattr(weight, "_s3d_shadow", None)
+    if s is None and cache is not None and cache[0] == key:
+        return cache[1]
+    D = weight.shape[0]
+    w16 = torch.zeros((D, kpad), device=weight.device, dtype=torch.bfloat16)
+    src = s if s is not None else L.cast_bf16(weight.detach().contiguous())
+    w16[:, :K] = src.reshape(D, K)
+    if s is None:
+        try:
+            weight._s3d_pad_cache = (key, w16)
+        except Exception:
+            pass
+    return w16
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# group_embed: nn.TransformerEncoderLayer (post-norm, ReLU, sequence-first) with a flash attention core
+# ----------------------------------------------------------------------------------------------------------------
+class GroupEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1w, n1b, n2w, n2b, nhead, eps):
+        S, Nb, E = x.shape
+        T = S * Nb
+        dh = E // nhead
+        scale = dh ** -0.5
+        x2 = x.contiguous().view(T, E)
+        x16 = L.cast_bf16(x2)
+        qkv = L.gemm(x16, shadow(in_w), bias=in_b)  # [S*Nb, 3E], sequence-first
+        o16 = torch.empty((T, E), device=x.device, dtype=torch.bfloat16)
+        lse = torch.empty((Nb, nhead, S), device=x.device, dtype=torch.float32)
+        qs = (3 * E, dh, Nb * 3 * E)
+        os_ = (E, dh, Nb * E)
+        base = qkv.data_ptr()
+        L.attn_fwd(base, base + 2 * E, base + 4 * E, o16, lse, Nb, nhead, S, dh, qs, os_, scale)
+        sa = L.gemm(o16, shadow(out_w), bias=out_b, residual=x2, out_dtype=torch.float32)  # x + attn(x)
+        y1_16, y1, _, mean1, rstd1 = L.layernorm_fwd(sa, n1w, n1b, eps, want_f32=True)
+        h16 = L.gemm(y1_16, shadow(l1_w), bias=l1_b, epilogue=L.EPI_RELU)
+        f = L.gemm(h16, shadow(l2_w), bias=l2_b, residual=y1, out_dtype=torch.float32)
+        _, y2, _, mean2, rstd2 = L.layernorm_fwd(f, n2w, n2b, eps, want_bf16=False, want_f32=True)
+        ctx.save_for_backward(x16, qkv, o16, lse, sa, mean1, rstd1, y1_16, h16, f, mean2, rstd2, in_w, out_w, l1_w, l2_w,
+                              n1w, n2w)
+        ctx.meta = (S, Nb, E, nhead, dh, scale, qs, os_)
+        return y2.view(S, Nb, E)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x16, qkv, o16, lse, sa, mean1, rstd1, y1_16, h16, f, mean2, rstd2, in_w, out_w, l1_w, l2_w, n1w,
+         n2w) = ctx.saved_tensors
+        S, Nb, E, nhead, dh, scale, qs, os_ = ctx.meta
+        T = S * Nb
+        dy2 = dy.reshape(T, E).contiguous()
+        df, df16, dn2w, dn2b = L.layernorm_bwd(dy2, f, n2w, mean2, rstd2, want_bf16=True)
+        dl2_w = L.gemm(df16, h16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dl2_b = L.colsum(df16)
+        dh16 = L.gemm(df16, shadow(l2_w), b_mn=True, epilogue=L.EPI_DRELU, aux_in=h16)
+        dl1_w = L.gemm(dh16, y1_16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dl1_b = L.colsum(dh16)
+        dy1 = L.gemm(dh16, shadow(l1_w), b_mn=True, residual=df, out_dtype=torch.float32)  # + residual branch of y1
+        dsa, dsa16, dn1w, dn1b = L.layernorm_bwd(dy1, sa, n1w, mean1, rstd1, want_bf16=True)
+        dout_w = L.gemm(dsa16, o16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dout_b = L.colsum(dsa16)
+        do16 = L.gemm(dsa16, shadow(out_w), b_mn=True)
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse)
+        base, dbase = qkv.data_ptr(), dqkv.data_ptr()
+        L.attn_bwd(base, base + 2 * E, base + 4 * E, o16, do16, lse, delta, dbase, dbase + 2 * E, dbase + 4 * E, Nb, nhead,
+                   S, dh, qs, os_, scale)
+        din_w = L.gemm(dqkv, x16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        din_b = L.colsum(dqkv)
+        dx = L.gemm(dqkv, shadow(in_w), b_mn=True, residual=dsa, out_dtype=torch.float32)
+        return (dx.view(S, Nb, E), din_w, din_b, dout_w, dout_b, dl1_w, dl1_b, dl2_w, dl2_b, dn1w, dn1b, dn2w, dn2b, None,
+                None)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# index_points with a scatter-add backward
+# ----------------------------------------------------------------------------------------------------------------
+class GatherRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        pts = points.contiguous().float()
+        flat = idx.reshape(idx.shape[0], -1).contiguous()
+        out = L.gather_rows(pts, flat)
+        ctx.save_for_backward(flat)
+        ctx.n = pts.shape[1]
+        return out.view(*idx.shape, pts.shape[-1])
+
+    @staticmethod
+    def backward(ctx, dout):
+        (flat,) = ctx.saved_tensors
+        g = dout.reshape(flat.shape[0], flat.shape[1], -1).contiguous().float()
+        return L.scatter_add_rows(g, flat, ctx.n), None

@@ -1,0 +1,270 @@
+"""Model wrappers of the reference ("callers" of the hot path) rebuilt on the fused
+modules: same constructor arguments, attributes and state-dict keys as
+
+  * models/vit_3d_2d_pretrain.py::Feature3D_ViT2D_V2  (:275-526)   -- voxel classification, 'default' / 'group_embed'
+  * models/3DViT/model.py::PointTransformerCls (:144-337) / ::PointTransformerSeg (:341-535)
+
+so reference checkpoints load unchanged and train_cls_voxel.py / train_cls.py / train_partseg.py can construct them
+in place of the originals. Reference quirks are kept on purpose: deit_base uses 3 heads,
+`voxel_pos_embed` / `group_pos_embed` / `group_cls_token` start at zero, the 12 blocks run twice in group-embed mode,
+no positional embedding is added to point tokens, PointEmbed / pos_embed / last_pos_embed are constructed but unused.
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from .pointnet_util import PointNetFeaturePropagation, PointNetSetAbstraction
+from .vision_transformer import FusedLayerNorm, VisionTransformer, _cfg, trunc_normal_
+
+_norm = partial(FusedLayerNorm, eps=1e-6)
+
+BACKBONES = {
+    'deit_tiny_patch16_224': dict(patch_size=16, embed_dim=192, depth=12, num_heads=3, mlp_ratio=4, qkv_bias=True, norm_layer=_norm),
+    'deit_small_patch16_224': dict(patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, qkv_bias=True, norm_layer=_norm),
+    'deit_base_patch16_224': dict(patch_size=16, embed_dim=768, depth=12, num_heads=3, mlp_ratio=4, qkv_bias=True, norm_layer=_norm),
+    'deit_base_distilled_patch16_224': dict(patch_size=16, embed_dim=768, depth=12, num_heads=3, mlp_ratio=4, qkv_bias=True, norm_layer=_norm),
+    'vit_base_patch16_224_21k': dict(patch_size=16, embed_dim=768, depth=12, num_heads=3, mlp_ratio=4, qkv_bias=True, norm_layer=_norm),
+}
+PRETRAINED_URLS = {
+    'deit_tiny_patch16_224': "https://dl.fbaipublicfiles.com/deit/deit_tiny_patch16_224-a1311bcf.pth",
+    'deit_small_patch16_224': "https://dl.fbaipublicfiles.com/deit/deit_small_patch16_224-cd65a155.pth",
+    'deit_base_patch16_224': "https://dl.fbaipublicfiles.com/deit/deit_base_patch16_224-b5f2ef4d.pth",
+    'deit_base_distilled_patch16_224': "https://dl.fbaipublicfiles.com/deit/deit_base_distilled_patch16_224-df68dfff.pth",
+}
+
+
+class _SelfAttnParams(nn.Module):
+    """Parameter container with nn.MultiheadAttention's names (in_proj_weight, in_proj_bias, out_proj.{weight,bias})."""
+
+    def __init__(self, embed_dim, num_heads):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.batch_first = embed_dim, num_heads, False
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.constant_(self.out_proj.bias, 0.)
+
+
+class GroupEmbedLayer(nn.Module):
+    """nn.TransformerEncoderLayer(d_model, nhead, dim_feedforward) as used for `group_embed`
+    (vit_3d_2d_pretrain.py:381): post-norm, ReLU, sequence-first [S, Nb, E] -- attention runs over S = B*px*py.
+    State-dict keys match torch's layer. Dropout: the reference's p=0.1 is active only in train(); parity is defined in
+    eval mode and this layer always evaluates the deterministic (p=0) arithmetic."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, layer_norm_eps=1e-5):
+        super().__init__()
+        self.self_attn = _SelfAttnParams(d_model, nhead)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.norm2 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.dropout_p = dropout
+        self.nhead = nhead
+
+    def forward(self, src):
+        a = self.self_attn
+        return Fn.GroupEmbedFn.apply(src, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias,
+                                     self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                                     self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias, self.nhead,
+                                     self.norm1.eps)
+
+
+def _load_pretrained(model, url, distilled=False):
+    checkpoint = torch.hub.load_state_dict_from_url(url=url, map_location="cpu", check_hash=True)
+    pretrained = {k: v for k, v in checkpoint["model"].items() if k in model.state_dict()}
+    if distilled:
+        pretrained['pos_embed'] = pretrained['pos_embed'][:, 1:, :]
+    model.load_state_dict(pretrained, strict=False)
+
+
+class Feature3D_ViT2D_V2(VisionTransformer):
+    def __init__(self, n_classes=10, embed_layer=None, data_shape=None, transformer_backbone='deit_base_patch16_224',
+                 pretrained=True, pos_embedding=None, **kwargs):
+        if transformer_backbone not in BACKBONES:
+            raise ValueError("Unknown transformer backbone name!")
+        self.transformer_backbone = transformer_backbone
+        self.pretrained = pretrained
+        super().__init__(**BACKBONES[transformer_backbone])
+        self.default_cfg = _cfg()
+        self.url = PRETRAINED_URLS.get(transformer_backbone)
+        self.dist_token = None
+        self.n_classes = n_classes
+        if pretrained:
+            _load_pretrained(self, self.url, 'distilled' in transformer_backbone)
+            self.freeze_image_branch()
+        self.voxel_embed = embed_layer
+        if kwargs.get('head') == 'AMSoftmax':
+            raise NotImplementedError("AMSoftmax head is outside the hot path")
+        self.voxel_head = nn.Linear(self.embed_dim, self.n_classes)
+        self.pos_embed_type = pos_embedding
+        if pos_embedding is None or pos_embedding == "default":
+            self.voxel_pos_embed = nn.Parameter(torch.zeros(1, self.voxel_embed.num_patches + 1, self.embed_dim))
+            trunc_normal_(self.pos_embed, std=.02)  # sic: the reference initialises pos_embed, not voxel_pos_embed
+        elif pos_embedding == "group_embed":
+            self.voxel_pos_embed = nn.Parameter(torch.zeros(1, self.voxel_embed.patch_size ** 2 + 1, self.embed_dim))
+            trunc_normal_(self.pos_embed, std=.02)
+            self.group_embed = GroupEmbedLayer(d_model=self.embed_dim, dim_feedforward=self.embed_dim, nhead=4)
+            self.group_pos_embed = nn.Parameter(torch.zeros(1, self.voxel_embed.patch_size + 1, self.embed_dim))
+            self.group_cls_token = nn.Parameter(torch.zeros(1, 1, self.embed_dim))
+        else:
+            raise ValueError("positional embedding scheme not on the hot path: %r" % (pos_embedding,))
+
+    def freeze_image_branch(self):
+        """head / pos_embed / patch_embed only serve forward_images; frozen as on the reference's pretrained path
+        (vit_3d_2d_pretrain.py:428-432) so data-parallel training sees no unused trainable parameters."""
+        self.head.weight.requires_grad = False
+        self.head.bias.requires_grad = False
+        self.pos_embed.requires_grad = False
+        for p in self.patch_embed.parameters():
+            p.requires_grad = False
+
+    def forward_images(self, x):
+        x = self.patch_embed(x)
+        x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), x), dim=1)
+        x = self.pos_drop(x + self.pos_embed)
+        for blk in self.blocks:
+            x = blk(x)
+        return self.head(self.norm(x)[:, 0])
+
+    def _tokens(self, x):
+        emb = self.voxel_embed
+        if hasattr(emb, "forward_tokens"):
+            return emb.forward_tokens(x)  # [B, T, D] token-major straight from the GEMM epilogue
+        y = emb(x)  # foreign embed layer: channel-first like the reference
+        return y.flatten(2).transpose(1, 2)
+
+    def forward_features(self, x):
+        B = x.shape[0]
+        if self.pos_embed_type in (None, "default"):
+            t = self._tokens(x)
+            t = torch.cat((self.cls_token.expand(B, -1, -1), t), dim=1)
+            t = self.pos_drop(t + self.voxel_pos_embed)
+            for blk in self.blocks:
+                t = blk(t)
+            return self.norm(t)[:, 0]
+        p = self.voxel_embed.patch_size
+        D = self.embed_dim
+        t = self._tokens(x).reshape(B * p * p, p, D)  # '(b px py) pz c'
+        t = torch.cat((self.group_cls_token.expand(t.shape[0], -1, -1), t), dim=1)
+        t = self.pos_drop(t + self.group_pos_embed)
+        t = self.group_embed(t)
+        for blk in self.blocks:
+            t = blk(t)
+        t = self.norm(t)[:, 0].reshape(B, p * p, D)
+        t = torch.cat((self.cls_token.expand(B, -1, -1), t), dim=1)
+        t = self.pos_drop(t + self.voxel_pos_embed)
+        for blk in self.blocks:
+            t = blk(t)
+        return self.norm(t)[:, 0]
+
+    def forward(self, x):
+        return self.voxel_head(self.forward_features(x))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# point models
+# ----------------------------------------------------------------------------------------------------------------
+class TransitionDown(nn.Module):
+    def __init__(self, k, nneighbor, channels):
+        super().__init__()
+        self.sa = PointNetSetAbstraction(k, 0, nneighbor, channels[0], channels[1:], group_all=False, knn=True)
+
+    def forward(self, xyz, points):
+        return self.sa(xyz, points)
+
+
+class _SwapAxes(nn.Module):
+    def forward(self, x):
+        return x.transpose(1, 2)
+
+
+class TransitionUp(nn.Module):
+    def __init__(self, dim1, dim2, dim_out):
+        super().__init__()
+        self.fc1 = nn.Sequential(nn.Linear(dim1, dim_out), _SwapAxes(), nn.BatchNorm1d(dim_out), _SwapAxes(), nn.ReLU())
+        self.fc2 = nn.Sequential(nn.Linear(dim2, dim_out), _SwapAxes(), nn.BatchNorm1d(dim_out), _SwapAxes(), nn.ReLU())
+        self.fp = PointNetFeaturePropagation(-1, [])
+
+    def forward(self, xyz1, points1, xyz2, points2):
+        feats1 = self.fc1(points1)
+        feats2 = self.fc2(points2)
+        feats1 = self.fp(xyz2.transpose(1, 2), xyz1.transpose(1, 2), None, feats1.transpose(1, 2)).transpose(1, 2)
+        return feats1 + feats2
+
+
+class _DeadPointEmbed(nn.Module):
+    """Stand-in for the reference's PointEmbed (models/3DViT/model.py:75-121): built in __init__, never called in
+    forward(). Only `parameters()` is ever touched, so an empty module keeps the attribute without the dead weights."""
+
+
+class _PointTransformerBase(VisionTransformer):
+    _seg = False
+
+    def __init__(self, cfg):
+        npoints, nneighbor, n_c, d_points = cfg.num_point, cfg.model.nneighbor, cfg.num_class, cfg.input_dim
+        self.transformer_backbone = cfg.model.transformer_backbone
+        self.pretrained = cfg.model.pretrained
+        if self.transformer_backbone not in BACKBONES:
+            raise ValueError("Unknown transformer backbone name!")
+        super().__init__(**BACKBONES[self.transformer_backbone])
+        self.default_cfg = _cfg()
+        self.url = PRETRAINED_URLS.get(self.transformer_backbone)
+        self.dist_token = None
+        self.n_classes = n_c
+        cfg.embed_dim = self.embed_dim
+        if self.pretrained:
+            _load_pretrained(self, self.url)
+        self.patch_embed = _DeadPointEmbed()
+        if cfg.model.head == 'AMSoftmax':
+            raise NotImplementedError("AMSoftmax head is outside the hot path")
+        q = self.embed_dim // 4
+        self.head = nn.Linear(q, self.n_classes)
+        self.pos_embed_type = 'default'
+        self.transition_downs = nn.ModuleList()
+        for i in range(2):
+            ch = q * 2 ** (i + 1)
+            self.transition_downs.append(TransitionDown(npoints // 4 ** i, nneighbor, [ch // 2 + 3, ch, ch]))
+        self.transition_ups = nn.ModuleList()
+        for i in reversed(range(2)):
+            ch = q * 2 ** i
+            self.transition_ups.append(TransitionUp(ch * 2, ch, ch))
+        self.fc1 = nn.Sequential(nn.Linear(d_points, q), nn.ReLU(), nn.Linear(q, q))
+        self.fc_pos_embed = nn.Sequential(nn.Linear(3, q), nn.ReLU(), nn.Linear(q, q))
+
+    def set_fps_starts(self, starts):
+        """Explicit FPS start indices for the two transition-down stages (None restores random starts)."""
+        for td, s in zip(self.transition_downs, starts or (None, None)):
+            td.sa.fps_start = s
+
+    def unused_parameter_names(self):
+        """Parameters that never receive a gradient (kept only for checkpoint compatibility)."""
+        return [n for n, _ in self.named_parameters() if n == "pos_embed" or "last_pos_embed" in n]
+
+    def forward_features(self, x):
+        xyz = x[..., :3].contiguous()
+        f = self.pos_drop(self.fc1(x) + self.fc_pos_embed(xyz))
+        xyz_0, points_0 = self.transition_downs[0](xyz, f)
+        xyz_1, points_1 = self.transition_downs[1](xyz_0, points_0)
+        t = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), points_1), dim=1)
+        for blk in self.blocks:
+            t = blk(t)
+        t = self.norm(t)[:, 1:]
+        t = self.transition_ups[0](xyz_1, t, xyz_0, points_0)
+        t = self.transition_ups[1](xyz_0, t, xyz, f)
+        return t if self._seg else t.mean(1)
+
+    def forward(self, x):
+        return self.head(self.forward_features(x))
+
+
+class PointTransformerCls(_PointTransformerBase):
+    _seg = False
+
+
+class PointTransformerSeg(_PointTransformerBase):
+    _seg = True

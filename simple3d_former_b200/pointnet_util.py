@@ -1,0 +1,137 @@
+"""Point-grouping utilities with the reference's function surface (data/pointnet_util.py), backed by sm_100a kernels.
+
+`square_distance + argsort()[:, :, :K]` (:119-120, :233-234) becomes `knn_point` (no [B,S,N] matrix, no full sort),
+`query_ball_point` (:76-96), `farthest_point_sample` (:53-73) and `index_points` (:39-50) are single kernels; integer
+outputs are bit-exact with the reference on tie-free inputs (tie contract: ascending (distance, index)).
+The set-abstraction / feature-propagation modules keep their 1x1 conv + BatchNorm layers as PyTorch ops (SURVEY.md
+section 8(f) rank 1 is the fusion of those) but use the kernels for sampling, grouping and gathering, and drop the
+reference's dead second kNN (:233-235) and its torch.cuda.empty_cache() stalls (:115-127).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import functional as Fn
+
+
+def pc_normalize(pc):
+    centroid = np.mean(pc, axis=0)
+    pc = pc - centroid
+    return pc / np.max(np.sqrt(np.sum(pc ** 2, axis=1)))
+
+
+def square_distance(src, dst):
+    """[B,N,3] x [B,M,3] -> [B,N,M]. Kept for API compatibility only; nothing on the hot path materialises it."""
+    return torch.sum((src[:, :, None] - dst[:, None]) ** 2, dim=-1)
+
+
+def index_points(points, idx):
+    """points [B,N,C], idx [B,S(,K)] -> [B,S(,K),C]"""
+    return Fn.GatherRowsFn.apply(points, idx)
+
+
+def farthest_point_sample(xyz, npoint, start=None):
+    """xyz [B,N,3] -> centroid indices [B,npoint] (int64). `start` makes the reference's torch.randint draw explicit."""
+    B, N, _ = xyz.shape
+    if start is None:
+        start = torch.randint(0, N, (B,), dtype=torch.long, device=xyz.device)
+    return L.fps(xyz.detach(), npoint, start.to(xyz.device))
+
+
+def knn_point(nsample, xyz, new_xyz, return_dist=False):
+    """Indices of the `nsample` nearest points of xyz [B,N,3] for every query new_xyz [B,S,3] -> int64 [B,S,nsample]."""
+    return L.knn(xyz.detach(), new_xyz.detach(), nsample, want_dist=return_dist)
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    r2 = float(np.float32(radius ** 2))
+    return L.ball_query(r2, nsample, xyz.detach(), new_xyz.detach())
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, knn=False, fps_start=None):
+    B, N, C = xyz.shape
+    fps_idx = farthest_point_sample(xyz, npoint, fps_start)
+    new_xyz = index_points(xyz, fps_idx)
+    idx = knn_point(nsample, xyz, new_xyz) if knn else query_ball_point(radius, nsample, xyz, new_xyz)
+    grouped_xyz = index_points(xyz, idx)
+    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, npoint, 1, C)
+    if points is not None:
+        new_points = torch.cat([grouped_xyz_norm, index_points(points, idx)], dim=-1)
+    else:
+        new_points = grouped_xyz_norm
+    if returnfps:
+        return new_xyz, new_points, grouped_xyz, fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    B, N, C = xyz.shape
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device)
+    grouped_xyz = xyz.view(B, 1, N, C)
+    new_points = torch.cat([grouped_xyz, points.view(B, 1, N, -1)], dim=-1) if points is not None else grouped_xyz
+    return new_xyz, new_points
+
+
+class PointNetSetAbstraction(nn.Module):
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all, knn=False):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.knn, self.group_all = npoint, radius, nsample, knn, group_all
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        self.pos_embeds = nn.ModuleList()
+        last = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last = out_channel
+        # constructed (never used in forward) by the reference; kept so checkpoints load with strict=True
+        self.last_pos_embed = nn.Sequential(nn.Linear(3, last), nn.ReLU(), nn.Linear(last, last))
+        self.fps_start = None  # optional explicit FPS start indices (parity tests)
+
+    def forward(self, xyz, points):
+        if self.group_all:
+            new_xyz, new_points = sample_and_group_all(xyz, points)
+        else:
+            new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz, points, knn=self.knn,
+                                                   fps_start=self.fps_start)
+        new_points = new_points.permute(0, 3, 2, 1)  # [B, C+D, nsample, npoint]
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            new_points = F.relu(bn(conv(new_points)))
+        return new_xyz, torch.max(new_points, 2)[0].transpose(1, 2)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(out_channel))
+            last = out_channel
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        """xyz1 [B,C,N], xyz2 [B,C,S], points1 [B,D,N] or None, points2 [B,D,S] -> [B,D',N] (3-NN interpolation)."""
+        xyz1 = xyz1.permute(0, 2, 1)
+        xyz2 = xyz2.permute(0, 2, 1)
+        points2 = points2.permute(0, 2, 1)
+        B, N, _ = xyz1.shape
+        S = xyz2.shape[1]
+        if S == 1:
+            interpolated = points2.repeat(1, N, 1)
+        else:
+            idx, dists = knn_point(3, xyz2.contiguous(), xyz1.contiguous(), return_dist=True)  # queries = xyz1
+            recip = 1.0 / (dists + 1e-8)
+            weight = recip / torch.sum(recip, dim=2, keepdim=True)
+            interpolated = torch.sum(index_points(points2, idx) * weight.view(B, N, 3, 1), dim=2)
+        if points1 is not None:
+            new_points = torch.cat([points1.permute(0, 2, 1), interpolated], dim=-1)
+        else:
+            new_points = interpolated
+        new_points = new_points.permute(0, 2, 1)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            new_points = F.relu(bn(conv(new_points)))
+        return new_points

@@ -1,0 +1,195 @@
+"""GPU parity: the sm_100a product path (through the C ABI) against the reference's golden outputs and the oracle.
+Tolerances are north_star's: logits / loss within 1e-2 (bf16 operands, fp32 accumulate); integer indices bit-exact."""
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import s3d_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-2
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _voxel_sd(fix):
+    sd = O.init_voxel_state_dict(fix["backbone"], fix["cell"], fix["patch"], fix["n_classes"], fix["pos"], seed=fix["weight_seed"])
+    g = torch.Generator().manual_seed(fix["embed_seed"])
+    for k in ("voxel_pos_embed", "group_pos_embed", "group_cls_token"):
+        if k in sd:
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.02
+    assert abs(O.state_dict_checksum(sd) - fix["sd_checksum"]) <= 1e-6 * abs(fix["sd_checksum"])
+    return sd
+
+
+def _build_voxel(fix):
+    from simple3d_former_b200.embed_layer_3d_modality import VoxelEmbed, VoxelEmbed_no_average
+    from simple3d_former_b200.models import Feature3D_ViT2D_V2
+    D = O.BACKBONES[fix["backbone"]]["embed_dim"]
+    emb = (VoxelEmbed if fix["average"] else VoxelEmbed_no_average)(fix["V"], fix["cell"], fix["patch"], embed_dim=D)
+    m = Feature3D_ViT2D_V2(embed_layer=emb, n_classes=fix["n_classes"], transformer_backbone=fix["backbone"],
+                           pretrained=False, pos_embedding=fix["pos"])
+    res = m.load_state_dict(_voxel_sd(fix), strict=False)
+    assert not res.unexpected_keys
+    assert all(k.startswith(("pos_embed", "patch_embed.", "head.")) for k in res.missing_keys), res.missing_keys
+    return m.to(_dev())
+
+
+def _check_grads(model, ref_grads, rel=3e-2):
+    named = dict(model.named_parameters())
+    for k, ref in ref_grads.items():
+        g = named[k].grad
+        assert g is not None, k
+        g = g.detach().float().cpu()
+        assert abs(float(g.norm()) - ref["norm"]) <= rel * ref["norm"] + 1e-7, (k, float(g.norm()), ref["norm"])
+        tol = rel * max(float(ref["head"].abs().max()), ref["norm"] / max(g.numel(), 1) ** 0.5) + 1e-7
+        assert torch.allclose(g.flatten()[:16], ref["head"], atol=tol), (k, g.flatten()[:16], ref["head"])
+
+
+@pytest.mark.parametrize("name", ["cfg1_deit_small_voxel30", "cfg3_small_deit_base_group36", "cfg3_deit_base_group128"])
+def test_voxel_model_matches_reference(golden, name):
+    fix = golden(name)
+    model = _build_voxel(fix).train()
+    x, y = O.synthetic_voxels(fix["B"], fix["V"], seed=fix["input_seed"], n_classes=fix["n_classes"])
+    logits = model(x.to(_dev()))
+    loss = F.cross_entropy(logits, y.to(_dev()))
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (logits.detach().cpu() - fix["logits"]).abs().max().item()
+    assert err <= LOGIT_TOL, f"logits differ from the reference by {err}"
+    assert abs(float(loss) - fix["loss"]) <= LOGIT_TOL
+    _check_grads(model, fix["grads"])
+
+
+def _point_cfg(fix):
+    model = types.SimpleNamespace(nblocks=4, nneighbor=16, transformer_backbone=fix["backbone"], pretrained=False,
+                                  head="Linear", transformer_dim=512)
+    return types.SimpleNamespace(num_point=fix["N"], num_class=fix["n_classes"], input_dim=fix["input_dim"], model=model)
+
+
+@pytest.mark.parametrize("name", ["cfg4_point_cls_tiny1024", "cfg5_point_seg_tiny2048"])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_point_model_matches_reference(golden, name, mode):
+    from simple3d_former_b200.models import PointTransformerCls, PointTransformerSeg
+    fix = golden(name)
+    model = (PointTransformerSeg if fix["seg"] else PointTransformerCls)(_point_cfg(fix))
+    sd = O.init_point_state_dict(fix["backbone"], fix["input_dim"], fix["n_classes"], seed=fix["weight_seed"])
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys
+    model = model.to(_dev()).train(mode == "train")
+    model.set_fps_starts([s.to(_dev()) for s in fix["fps_starts"]])
+    x, y = O.synthetic_points(fix["B"], fix["N"], extra=fix["input_dim"] - 3, seed=fix["input_seed"], n_classes=fix["n_classes"])
+    if fix["seg"]:
+        y = torch.randint(0, fix["n_classes"], (fix["B"], fix["N"]), generator=torch.Generator().manual_seed(fix["label_seed"]))
+    logits = model(x.to(_dev()))
+    loss = F.cross_entropy(logits.reshape(-1, fix["n_classes"]), y.reshape(-1).to(_dev()))
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (logits.detach().cpu() - fix[mode]["logits"]).abs().max().item()
+    assert err <= LOGIT_TOL, f"logits differ from the reference by {err}"
+    assert abs(float(loss) - fix[mode]["loss"]) <= LOGIT_TOL
+    _check_grads(model, fix[mode]["grads"], rel=5e-2)
+
+
+def test_point_ops_bit_exact(golden):
+    from simple3d_former_b200 import pointnet_util as P
+    fix = golden("pointops")
+    dev = _dev()
+    for c in fix["cases"]:
+        xyz, q = c["xyz"].to(dev), c["query"].to(dev)
+        idx, dist = P.knn_point(c["K"], xyz, q, return_dist=True)
+        assert torch.equal(idx.cpu(), c["knn"])
+        assert torch.equal(dist.cpu(), c["knn_dist"])
+        assert torch.equal(P.query_ball_point(c["radius"], c["nsample"], xyz, q).cpu(), c["ball"])
+        assert torch.equal(P.farthest_point_sample(xyz, c["S"], c["fps_start"].to(dev)).cpu(), c["fps"])
+        pts = torch.randn(c["B"], c["N"], 7, generator=torch.Generator().manual_seed(3))
+        got = P.index_points(pts.to(dev), c["knn"].to(dev)).cpu()
+        assert torch.equal(got, O.index_points(pts, c["knn"]))
+    t = fix["tie_case"]  # duplicated points: ascending (distance, index)
+    assert torch.equal(P.knn_point(t["K"], t["xyz"].to(dev), t["xyz"].to(dev)).cpu(), t["knn_stable"])
+
+
+def test_point_ops_edge_cases_and_full_size_properties():
+    from simple3d_former_b200 import pointnet_util as P
+    dev = _dev()
+    xyz = torch.zeros(1, 16, 3, device=dev)
+    assert torch.equal(P.knn_point(16, xyz, xyz[:, :2])[0, 0].cpu(), torch.arange(16))
+    far = torch.full((1, 4, 3), 5.0, device=dev)
+    assert (P.query_ball_point(0.2, 8, xyz, far) == 16).all()
+    assert torch.equal(P.farthest_point_sample(xyz, 4, torch.tensor([3], device=dev))[0].cpu(), torch.tensor([3, 0, 0, 0]))
+    # BASELINE cfg4 sizes (B=128, N=S=1024, K=16): size-independent properties
+    x, _ = O.synthetic_points(128, 1024)
+    pts = x[..., :3].contiguous().to(dev)
+    idx, dist = P.knn_point(16, pts, pts, return_dist=True)
+    assert torch.equal(idx[:, :, 0].cpu(), torch.arange(1024).expand(128, -1))  # each point is its own nearest neighbour
+    assert bool((dist[:, :, 1:] >= dist[:, :, :-1]).all())  # sortedness
+    assert bool((dist[:, :, 0] == 0).all())
+    sub = slice(0, 4)  # oracle on a slice the CPU finishes in seconds
+    assert np.array_equal(idx[sub].cpu().numpy(), O.knn_np(pts[sub].cpu().numpy(), pts[sub].cpu().numpy(), 16))
+    fps = P.farthest_point_sample(pts, 1024, torch.zeros(128, dtype=torch.long, device=dev))
+    assert torch.equal(fps.sort(dim=1)[0].cpu(), torch.arange(1024).expand(128, -1))  # npoint == N -> a permutation
+    assert np.array_equal(fps[:2].cpu().numpy(), O.fps_np(pts[:2].cpu().numpy(), 1024, np.zeros(2, np.int64)))
+
+
+def test_block_matches_oracle_all_shapes():
+    """timm Block forward/backward at the (N, D, heads) of every BASELINE config, against the fp32 oracle."""
+    from simple3d_former_b200.vision_transformer import Block
+    dev = _dev()
+    for (B, N, D, H) in [(64, 26, 384, 6), (40, 15, 768, 3), (4, 197, 768, 3), (8, 257, 192, 3), (4, 513, 192, 3)]:
+        torch.manual_seed(0)
+        blk = Block(D, H, qkv_bias=True, norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6))
+        for p in blk.parameters():
+            if p.dim() > 1:
+                torch.nn.init.normal_(p, std=0.03)
+            else:
+                torch.nn.init.normal_(p, mean=1.0 if "norm" in "" else 0.0, std=0.05)
+        blk.norm1.weight.data.add_(1.0)
+        blk.norm2.weight.data.add_(1.0)
+        sd = {"b." + k: v.detach().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+        x = torch.randn(B, N, D)
+        dy = torch.randn(B, N, D)
+        xr = x.clone().requires_grad_(True)
+        yr = O.block(sd, "b.", xr, H)
+        yr.backward(dy)
+        blk = blk.to(dev)
+        xg = x.to(dev).requires_grad_(True)
+        yg = blk(xg)
+        yg.backward(dy.to(dev))
+        torch.cuda.synchronize()
+        scale = yr.abs().max().item()
+        assert (yg.detach().cpu() - yr.detach()).abs().max().item() <= 1e-2 * scale, (N, D)
+        assert (xg.grad.cpu() - xr.grad).abs().max().item() <= 2e-2 * xr.grad.abs().max().item(), (N, D)
+        for k, p in blk.named_parameters():
+            gr = sd["b." + k].grad
+            assert (p.grad.cpu() - gr).abs().max().item() <= 3e-2 * gr.abs().max().item() + 1e-6, (k, N, D)
+
+
+def test_convert_swaps_reference_style_modules():
+    """convert() on a model built from the oracle's timm restatement (same module layout as the reference)."""
+    import os
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.abspath(O.__file__)), "timm_shim")
+    sys.path.insert(0, shim)
+    try:
+        from timm.models.vision_transformer import VisionTransformer as RefViT
+    finally:
+        sys.path.remove(shim)
+    from simple3d_former_b200.convert import convert
+    from simple3d_former_b200.vision_transformer import Block
+    torch.manual_seed(1)
+    ref = RefViT(embed_dim=192, depth=2, num_heads=3, qkv_bias=True, num_classes=10)
+    x = torch.randn(2, 3, 224, 224)
+    with torch.no_grad():
+        want = ref(x)
+    fused = convert(ref).to(_dev())
+    assert all(isinstance(b, Block) for b in fused.blocks)
+    with torch.no_grad():
+        got = fused(x.to(_dev())).cpu()
+    assert (got - want).abs().max().item() <= 1e-2
