@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""Benchmark of the Simple3D-Former encoder hot path on B200 (metric: voxels/s or points/s, forward + backward + Adam).
+
+  python bench.py --gpus N --steps K --warmup W [--config cfg2|cfg3|cfg4|cfg5] [--impl ours|reference]
+
+One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE); weak scaling: the per-GPU batch is fixed and
+gradients are averaged with NCCL allreduce. Rank 0 prints ONE JSON line. A "step" is one training step over one
+synthetic batch resident in HBM (`value`) or starting from pinned host memory and ending with the loss read back
+(`e2e`). `--impl reference` times the reference's CPU implementation of the same step (the oracle port: the reference
+tree does not exist on the GPU box) on the host cores with a bounded per-step sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+CONFIGS = {
+    # BASELINE.json configs[1]: deit_small + VoxelEmbed (cell 6 / patch 5), 30^3 voxels, batch 64, bf16, 1xB200
+    "cfg2": dict(kind="voxel", model="deit_small_patch16_224+VoxelEmbed(30,6,5)", backbone="deit_small_patch16_224", V=30,
+                 cell=6, patch=5, pos="default", average=True, B=64, n_classes=40, unit="voxels/s", per_sample=30 ** 3,
+                 cpu_B=64),
+    # configs[2]: deit_base (3 heads) + VoxelEmbed_no_average (cell 9 / patch 14) + group_embed, 128^3, batch 64/GPU
+    "cfg3": dict(kind="voxel", model="deit_base_patch16_224+VoxelEmbed_no_average(128,9,14)+group_embed",
+                 backbone="deit_base_patch16_224", V=128, cell=9, patch=14, pos="group_embed", average=False, B=64,
+                 n_classes=55, unit="voxels/s", per_sample=128 ** 3, cpu_B=2),
+    # configs[3]: 3DViT point classification, 1024 points, kNN K=16, batch 128/GPU
+    "cfg4": dict(kind="point", model="PointTransformerCls(deit_tiny)", backbone="deit_tiny_patch16_224", seg=False, N=1024,
+                 input_dim=6, n_classes=40, B=128, unit="points/s", per_sample=1024, cpu_B=8),
+    # configs[4]: ShapeNetPart part segmentation, 2048 points x 50 parts, batch 32/GPU
+    "cfg5": dict(kind="point", model="PointTransformerSeg(deit_tiny)", backbone="deit_tiny_patch16_224", seg=True, N=2048,
+                 input_dim=22, n_classes=50, B=32, unit="points/s", per_sample=2048, cpu_B=4),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic data: binary occupancy grids / unit-ball point clouds, random labels
+# ----------------------------------------------------------------------------------------------------------------
+def synthetic_batch(cfg, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    if cfg["kind"] == "voxel":
+        V = cfg["V"]
+        x = (torch.rand(B, 1, V, V, V, generator=g) < 0.1).float()
+        y = torch.randint(0, cfg["n_classes"], (B,), generator=g)
+        return x, y
+    N, d = cfg["N"], cfg["input_dim"]
+    xyz = torch.rand(B, N, 3, generator=g) * 2 - 1
+    xyz = xyz / xyz.norm(dim=-1).max(dim=1, keepdim=True)[0][..., None].clamp_min(1e-6)
+    feats = F.normalize(torch.randn(B, N, 3, generator=g), dim=-1)
+    x = torch.cat([xyz, feats], dim=-1)
+    if d > 6:
+        onehot = F.one_hot(torch.randint(0, d - 6, (B,), generator=g), d - 6).float()
+        x = torch.cat([x, onehot[:, None, :].expand(-1, N, -1)], dim=-1)
+    y = torch.randint(0, cfg["n_classes"], (B, N) if cfg["seg"] else (B,), generator=g)
+    return x.contiguous(), y
+
+
+def loss_fn_for(cfg):
+    n = cfg["n_classes"]
+    return lambda logits, y: F.cross_entropy(logits.reshape(-1, n), y.reshape(-1))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(cfg, B):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import s3d_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    if cfg["kind"] == "voxel":
+        sd = O.init_voxel_state_dict(cfg["backbone"], cfg["cell"], cfg["patch"], cfg["n_classes"], cfg["pos"], seed=9)
+        frozen = ()
+    else:
+        sd = O.init_point_state_dict(cfg["backbone"], cfg["input_dim"], cfg["n_classes"], seed=9)
+        frozen = tuple(k for k in sd if "running_" in k)
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if k not in frozen}
+    sd = {**sd, **params}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-3)
+    x, y = synthetic_batch(cfg, B, seed=9)
+    lf = loss_fn_for(cfg)
+    starts = None
+    if cfg["kind"] == "point":
+        starts = [torch.zeros(B, dtype=torch.long).numpy(), torch.zeros(B, dtype=torch.long).numpy()]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        if cfg["kind"] == "voxel":
+            logits = O.voxel_vit_logits(sd, x, cfg["backbone"], cfg["cell"], cfg["patch"], cfg["pos"])
+        else:
+            logits = O.point_vit_logits(sd, x, cfg["backbone"], cfg["N"], 16, starts, training=True, seg=cfg["seg"])
+        loss = lf(logits, y)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step
+
+
+def run_cpu(cfg, B, steps, warmup, budget_s=None):
+    step = cpu_reference_step_fn(cfg, B)
+    for _ in range(warmup):
+        step()
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s and i >= 1:
+            break
+    mean = sum(times) / len(times)
+    return B * cfg["per_sample"] / mean, mean * 1e3, len(times)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def build_model(cfg, device):
+    import types
+    from simple3d_former_b200.embed_layer_3d_modality import VoxelEmbed, VoxelEmbed_no_average
+    from simple3d_former_b200.models import BACKBONES, Feature3D_ViT2D_V2, PointTransformerCls, PointTransformerSeg
+    torch.manual_seed(9)  # train_cls_voxel.py:383
+    if cfg["kind"] == "voxel":
+        D = BACKBONES[cfg["backbone"]]["embed_dim"]
+        emb = (VoxelEmbed if cfg["average"] else VoxelEmbed_no_average)(cfg["V"], cfg["cell"], cfg["patch"], embed_dim=D)
+        model = Feature3D_ViT2D_V2(embed_layer=emb, n_classes=cfg["n_classes"], transformer_backbone=cfg["backbone"],
+                                   pretrained=False, pos_embedding=cfg["pos"])
+        model.freeze_image_branch()
+        exclude = ()
+    else:
+        mc = types.SimpleNamespace(nblocks=4, nneighbor=16, transformer_backbone=cfg["backbone"], pretrained=False,
+                                   head="Linear", transformer_dim=512)
+        pc = types.SimpleNamespace(num_point=cfg["N"], num_class=cfg["n_classes"], input_dim=cfg["input_dim"], model=mc)
+        model = (PointTransformerSeg if cfg["seg"] else PointTransformerCls)(pc)
+        exclude = model.unused_parameter_names()
+    return model.to(device).train(), exclude
+
+
+class KernelProfile:
+    """CUDA-event timing of every C-ABI launch (installed into _lib.call for an instrumented pass)."""
+
+    def __init__(self):
+        self.records = []
+
+    def wrap(self, L):
+        orig = L.call
+
+        def call(name, *args):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig(name, *args)
+            e.record()
+            self.records.append((name, args, s, e))
+
+        L.call = call
+        return orig
+
+    @staticmethod
+    def work(name, a):
+        """Algorithmic (flops, bytes) of one launch."""
+        if name == "s3d_gemm_bf16":
+            M, N, K, batch = a[3], a[4], a[5], a[21]
+            return 2.0 * M * N * K * batch, 2.0 * batch * (M * K + N * K + M * N)
+        if name == "s3d_attn_fwd":
+            B, H, N, dh = a[5], a[6], a[7], a[8]
+            return 4.0 * B * H * N * N * dh, 2.0 * 4 * B * H * N * dh
+        if name == "s3d_attn_bwd":
+            B, H, N, dh = a[10], a[11], a[12], a[13]
+            return 10.0 * B * H * N * N * dh, 2.0 * 8 * B * H * N * dh
+        if name == "s3d_layernorm_fwd":
+            return 0.0, a[9] * a[10] * 6.0
+        if name == "s3d_layernorm_bwd":
+            return 0.0, a[11] * a[12] * 14.0
+        return 0.0, 0.0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        fam = {}
+        for name, args, s, e in self.records:
+            ms = s.elapsed_time(e)
+            fl, by = self.work(name, args)
+            f = fam.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            f["ms"] += ms
+            f["flops"] += fl
+            f["bytes"] += by
+            f["launches"] += 1
+        return fam
+
+
+def run_ours(args, cfg, rank, world, local_rank):
+    from simple3d_former_b200 import _lib as L
+    from simple3d_former_b200.dp import DataParallelTrainer
+    import torch.distributed as dist
+
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    L.lib()  # fail loudly if the CUDA extension is missing
+    model, exclude = build_model(cfg, device)
+    trainer = DataParallelTrainer(model, lr=1e-3, exclude=exclude)
+    lf = loss_fn_for(cfg)
+    B = cfg["B"]
+    xh, yh = synthetic_batch(cfg, B, seed=9 + rank)
+    xh, yh = xh.pin_memory(), yh.pin_memory()
+    x = xh.to(device)
+    y = yh.to(device)
+    loss_host = torch.zeros(1).pin_memory()
+    if cfg["kind"] == "point":
+        model.set_fps_starts([torch.zeros(B, dtype=torch.long, device=device)] * 2)
+
+    def eager_step():
+        return trainer.step(x, y, lf)
+
+    # launches per step (C-ABI calls; attn_bwd enqueues 3 kernels)
+    L.LAUNCHES = 0
+    n_before = L.LAUNCHES
+    eager_step()
+    torch.cuda.synchronize()
+    launches_per_step = L.LAUNCHES - n_before
+    use_graph = (world == 1) and not args.no_graph
+    step_fn = eager_step
+    graph_note = "eager"
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    eager_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = eager_step()
+
+            def step_fn():
+                graph.replay()
+                return static_loss
+
+            graph_note = "cuda_graph(whole step)"
+        except Exception as exc:  # capture is an optimisation, never a requirement
+            graph_note = f"eager (graph capture failed: {type(exc).__name__})"
+            step_fn = eager_step
+            torch.cuda.synchronize()
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, e2e):
+        """Sum of per-step CUDA-event durations (the L2 flush between steps is outside the event pairs). The e2e
+        variant starts from pinned host buffers and ends when the loss has landed in host memory (host sync per step)."""
+        pairs = []
+        for _ in range(n_steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            if e2e:
+                x.copy_(xh, non_blocking=True)
+                y.copy_(yh, non_blocking=True)
+            loss = step_fn()
+            if e2e:
+                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            e.record()
+            if e2e:
+                e.synchronize()
+            pairs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in pairs)
+
+    for _ in range(max(args.warmup, 3)):
+        step_fn()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    dev_ms = timed(args.steps, e2e=False)
+    barrier()
+    e2e_ms = timed(args.steps, e2e=True)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+
+    # instrumented pass: per-kernel CUDA-event timing of 2 eager steps (separate from the timed region)
+    prof = KernelProfile()
+    orig = prof.wrap(L)
+    try:
+        for _ in range(2):
+            eager_step()
+        fam = prof.summary()
+    finally:
+        L.call = orig
+    if rank != 0:
+        return None
+    pk = peaks()
+    dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    name, f = dom
+    tensor_bound = f["flops"] > 0
+    achieved = (f["flops"] / (f["ms"] * 1e-3) / 1e12) if tensor_bound else (f["bytes"] / (f["ms"] * 1e-3) / 1e9)
+    peak = pk["tf_sustained"] if tensor_bound else pk["hbm"]
+    step_kernel_ms = sum(v["ms"] for v in fam.values())
+    roofline = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": round(achieved, 2),
+                "peak": peak, "peak_source": pk["src"] + (" sustained bf16" if tensor_bound else " copy"),
+                "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "launches_per_step": f["launches"] // 2, "avg_launch_us": round(1e3 * f["ms"] / f["launches"], 2),
+                "share_of_kernel_time": round(f["ms"] / step_kernel_ms, 3),
+                "timing": "cuda events around every C-ABI launch, instrumented eager pass of 2 steps after the timed region",
+                "families_ms_per_step": {k: round(v["ms"] / 2, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
+    samples = B * world * args.steps
+    value = samples * cfg["per_sample"] / (dev_ms * 1e-3)
+    e2e_value = samples * cfg["per_sample"] / (e2e_ms * 1e-3)
+    h2d = xh.numel() * xh.element_size() + yh.numel() * yh.element_size()
+    out = {
+        "metric": "voxels/sec fwd+bwd" if cfg["kind"] == "voxel" else "points/sec fwd+bwd",
+        "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg['model']}, batch {B}/GPU, fwd+bwd+Adam, bf16 operands / fp32 accumulate",
+                   "global_batch": B * world, "parallelism": f"dp{world}", "launch": graph_note,
+                   "l2": "256 MB flush between timed steps; per-step working set (weights + Adam state + activations) >> 126 MB L2",
+                   "samples_per_s": samples / (dev_ms * 1e-3)},
+        "e2e": {"value": e2e_value, "unit": cfg["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms, n = run_cpu(cfg, cfg["cpu_B"], steps=50, warmup=1, budget_s=12.0)
+        out["cpu_baseline"] = {"value": v, "unit": cfg["unit"], "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"oracle port (torch CPU fp32), batch {cfg['cpu_B']} fwd+bwd+Adam, {n} steps, {ms:.0f} ms/step"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        B = cfg["cpu_B"]
+        v, ms, n = run_cpu(cfg, B, steps=args.steps, warmup=args.warmup)
+        cores = torch.get_num_threads()
+        print(json.dumps({
+            "impl": "reference", "metric": "voxels/sec fwd+bwd" if cfg["kind"] == "voxel" else "points/sec fwd+bwd",
+            "value": v, "unit": cfg["unit"], "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {cfg['model']}, CPU fp32, bounded sample batch {B}, fwd+bwd+Adam"},
+            "cpu_baseline": {"value": v, "unit": cfg["unit"], "cores": cores, "kind": "port",
+                             "sample": f"oracle port of the reference modules (torch CPU fp32, {cores} threads), batch {B} per step"},
+            "e2e": {"value": v, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    out = run_ours(args, cfg, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

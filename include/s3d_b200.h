@@ -99,10 +99,11 @@ int s3d_colsum_bf16(const void* in, float* out, int T, int C, int64_t ld, int ac
 int s3d_voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
                            void* stream);
 /* torch.optim.Adam step (train_cls_voxel.py:195) over a flat f32 segment; refreshes the bf16 shadow; grad_scale folds
- * the 1/world_size of the DDP gradient average (train_cls_voxel.py:154-165). */
+ * the 1/world_size of the DDP gradient average (train_cls_voxel.py:154-165). step_device (optional, int32 on the
+ * device) overrides `step` so a captured CUDA graph advances the bias correction on replay. */
 int s3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
-                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                  void* stream);
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, const int* step_device,
+                  float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Point grouping (reference data/pointnet_util.py). xyz f32 [B,N,3], query f32 [B,S,3].

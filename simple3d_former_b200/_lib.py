@@ -34,7 +34,7 @@ SIGNATURES = {
     "s3d_transpose_to_bf16": (c_int, [_P, c_int, _P, c_int, c_int, c_int64, c_int64, _P]),
     "s3d_colsum_bf16": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, _P]),
     "s3d_voxel_patch_gather": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "s3d_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int,
+    "s3d_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, _P,
                               c_float, _P]),
     "s3d_knn": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "s3d_ball_query": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P]),
@@ -233,10 +233,10 @@ def voxel_patch_gather(x, cell, patch, kpad, zsum):
     return P
 
 
-def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, step_tensor=None):
     _need_cuda(p, g, m, v)
     call("s3d_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), float(lr), float(beta1), float(beta2),
-         float(eps), float(weight_decay), int(step), float(grad_scale), stream())
+         float(eps), float(weight_decay), int(step), ptr(step_tensor), float(grad_scale), stream())
 
 
 def knn(xyz, query, K, want_dist=False):

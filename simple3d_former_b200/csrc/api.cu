@@ -137,10 +137,10 @@ int s3d_voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int 
   return s3d::voxel_patch_gather(x, P, B, V, cell, patch, Kpad, zsum, as_stream(stream));
 }
 int s3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
-                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                  void* stream) {
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, const int* step_device,
+                  float grad_scale, void* stream) {
   return s3d::adam_step(param, grad, exp_avg, exp_avg_sq, shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, step,
-                        grad_scale, as_stream(stream));
+                        step_device, grad_scale, as_stream(stream));
 }
 
 int s3d_knn(const float* xyz, const float* query, int64_t* idx, float* dist, int B, int N, int S, int K, void* stream) {

@@ -50,7 +50,8 @@ int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accu
 int voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
                        cudaStream_t stream);
 int adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
-              float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);
+              float beta2, float eps, float weight_decay, int step, const int* step_dev, float grad_scale,
+              cudaStream_t stream);
 
 // attention_mma.cu
 struct AttnParams {

@@ -452,7 +452,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                   float* __restrict__ m, float* __restrict__ v,
                                                   __nv_bfloat16* __restrict__ shadow, size_t n, float lr, float beta1,
                                                   float beta2, float eps, float weight_decay, float bias_corr1,
-                                                  float bias_corr2_sqrt, float grad_scale) {
+                                                  float bias_corr2_sqrt, float grad_scale,
+                                                  const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {  // CUDA-graph replays: the step counter lives on the device
+    const float st = (float)(*step_dev);
+    bias_corr1 = 1.f - powf(beta1, st);
+    bias_corr2_sqrt = sqrtf(1.f - powf(beta2, st));
+  }
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale;
     const float pi = p[i];
@@ -469,16 +475,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 int adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
-              float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream) {
-  if (n <= 0 || step <= 0) return S3D_ERR_BAD_SHAPE;
+              float beta2, float eps, float weight_decay, int step, const int* step_dev, float grad_scale,
+              cudaStream_t stream) {
+  if (n <= 0 || (step <= 0 && step_dev == nullptr)) return S3D_ERR_BAD_SHAPE;
   if (p == nullptr || g == nullptr || m == nullptr || v == nullptr) return S3D_ERR_NULL;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  const float bc1 = 1.f - powf(beta1, (float)(step > 0 ? step : 1));
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)(step > 0 ? step : 1)));
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   adam_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), (size_t)n,
-                                               lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale);
+                                               lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale, step_dev);
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
