@@ -52,12 +52,14 @@ __global__ void __launch_bounds__(128) knn_kernel(const float* __restrict__ xyz,
         if (d < bd[KMAX - 1]) {
           float cd = d;
           int ci = base + j;
+          bool placed = false;  // once the new entry is placed, every later slot shifts down by one (ties included)
 #pragma unroll
           for (int t = 0; t < KMAX; ++t) {
-            if (cd < bd[t]) {
+            if (placed || cd < bd[t]) {
               const float td = bd[t]; const int ti = bi[t];
               bd[t] = cd; bi[t] = ci;
               cd = td; ci = ti;
+              placed = true;
             }
           }
         }
