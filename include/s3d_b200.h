@@ -52,12 +52,14 @@ const char* s3d_error_string(int code);
  *                   DGELU: v *= gelu_erf'(aux_in[m,n]); RELU: v = max(v,0); DRELU: v = aux_in[m,n] > 0 ? v : 0;
  *                   v += residual[m,n]; D = (out_fp32 ? v : bf16(v)).
  *   residual may alias D (fp32 accumulate). batch > 1 runs `batch` independent problems with element strides.
+ *   force_bn / force_cluster / force_splits: 0 = heuristic; otherwise tile N (64/128/256), cluster size along M
+ *   (1/2/4, TMA multicast of the B tile) and split-K factor (fp32 outputs without activation epilogue only).
  * ------------------------------------------------------------------------------------------------------------- */
 int s3d_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldd,
                   int a_mn_major, int b_mn_major, int out_fp32, float alpha, const float* bias, const float* residual,
                   int64_t ldr, int epilogue, const void* aux_in, int64_t ld_aux_in, void* aux_out, int64_t ld_aux_out,
                   int batch, int64_t batch_stride_a, int64_t batch_stride_b, int64_t batch_stride_d,
-                  int64_t batch_stride_r, int force_bn, void* stream);
+                  int64_t batch_stride_r, int force_bn, int force_cluster, int force_splits, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * LayerNorm (timm Block.norm1/norm2, VisionTransformer.norm: eps 1e-6, vit_3d_2d_pretrain.py:287; post-norm layers of

@@ -23,7 +23,7 @@ SIGNATURES = {
     "s3d_error_string": (c_char_p, [c_int]),
     "s3d_gemm_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float,
                               _P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_int64, c_int64, c_int64,
-                              c_int64, c_int, _P]),
+                              c_int64, c_int, c_int, c_int, _P]),
     "s3d_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "s3d_layernorm_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "s3d_attn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64,
@@ -107,7 +107,7 @@ EPI_NONE, EPI_GELU, EPI_DGELU, EPI_RELU, EPI_DRELU = 0, 1, 2, 3, 4
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, alpha=1.0, bias=None, residual=None,
-         epilogue=EPI_NONE, aux_in=None, aux_out=None, force_bn=0):
+         epilogue=EPI_NONE, aux_in=None, aux_out=None, force_bn=0, force_cluster=0, force_splits=0):
     """D[M,N] = epi(alpha * A @ B^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn); 2-D or batched 3-D."""
     _need_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -144,7 +144,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, al
          r2.stride(0) if r2 is not None else 0, epilogue, ptr(aux_in), aux_in.stride(0) if aux_in is not None else 0,
          ptr(aux_out), aux_out.stride(0) if aux_out is not None else 0, batch,
          a.stride(0) if batched else 0, b.stride(0) if batched else 0, out.stride(0) if batched else 0,
-         residual.stride(0) if (batched and residual is not None) else 0, force_bn, stream())
+         residual.stride(0) if (batched and residual is not None) else 0, force_bn, force_cluster, force_splits,
+         stream())
     return out
 
 

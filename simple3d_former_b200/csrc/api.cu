@@ -30,7 +30,7 @@ int s3d_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
                   int a_mn_major, int b_mn_major, int out_fp32, float alpha, const float* bias, const float* residual,
                   int64_t ldr, int epilogue, const void* aux_in, int64_t ld_aux_in, void* aux_out, int64_t ld_aux_out,
                   int batch, int64_t batch_stride_a, int64_t batch_stride_b, int64_t batch_stride_d,
-                  int64_t batch_stride_r, int force_bn, void* stream) {
+                  int64_t batch_stride_r, int force_bn, int force_cluster, int force_splits, void* stream) {
   if (epilogue < S3D_EPI_NONE || epilogue > S3D_EPI_DRELU) return S3D_ERR_UNSUPPORTED;
   if (batch < 1 || batch > 65535) return S3D_ERR_BAD_SHAPE;
   s3d::GemmArgs g;
@@ -44,6 +44,8 @@ int s3d_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
   g.batch_stride_a = batch_stride_a;
   g.batch_stride_b = batch_stride_b;
   g.force_bn = force_bn;
+  g.force_cluster = force_cluster;
+  g.force_splits = force_splits;
   g.p.M = M;
   g.p.N = N;
   g.p.K = K;

@@ -12,6 +12,13 @@
 //   warp 2      : TMEM allocator (2 accumulator stages of BN columns)
 //   warps 4..11 : epilogue; TMEM -> registers (tcgen05.ld 32x32b.x32) -> bias / GELU / dGELU / residual -> HBM
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// L2 -> SM operand traffic is what bounds a 128 x BN tile (48 KB per 4.2 MFLOP at BN = 256 hits the ~6.9 TB/s L2 cap at
+// ~580 TFLOP/s), so CTAs are launched as clusters of CL along M that share the B tile: every CTA loads 1/CL of B and
+// TMA-multicasts it to all CL shared memories; smem slots are released with a multicast tcgen05.commit so a producer
+// only overwrites a slot once every CTA of the cluster has consumed it.
+// Split-K (weight-gradient GEMMs: few output tiles, K = tokens) gives each work item a K range and reduces with
+// red.global.add.v4.f32 into the fp32 output.
 #include "kernels.h"
 
 #include <stdlib.h>
@@ -33,7 +40,7 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const GemmParams p) {
@@ -51,10 +58,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int batch = blockIdx.y;
 
+  static_assert(CL == 1 || (BN / 64) % CL == 0, "every CTA of the cluster loads BN / CL rows (whole 64-wide chunks)");
   const int num_m = (p.M + BM - 1) / BM;
+  const int num_msuper = (num_m + CL - 1) / CL;
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int splits = p.splits;
+  const int kb_per_split = (num_kb_total + splits - 1) / splits;
+  const int num_items = num_msuper * num_n * splits;
+  const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL;
+  const int num_clusters = gridDim.x / CL;
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1);
+  constexpr int kBRowsPerCta = BN / CL;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -63,7 +79,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);  // one multicast commit from every CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -74,48 +90,67 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (m tile of this CTA, n tile, k-block range)
+  auto decode = [&](int item, int& m0, int& n0, int& kb0, int& kb1, int& split) {
+    split = item % splits;
+    const int t = item / splits;
+    n0 = (t % num_n) * BN;
+    m0 = ((t / num_n) * CL + crank) * BM;
+    kb0 = split * kb_per_split;
+    kb1 = min(num_kb_total, kb0 + kb_per_split);
+  };
 
   if (warp == 0) {
     // ------------------------------------------ TMA producer ------------------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM;
-        const int n0 = (tile % num_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        int m0, n0, kb0, kb1, split;
+        decode(item, m0, n0, kb0, kb1, split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = kb * BK;
-          if (p.batched) {
-            if (A_MN) {
+          // A: this CTA's own 128 rows
+          if (A_MN) {
 #pragma unroll
-              for (int i = 0; i < BM / 64; ++i) tma_load_3d(sa + i * 8192, &tma_a, &full_bar[stage], m0 + 64 * i, k0, batch);
-            } else {
-              tma_load_3d(sa, &tma_a, &full_bar[stage], k0, m0, batch);
-            }
-            if (B_MN) {
-#pragma unroll
-              for (int i = 0; i < BN / 64; ++i) tma_load_3d(sb + i * 8192, &tma_b, &full_bar[stage], n0 + 64 * i, k0, batch);
-            } else {
-              tma_load_3d(sb, &tma_b, &full_bar[stage], k0, n0, batch);
+            for (int i = 0; i < BM / 64; ++i) {
+              if (p.batched) tma_load_3d(sa + i * 8192, &tma_a, &full_bar[stage], m0 + 64 * i, k0, batch);
+              else tma_load_2d(sa + i * 8192, &tma_a, &full_bar[stage], m0 + 64 * i, k0);
             }
           } else {
-            if (A_MN) {
+            if (p.batched) tma_load_3d(sa, &tma_a, &full_bar[stage], k0, m0, batch);
+            else tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
+          }
+          // B: 1/CL of the tile, multicast to every CTA of the cluster
+          if (B_MN) {
 #pragma unroll
-              for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &tma_a, &full_bar[stage], m0 + 64 * i, k0);
-            } else {
-              tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
+            for (int i = 0; i < BN / 64 / CL; ++i) {
+              const int ch = crank * (BN / 64 / CL) + i;
+              if (CL > 1) {
+                if (p.batched) tma_load_3d_mc(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0, batch, kMcMask);
+                else tma_load_2d_mc(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0, kMcMask);
+              } else {
+                if (p.batched) tma_load_3d(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0, batch);
+                else tma_load_2d(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0);
+              }
             }
-            if (B_MN) {
-#pragma unroll
-              for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &tma_b, &full_bar[stage], n0 + 64 * i, k0);
+          } else {
+            uint8_t* dst = sb + crank * kBRowsPerCta * 128;
+            const int nrow = n0 + crank * kBRowsPerCta;
+            if (CL > 1) {
+              if (p.batched) tma_load_3d_mc(dst, &tma_b, &full_bar[stage], k0, nrow, batch, kMcMask);
+              else tma_load_2d_mc(dst, &tma_b, &full_bar[stage], k0, nrow, kMcMask);
             } else {
-              tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
+              if (p.batched) tma_load_3d(dst, &tma_b, &full_bar[stage], k0, nrow, batch);
+              else tma_load_2d(dst, &tma_b, &full_bar[stage], k0, nrow);
             }
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -131,11 +166,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        int m0, n0, kb0, kb1, split;
+        decode(item, m0, n0, kb0, kb1, split);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -146,9 +183,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                                         : make_smem_desc_sw128(sa + k * 32, p.k_lbo, p.k_sbo);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, p.mn_lbo, p.mn_sbo)
                                         : make_smem_desc_sw128(sb + k * 32, p.k_lbo, p.k_sbo);
-            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0) || (k != 0));
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in every CTA of the cluster) once these MMAs retire
+          if (CL > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
@@ -166,9 +205,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t aphase = 0;
     const long long boff_d = p.batched ? (long long)batch * p.batch_stride_d : 0;
     const long long boff_r = p.batched ? (long long)batch * p.batch_stride_r : 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * BM;
-      const int n0 = (tile % num_n) * BN;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      int m0, n0, kb0, kb1, split;
+      decode(item, m0, n0, kb0, kb1, split);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
@@ -185,10 +224,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-        if (p.bias != nullptr) {
+        if (p.bias != nullptr && split == 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (full_chunk || n + j < p.N) f[j] += __ldg(p.bias + n + j);
+        }
+        if (splits > 1) {
+          // split-K: reduce the partial tile into fp32 D (zeroed or accumulating); no other epilogue applies
+          if (row_ok && kb1 > kb0) {
+            float* d = reinterpret_cast<float*>(p.D) + boff_d + (long long)row * p.ldd + n;
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) red_add_f32x4(d + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < 32 && n + j < p.N; ++j) atomicAdd(d + j, f[j]);
+            }
+          }
+          continue;
         }
         if (p.epilogue == EPI_GELU) {
           if (p.aux_out != nullptr && row_ok) {
@@ -308,6 +360,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into its smem / barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -370,50 +423,63 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int CL>
 static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
   int rc;
   const GemmParams& p = g.p;
+  constexpr int kBBoxRows = BN / CL;
   if (g.batch > 1) {
     if (A_MN) rc = make_tmap_bf16_3d(&ta, g.A, p.M, p.K, g.batch, g.lda, g.batch_stride_a, 64, 64);
     else rc = make_tmap_bf16_3d(&ta, g.A, p.K, p.M, g.batch, g.lda, g.batch_stride_a, 64, BM);
     if (rc) return rc;
     if (B_MN) rc = make_tmap_bf16_3d(&tb, g.B, p.N, p.K, g.batch, g.ldb, g.batch_stride_b, 64, 64);
-    else rc = make_tmap_bf16_3d(&tb, g.B, p.K, p.N, g.batch, g.ldb, g.batch_stride_b, 64, BN);
+    else rc = make_tmap_bf16_3d(&tb, g.B, p.K, p.N, g.batch, g.ldb, g.batch_stride_b, 64, kBBoxRows);
     if (rc) return rc;
   } else {
     if (A_MN) rc = make_tmap_bf16_2d(&ta, g.A, p.M, p.K, g.lda, 64, 64);
     else rc = make_tmap_bf16_2d(&ta, g.A, p.K, p.M, g.lda, 64, BM);
     if (rc) return rc;
     if (B_MN) rc = make_tmap_bf16_2d(&tb, g.B, p.N, p.K, g.ldb, 64, 64);
-    else rc = make_tmap_bf16_2d(&tb, g.B, p.K, p.N, g.ldb, 64, BN);
+    else rc = make_tmap_bf16_2d(&tb, g.B, p.K, p.N, g.ldb, 64, kBBoxRows);
     if (rc) return rc;
   }
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  int gx = tiles;
+  const int num_m = (p.M + BM - 1) / BM;
+  const int items = ((num_m + CL - 1) / CL) * ((p.N + BN - 1) / BN) * p.splits;
   const int sms = num_sms();
-  const int per_batch_cap = g.batch > 1 ? (sms / g.batch > 0 ? sms / g.batch : 1) : sms;
-  if (gx > per_batch_cap) gx = per_batch_cap;
-  dim3 grid(gx, g.batch > 1 ? g.batch : 1);
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  S3D_LAUNCH_OK();
+  const int nb = g.batch > 1 ? g.batch : 1;
+  int max_clusters = (sms / nb) / CL;
+  if (max_clusters < 1) max_clusters = 1;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL, nb, 1);
+  cfg.blockDim = dim3(kNumThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  S3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return S3D_OK;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int dispatch_major(const GemmArgs& g, cudaStream_t s) {
-  if (g.a_mn == 0 && g.b_mn == 0) return launch_gemm<BN, 0, 0>(g, s);
-  if (g.a_mn == 1 && g.b_mn == 1) return launch_gemm<BN, 1, 1>(g, s);
-  if (g.a_mn == 0 && g.b_mn == 1) return launch_gemm<BN, 0, 1>(g, s);
-  return launch_gemm<BN, 1, 0>(g, s);
+  if (g.a_mn == 0 && g.b_mn == 0) return launch_gemm<BN, 0, 0, CL>(g, s);
+  if (g.a_mn == 1 && g.b_mn == 1) return launch_gemm<BN, 1, 1, CL>(g, s);
+  if (g.a_mn == 0 && g.b_mn == 1) return launch_gemm<BN, 0, 1, CL>(g, s);
+  return launch_gemm<BN, 1, 0, CL>(g, s);
 }
 
 static unsigned env_u32(const char* name, unsigned dflt) {
@@ -424,12 +490,13 @@ static unsigned env_u32(const char* name, unsigned dflt) {
 int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   static const unsigned mn_lbo = env_u32("S3D_DBG_MN_LBO", 8192), mn_sbo = env_u32("S3D_DBG_MN_SBO", 1024);
   static const unsigned k_lbo = env_u32("S3D_DBG_K_LBO", 16), k_sbo = env_u32("S3D_DBG_K_SBO", 1024);
+  static const int env_cluster = (int)env_u32("S3D_GEMM_CLUSTER", 0);
   GemmArgs g = g_in;
   g.p.mn_lbo = mn_lbo;
   g.p.mn_sbo = mn_sbo;
   g.p.k_lbo = k_lbo;
   g.p.k_sbo = k_sbo;
-  const GemmParams& p = g.p;
+  GemmParams& p = g.p;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return S3D_ERR_BAD_SHAPE;
   if (g.A == nullptr || g.B == nullptr || p.D == nullptr) return S3D_ERR_NULL;
   if ((p.epilogue == EPI_DGELU || p.epilogue == EPI_DRELU) && p.aux_in == nullptr) return S3D_ERR_NULL;
@@ -442,21 +509,57 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
     return S3D_ERR_ALIGNMENT;
   if (p.aux_out != nullptr && (p.ld_aux_out % 8 != 0 || (reinterpret_cast<uintptr_t>(p.aux_out) & 15) != 0))
     return S3D_ERR_ALIGNMENT;
+  const int sms = num_sms();
+  const int nb = g.batch > 1 ? g.batch : 1;
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_kb = (p.K + BK - 1) / BK;
   int bn = g.force_bn;
   if (bn == 0) {
-    // BN=256 halves the smem operand traffic per flop; use it only when it still fills the machine.
-    const long long t256 = (long long)((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * (g.batch > 1 ? g.batch : 1);
-    const long long t128 = (long long)((p.M + BM - 1) / BM) * ((p.N + 127) / 128) * (g.batch > 1 ? g.batch : 1);
-    if (p.N > 128 && t256 >= num_sms()) bn = 256;
-    else if (p.N > 64 && t128 >= num_sms() / 2) bn = 128;
-    else if (p.N > 64 && p.N % 128 == 0) bn = 128;
-    else bn = (p.N > 64 && t128 * 2 > num_sms()) ? 128 : 64;
+    // BN=256 halves the smem/L2 operand traffic per flop; prefer it whenever the problem still offers enough tiles
+    // (split-K can recover parallelism for fp32 outputs).
+    const long long t256 = (long long)num_m * ((p.N + 255) / 256) * nb;
+    const long long t128 = (long long)num_m * ((p.N + 127) / 128) * nb;
+    if (p.N > 128 && (t256 >= sms || (p.N % 256 == 0 && t256 * 4 >= sms))) bn = 256;
+    else if (p.N > 64 && (t128 >= sms / 2 || p.N % 128 == 0)) bn = 128;
+    else bn = (p.N > 64 && t128 * 2 > sms) ? 128 : 64;
   }
+  if (bn != 64 && bn != 128 && bn != 256) return S3D_ERR_UNSUPPORTED;
+  const long long tiles = (long long)num_m * ((p.N + bn - 1) / bn) * nb;
+  // split-K: plain fp32 output (optionally accumulating onto itself), too few tiles to fill the machine, long K
+  const bool split_ok = p.out_fp32 && p.epilogue == EPI_NONE && p.aux_out == nullptr &&
+                        (p.residual == nullptr || p.residual == p.D) && nb == 1;
+  int splits = 1;
+  if (g.force_splits > 0) splits = split_ok ? g.force_splits : 1;
+  else if (split_ok && tiles * 2 <= sms && num_kb >= 8) {
+    splits = (int)((2LL * sms + tiles - 1) / tiles);
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > num_kb) splits = num_kb;
+  p.splits = splits;
+  if (splits > 1) {
+    if (p.residual == nullptr) {
+      // partial sums are reduced with red.add: start from zero (row by row when D is a strided view)
+      if (p.ldd == p.N) S3D_CUDA_OK(cudaMemsetAsync(p.D, 0, sizeof(float) * (size_t)p.M * p.N, stream));
+      else S3D_CUDA_OK(cudaMemset2DAsync(p.D, sizeof(float) * p.ldd, 0, sizeof(float) * p.N, p.M, stream));
+    }
+    p.residual = nullptr;  // accumulate-in-place is what the reduction does anyway
+  }
+  // cluster size along M (B-tile multicast): needs >= 2 m-tiles and whole 64-wide chunks of B per CTA
+  int cl = g.force_cluster > 0 ? g.force_cluster : (env_cluster > 0 ? env_cluster : 2);
+  if (cl > bn / 64) cl = bn / 64;
+  if (num_m < 2 || cl < 1) cl = 1;
+  if (cl == 4 && (bn != 256 || num_m < 4)) cl = 2;
+  if (cl == 3 || cl > 4) cl = 2;
   switch (bn) {
-    case 256: return dispatch_major<256>(g, stream);
-    case 128: return dispatch_major<128>(g, stream);
-    case 64: return dispatch_major<64>(g, stream);
-    default: return S3D_ERR_UNSUPPORTED;
+    case 256:
+      if (cl == 4) return dispatch_major<256, 4>(g, stream);
+      if (cl == 2) return dispatch_major<256, 2>(g, stream);
+      return dispatch_major<256, 1>(g, stream);
+    case 128:
+      if (cl == 2) return dispatch_major<128, 2>(g, stream);
+      return dispatch_major<128, 1>(g, stream);
+    default: return dispatch_major<64, 1>(g, stream);
   }
 }
 

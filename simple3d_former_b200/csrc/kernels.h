@@ -24,6 +24,7 @@ struct GemmParams {
   // UMMA smem-descriptor byte offsets (defaults: MN-major LBO 8192 / SBO 1024, K-major LBO 16 / SBO 1024);
   // overridable through S3D_DBG_* environment variables for bring-up on new silicon.
   unsigned mn_lbo, mn_sbo, k_lbo, k_sbo;
+  int splits;  // split-K factor (> 1: fp32 red.add epilogue into a zeroed / accumulating D)
 };
 struct GemmArgs {
   const void* A;
@@ -33,6 +34,8 @@ struct GemmArgs {
   int batch;
   long long batch_stride_a, batch_stride_b;
   int force_bn;
+  int force_cluster;  // 0 = auto
+  int force_splits;   // 0 = auto
   GemmParams p;
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);

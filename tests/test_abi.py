@@ -46,7 +46,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.s3d_layernorm_fwd(None, None, None, None, None, None, None, None, None, 4, 770, 1e-6, None) == -1
     assert lib.s3d_attn_fwd(None, None, None, None, None, 1, 1, 4, 48, 0, 0, 0, 0, 0, 0, 1.0, None) == -2  # head_dim
     assert lib.s3d_gemm_bf16(None, None, None, 0, 1, 1, 8, 8, 8, 0, 0, 0, 1.0, None, None, 0, 0, None, 0, None, 0, 1, 0,
-                             0, 0, 0, 0, None) == -1
+                             0, 0, 0, 0, 0, 0, None) == -1
 
 
 def test_product_raises_without_cuda():

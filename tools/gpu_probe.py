@@ -11,7 +11,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-GROUPS = ["gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
+GROUPS = ["gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
 
 
 def rel_err(a, b):
@@ -23,6 +23,39 @@ def rel_err(a, b):
 
 def report(name, err, tol):
     print(f"  [{'PASS' if err <= tol else 'FAIL'}] {name}: rel_err={err:.3e} (tol {tol:g})", flush=True)
+
+
+def g_gemm_perf():
+    """TFLOP/s of the shapes that dominate cfg3 / cfg2, per (BN, cluster, splits) variant (CUDA events, L2-cold-ish)."""
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(0)
+    shapes = [("fwd qkv  cfg3", 188160, 2304, 768, False, False), ("fwd fc1  cfg3", 188160, 3072, 768, False, False),
+              ("fwd fc2  cfg3", 188160, 768, 3072, False, False), ("dX  fc1  cfg3", 188160, 768, 3072, False, True),
+              ("dW  fc1  cfg3", 3072, 768, 188160, True, True), ("dW  qkv  cfg3", 2304, 768, 188160, True, True),
+              ("fwd fc1  cfg2", 1664, 1536, 384, False, False), ("dW  fc1  cfg2", 1536, 384, 1664, True, True)]
+    for (name, M, N, K, amn, bmn) in shapes:
+        a = torch.randn((K, M) if amn else (M, K), device="cuda").bfloat16()
+        b = torch.randn((K, N) if bmn else (N, K), device="cuda").bfloat16()
+        dw = amn and bmn
+        out = torch.empty(M, N, device="cuda", dtype=torch.float32 if dw else torch.bfloat16)
+        variants = [(256, 1, 0), (256, 2, 0), (256, 4, 0), (128, 2, 0), (128, 1, 0)]
+        if dw:
+            variants += [(256, 2, 1), (256, 1, 1), (128, 2, 0)]
+        for (bn, cl, sp) in variants:
+            if N < bn:
+                continue
+            for _ in range(2):
+                L.gemm(a, b, a_mn=amn, b_mn=bmn, out=out, force_bn=bn, force_cluster=cl, force_splits=sp)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5 if M * N * K > 1e11 else 20
+            s.record()
+            for _ in range(reps):
+                L.gemm(a, b, a_mn=amn, b_mn=bmn, out=out, force_bn=bn, force_cluster=cl, force_splits=sp)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / reps
+            print(f"  [PERF] {name} M{M} N{N} K{K} BN{bn} cl{cl} split{sp}: {ms * 1e3:9.1f} us  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s", flush=True)
 
 
 def g_gemm_k():
@@ -41,6 +74,17 @@ def g_gemm_k():
         out = L.gemm(a, b)  # auto BN, bf16 out
         torch.cuda.synchronize()
         report(f"gemm K-major M{M} N{N} K{K} auto bf16", rel_err(out, ref), 1e-2)
+        for (bn, cl) in ((128, 2), (256, 2), (256, 4), (256, 1)):
+            out = L.gemm(a, b, out_dtype=torch.float32, force_bn=bn, force_cluster=cl)
+            torch.cuda.synchronize()
+            report(f"gemm K-major M{M} N{N} K{K} BN{bn} cluster{cl}", rel_err(out, ref), 2e-3)
+        for sp in (2, 5):
+            out = L.gemm(a, b, out_dtype=torch.float32, force_splits=sp)
+            acc = ref.clone()
+            L.gemm(a, b, out=acc, residual=acc, force_splits=sp)
+            torch.cuda.synchronize()
+            report(f"gemm K-major M{M} N{N} K{K} splitK{sp}", rel_err(out, ref), 2e-3)
+            report(f"gemm K-major M{M} N{N} K{K} splitK{sp} accumulate", rel_err(acc, 2 * ref), 2e-3)
 
 
 def g_gemm_mn():
@@ -61,6 +105,12 @@ def g_gemm_mn():
             report(f"gemm A-MN     M{M} N{N} K{K} BN{bn}", rel_err(o1, ref), 2e-3)
             report(f"gemm B-MN     M{M} N{N} K{K} BN{bn}", rel_err(o2, ref), 2e-3)
             report(f"gemm A-MN B-MN M{M} N{N} K{K} BN{bn}", rel_err(o3, ref), 2e-3)
+        for (bn, cl, sp) in ((256, 2, 0), (256, 4, 3), (128, 2, 7), (256, 1, 2)):
+            o2 = L.gemm(a, bt, b_mn=True, out_dtype=torch.float32, force_bn=bn, force_cluster=cl, force_splits=sp)
+            o3 = L.gemm(at, bt, a_mn=True, b_mn=True, out_dtype=torch.float32, force_bn=bn, force_cluster=cl, force_splits=sp)
+            torch.cuda.synchronize()
+            report(f"gemm B-MN      M{M} N{N} K{K} BN{bn} cluster{cl} split{sp}", rel_err(o2, ref), 2e-3)
+            report(f"gemm A-MN B-MN M{M} N{N} K{K} BN{bn} cluster{cl} split{sp}", rel_err(o3, ref), 2e-3)
 
 
 def g_gemm_epi():
