@@ -8,6 +8,8 @@
 // both consumed in place (no permute/contiguous copies).
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace s3d {
 
 // ------------------------------------------------------------------------------------------------
@@ -627,6 +629,12 @@ int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream) {
   int rc = check_attn(p, DH);
   if (rc) return rc;
   if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.out == nullptr) return S3D_ERR_NULL;
+  // long sequences run on the tcgen05 / TMEM flash kernel; everything else on the warp-level mma.sync kernels
+  static const bool tc_enabled = []() { const char* v = getenv("S3D_ATTN_TC"); return v == nullptr || v[0] != '0'; }();
+  if (tc_enabled && (DH == 192 || DH == 64) && p.N >= 512) {
+    const int rc_tc = attn_fwd_tc(p, DH, stream);
+    if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;
+  }
   switch (DH) {
     case 64: return attn_fwd_dh<64>(p, stream);
     case 192: return attn_fwd_dh<192>(p, stream);

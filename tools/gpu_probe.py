@@ -11,7 +11,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-GROUPS = ["gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
+GROUPS = ["attn_tc", "gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
 
 
 def rel_err(a, b):
@@ -232,6 +232,38 @@ def _make_qkv(B, N, H, dh, layout):
         out = torch.empty(N, B, H, dh, device="cuda", dtype=torch.bfloat16)
         perm = lambda t: t.permute(1, 2, 0, 3)
     return qkv, q, k, v, qs, os_, out, perm
+
+
+def g_attn_tc():
+    """tcgen05 flash attention (long sequences): correctness vs torch and TFLOP/s (S3D_ATTN_TC=0 -> mma.sync kernels)."""
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(11)
+    print("  S3D_ATTN_TC =", os.environ.get("S3D_ATTN_TC", "1"), flush=True)
+    for (B, N, H, dh, layout) in [(2, 1024, 4, 192, "seqfirst"), (3, 700, 4, 192, "seqfirst"), (2, 12544, 4, 192, "seqfirst"),
+                                  (2, 513, 3, 64, "timm"), (3, 640, 2, 192, "timm"), (1, 2048, 3, 64, "timm")]:
+        qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
+        lse = torch.empty(B, H, N, device="cuda")
+        scale = dh ** -0.5
+        L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale)
+        torch.cuda.synchronize()
+        ro, rl = _attn_ref(perm(q), perm(k), perm(v), scale)
+        report(f"attn fwd out B{B} N{N} H{H} dh{dh} {layout}", rel_err(perm(out), ro), 1.5e-2)
+        report(f"attn fwd lse B{B} N{N} H{H} dh{dh} {layout}", rel_err(lse, rl), 1e-3)
+        del ro, rl
+    B, N, H, dh = 15, 12544, 4, 192
+    qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, "seqfirst")
+    lse = torch.empty(B, H, N, device="cuda")
+    for _ in range(2):
+        L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, dh ** -0.5)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(5):
+        L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, dh ** -0.5)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 5
+    print(f"  [PERF] attn fwd group_embed shape B15 H4 S12544 dh192: {ms:.2f} ms  {4.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
 def g_attn_fwd():
