@@ -648,6 +648,11 @@ int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream) {
   if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.o == nullptr || p.dout == nullptr || p.dq == nullptr ||
       p.dk == nullptr || p.dv == nullptr || p.lse == nullptr || p.delta == nullptr)
     return S3D_ERR_NULL;
+  static const bool tc_enabled = []() { const char* v = getenv("S3D_ATTN_TC"); return v == nullptr || v[0] != '0'; }();
+  if (tc_enabled && (DH == 192 || DH == 64) && p.N >= 512) {
+    const int rc_tc = attn_bwd_tc(p, DH, stream);
+    if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;
+  }
   switch (DH) {
     case 64: return attn_bwd_dh<64>(p, stream);
     case 192: return attn_bwd_dh<192>(p, stream);

@@ -330,6 +330,551 @@ static int fa_fwd_launch(const AttnParams& a, cudaStream_t stream) {
   return S3D_OK;
 }
 
+// ================================================================================================
+// Backward on tcgen05. Two kernels (no atomics, no dQ round trips through HBM):
+//   dQ   : CTA = 128 query rows; per 64-key block  S = Q K^T, dP = dO V^T (TMEM, double buffered),
+//          dS = P o (dP - delta) -> bf16 smem,  dQ += dS K  (K block re-read as an MN-major B operand)
+//   dKdV : CTA = 128 key rows; per 64-query block S^T = K Q^T, dP^T = V dO^T,  P^T / dS^T -> bf16 smem,
+//          dV += P^T dO,  dK += dS^T Q  (Q / dO blocks re-read as MN-major B operands)
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 element-wise (one TMEM lane = one row each).
+// ================================================================================================
+struct FaBwdParams {
+  __nv_bfloat16 *dq, *dk, *dv;  // outputs, qkv strides
+  const float* lse;
+  const float* delta;
+  int N, H;
+  long long row_bs, col_bs;      // qkv 2-D view
+  int col_q, col_k, col_v;
+  long long o_row_bs, o_col_bs;  // dout 2-D view
+  long long qkv_bs, qkv_hs, qkv_rs;
+  float scale;
+};
+
+constexpr int kFaBwdThreads = 192;
+
+template <int DH>
+struct FaBwdCfg {
+  static constexpr int kTileBytes = 128 * DH * 2;   // 128-row operand tile
+  static constexpr int kBlkBytes = 64 * DH * 2;     // 64-row streamed block
+  static constexpr int kSBytes = 128 * 64 * 2;      // bf16 P / dS tile
+  static constexpr int kSmemBytes = 2 * kTileBytes + 4 * kBlkBytes + 2 * kSBytes + 1024 + 1024;
+};
+
+__device__ __forceinline__ void store_row_bf16_sw128(uint8_t* row_base, int r, const float (&e)[64]) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint4 u;
+    u.x = pack_bf16x2(e[ch * 8 + 0], e[ch * 8 + 1]);
+    u.y = pack_bf16x2(e[ch * 8 + 2], e[ch * 8 + 3]);
+    u.z = pack_bf16x2(e[ch * 8 + 4], e[ch * 8 + 5]);
+    u.w = pack_bf16x2(e[ch * 8 + 6], e[ch * 8 + 7]);
+    *reinterpret_cast<uint4*>(row_base + ((ch ^ (r & 7)) << 4)) = u;
+  }
+}
+
+// ------------------------------------------------ dQ ------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(kFaBwdThreads, 1)
+fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_constant__ CUtensorMap tma_kv64,
+                    const __grid_constant__ CUtensorMap tma_do128, const FaBwdParams p) {
+  using Cfg = FaBwdCfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                          // [DH/64][128][128B]
+  uint8_t* sdO = sQ + Cfg::kTileBytes;         // [DH/64][128][128B]
+  uint8_t* sK = sdO + Cfg::kTileBytes;         // [2][DH/64][64][128B]
+  uint8_t* sV = sK + 2 * Cfg::kBlkBytes;       // [2][DH/64][64][128B]
+  uint8_t* sdS = sV + 2 * Cfg::kBlkBytes;      // [2][128][128B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * Cfg::kSBytes);
+  uint64_t* qdo_full = bars;       // [1]
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* v_full = bars + 3;     // [2]
+  uint64_t* kv_empty = bars + 5;   // [2]
+  uint64_t* sp_full = bars + 7;    // [2]
+  uint64_t* ds_full = bars + 9;    // [2]
+  uint64_t* dq_full = bars + 11;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 128;
+  const int nkv = (p.N + 63) / 64;
+  const int row_base = (int)(b * p.row_bs);
+  const int cq = (int)(b * p.col_bs) + p.col_q + h * DH;
+  const int ck = (int)(b * p.col_bs) + p.col_k + h * DH;
+  const int cv = (int)(b * p.col_bs) + p.col_v + h * DH;
+  const int o_row_base = (int)(b * p.o_row_bs);
+  const int co = (int)(b * p.o_col_bs) + h * DH;
+  constexpr int kColS = DH;  // TMEM: dQ [0,DH)  then per buffer u: S [DH + 128u, +64), dP [DH + 128u + 64, +64)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q128);
+    tma_prefetch_desc(&tma_kv64);
+    tma_prefetch_desc(&tma_do128);
+    mbar_init(qdo_full, 1);
+    mbar_init(dq_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&sp_full[i], 1);
+      mbar_init(&ds_full[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(qdo_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+      for (int c = 0; c < DH / 64; ++c) {
+        tma_load_2d(sQ + c * (128 * 128), &tma_q128, qdo_full, cq + 64 * c, row_base + q0);
+        tma_load_2d(sdO + c * (128 * 128), &tma_do128, qdo_full, co + 64 * c, o_row_base + q0);
+      }
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::kBlkBytes);
+#pragma unroll
+        for (int c = 0; c < DH / 64; ++c)
+          tma_load_2d(sK + st * Cfg::kBlkBytes + c * (64 * 128), &tma_kv64, &k_full[st], ck + 64 * c, row_base + j * 64);
+        mbar_expect_tx(&v_full[st], Cfg::kBlkBytes);
+#pragma unroll
+        for (int c = 0; c < DH / 64; ++c)
+          tma_load_2d(sV + st * Cfg::kBlkBytes + c * (64 * 128), &tma_kv64, &v_full[st], cv + 64 * c, row_base + j * 64);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_q = make_idesc_bf16(128, DH, 0, 1);
+      auto issue_s_dp = [&](int u, int st) {
+        const uint32_t aq = smem_u32(sQ), ao = smem_u32(sdO);
+        const uint32_t bk = smem_u32(sK + st * Cfg::kBlkBytes), bv = smem_u32(sV + st * Cfg::kBlkBytes);
+        const uint32_t ds_ = tmem_base + kColS + u * 128, dp_ = ds_ + 64;
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {
+          const uint32_t offa = (kk >> 2) * (128 * 128) + (kk & 3) * 32, offb = (kk >> 2) * (64 * 128) + (kk & 3) * 32;
+          umma_f16_ss(ds_, make_smem_desc_sw128(aq + offa, 16, 1024), make_smem_desc_sw128(bk + offb, 16, 1024), idesc_s, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {
+          const uint32_t offa = (kk >> 2) * (128 * 128) + (kk & 3) * 32, offb = (kk >> 2) * (64 * 128) + (kk & 3) * 32;
+          umma_f16_ss(dp_, make_smem_desc_sw128(ao + offa, 16, 1024), make_smem_desc_sw128(bv + offb, 16, 1024), idesc_s, kk != 0);
+        }
+        umma_commit(&sp_full[u]);
+      };
+      mbar_wait(qdo_full, 0);
+      mbar_wait(&k_full[0], 0);
+      mbar_wait(&v_full[0], 0);
+      tc_fence_after();
+      issue_s_dp(0, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int u = j & 1, st = j & 1;
+        if (j + 1 < nkv) {
+          mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
+          mbar_wait(&v_full[st ^ 1], ((j + 1) >> 1) & 1);
+          // TMEM buffer u^1 was released by ds_full[u^1] of block j-1 (waited below in the previous iteration)
+          tc_fence_after();
+          issue_s_dp(u ^ 1, st ^ 1);
+        }
+        mbar_wait(&ds_full[u], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sdS + u * Cfg::kSBytes);
+        const uint32_t b0 = smem_u32(sK + st * Cfg::kBlkBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16_ss(tmem_base, make_smem_desc_sw128(a0 + kk * 32, 16, 1024),
+                      make_smem_desc_sw128(b0 + kk * 2048, 64 * 128, 1024), idesc_q, (j > 0) || (kk != 0));
+        umma_commit(&kv_empty[st]);
+      }
+      umma_commit(dq_full);
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int row = q0 + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const long long bh = (long long)b * p.H + h;
+    const float lse2 = row < p.N ? p.lse[bh * p.N + row] * kFaLog2e : INFINITY;
+    const float del = row < p.N ? p.delta[bh * p.N + row] : 0.f;
+    const float c = p.scale * kFaLog2e;
+    for (int j = 0; j < nkv; ++j) {
+      const int u = j & 1;
+      mbar_wait(&sp_full[u], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t a0[32], a1[32], d0[32], d1[32];
+      const uint32_t s_addr = tmem_base + lane_addr + kColS + u * 128;
+      tmem_ld_32x32b_x32(s_addr, a0);
+      tmem_ld_32x32b_x32(s_addr + 32, a1);
+      tmem_ld_32x32b_x32(s_addr + 64, d0);
+      tmem_ld_32x32b_x32(s_addr + 96, d1);
+      tc_wait_ld();
+      float e[64];
+      const int key0 = j * 64;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float p0 = (key0 + i < p.N) ? fast_exp2(__uint_as_float(a0[i]) * c - lse2) : 0.f;
+        const float p1 = (key0 + 32 + i < p.N) ? fast_exp2(__uint_as_float(a1[i]) * c - lse2) : 0.f;
+        e[i] = p0 * (__uint_as_float(d0[i]) - del);
+        e[32 + i] = p1 * (__uint_as_float(d1[i]) - del);
+      }
+      store_row_bf16_sw128(sdS + u * Cfg::kSBytes + r * 128, r, e);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&ds_full[u]);
+    }
+    mbar_wait(dq_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = p.dq + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)row * p.qkv_rs;
+#pragma unroll 1
+    for (int cc = 0; cc < DH; cc += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + cc, o);
+      tc_wait_ld();
+      if (row < p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[i]) * p.scale, __uint_as_float(o[i + 1]) * p.scale);
+          w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * p.scale, __uint_as_float(o[i + 3]) * p.scale);
+          w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * p.scale, __uint_as_float(o[i + 5]) * p.scale);
+          w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * p.scale, __uint_as_float(o[i + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(orow + cc + i) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------- dK, dV -----------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(kFaBwdThreads, 1)
+fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid_constant__ CUtensorMap tma_q64,
+                     const __grid_constant__ CUtensorMap tma_do64, const FaBwdParams p) {
+  using Cfg = FaBwdCfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                          // [DH/64][128][128B]
+  uint8_t* sV = sK + Cfg::kTileBytes;
+  uint8_t* sQ = sV + Cfg::kTileBytes;          // [2][DH/64][64][128B]
+  uint8_t* sdO = sQ + 2 * Cfg::kBlkBytes;      // [2][DH/64][64][128B]
+  uint8_t* sPT = sdO + 2 * Cfg::kBlkBytes;     // [128][128B]
+  uint8_t* sdST = sPT + Cfg::kSBytes;          // [128][128B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdST + Cfg::kSBytes);
+  uint64_t* kv_full = bars;        // [1]
+  uint64_t* q_full = bars + 1;     // [2]
+  uint64_t* do_full = bars + 3;    // [2]
+  uint64_t* qdo_empty = bars + 5;  // [2]
+  uint64_t* sp_full = bars + 7;    // [1] S^T and dP^T complete
+  uint64_t* s_free = bars + 8;     // [1] element-wise warps hold S^T / dP^T in registers
+  uint64_t* pds_full = bars + 9;   // [1] P^T / dS^T written to smem
+  uint64_t* pds_free = bars + 10;  // [1] dV / dK MMAs that read P^T / dS^T retired
+  uint64_t* acc_full = bars + 11;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* s_lse = reinterpret_cast<float*>(bars + 16);  // [2][64]
+  float* s_del = s_lse + 128;                          // [2][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int k0 = blockIdx.x * 128;
+  const int nq = (p.N + 63) / 64;
+  const int row_base = (int)(b * p.row_bs);
+  const int cq = (int)(b * p.col_bs) + p.col_q + h * DH;
+  const int ck = (int)(b * p.col_bs) + p.col_k + h * DH;
+  const int cv = (int)(b * p.col_bs) + p.col_v + h * DH;
+  const int o_row_base = (int)(b * p.o_row_bs);
+  const int co = (int)(b * p.o_col_bs) + h * DH;
+  constexpr int kColS = 2 * DH;  // TMEM: dV [0,DH) dK [DH,2DH) S^T [2DH,+64) dP^T [2DH+64,+64)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_kv128);
+    tma_prefetch_desc(&tma_q64);
+    tma_prefetch_desc(&tma_do64);
+    mbar_init(kv_full, 1);
+    mbar_init(sp_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(pds_full, 128);
+    mbar_init(pds_free, 1);
+    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&do_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+      for (int c = 0; c < DH / 64; ++c) {
+        tma_load_2d(sK + c * (128 * 128), &tma_kv128, kv_full, ck + 64 * c, row_base + k0);
+        tma_load_2d(sV + c * (128 * 128), &tma_kv128, kv_full, cv + 64 * c, row_base + k0);
+      }
+      for (int j = 0; j < nq; ++j) {
+        const int st = j & 1;
+        mbar_wait(&qdo_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], Cfg::kBlkBytes);
+#pragma unroll
+        for (int c = 0; c < DH / 64; ++c)
+          tma_load_2d(sQ + st * Cfg::kBlkBytes + c * (64 * 128), &tma_q64, &q_full[st], cq + 64 * c, row_base + j * 64);
+        mbar_expect_tx(&do_full[st], Cfg::kBlkBytes);
+#pragma unroll
+        for (int c = 0; c < DH / 64; ++c)
+          tma_load_2d(sdO + st * Cfg::kBlkBytes + c * (64 * 128), &tma_do64, &do_full[st], co + 64 * c, o_row_base + j * 64);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_a = make_idesc_bf16(128, DH, 0, 1);
+      auto issue_st_dpt = [&](int st) {
+        const uint32_t ak = smem_u32(sK), av = smem_u32(sV);
+        const uint32_t bq = smem_u32(sQ + st * Cfg::kBlkBytes), bo = smem_u32(sdO + st * Cfg::kBlkBytes);
+        const uint32_t dst = tmem_base + kColS, ddp = dst + 64;
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {
+          const uint32_t offa = (kk >> 2) * (128 * 128) + (kk & 3) * 32, offb = (kk >> 2) * (64 * 128) + (kk & 3) * 32;
+          umma_f16_ss(dst, make_smem_desc_sw128(ak + offa, 16, 1024), make_smem_desc_sw128(bq + offb, 16, 1024), idesc_s, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {
+          const uint32_t offa = (kk >> 2) * (128 * 128) + (kk & 3) * 32, offb = (kk >> 2) * (64 * 128) + (kk & 3) * 32;
+          umma_f16_ss(ddp, make_smem_desc_sw128(av + offa, 16, 1024), make_smem_desc_sw128(bo + offb, 16, 1024), idesc_s, kk != 0);
+        }
+        umma_commit(sp_full);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&do_full[0], 0);
+      tc_fence_after();
+      issue_st_dpt(0);
+      for (int j = 0; j < nq; ++j) {
+        const int st = j & 1;
+        if (j + 1 < nq) {
+          mbar_wait(&q_full[st ^ 1], ((j + 1) >> 1) & 1);
+          mbar_wait(&do_full[st ^ 1], ((j + 1) >> 1) & 1);
+          mbar_wait(s_free, j & 1);  // S^T / dP^T of block j are in registers: the TMEM columns can be overwritten
+          tc_fence_after();
+          issue_st_dpt(st ^ 1);
+        }
+        mbar_wait(pds_full, j & 1);
+        tc_fence_after();
+        const uint32_t ap = smem_u32(sPT), as_ = smem_u32(sdST);
+        const uint32_t bo = smem_u32(sdO + st * Cfg::kBlkBytes), bq = smem_u32(sQ + st * Cfg::kBlkBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO
+          umma_f16_ss(tmem_base, make_smem_desc_sw128(ap + kk * 32, 16, 1024),
+                      make_smem_desc_sw128(bo + kk * 2048, 64 * 128, 1024), idesc_a, (j > 0) || (kk != 0));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q
+          umma_f16_ss(tmem_base + DH, make_smem_desc_sw128(as_ + kk * 32, 16, 1024),
+                      make_smem_desc_sw128(bq + kk * 2048, 64 * 128, 1024), idesc_a, (j > 0) || (kk != 0));
+        umma_commit(&qdo_empty[st]);
+        umma_commit(pds_free);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;        // key row within the tile
+    const int tid = threadIdx.x - 64;      // 0..127 within the element-wise group
+    const int krow = k0 + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const long long bh = (long long)b * p.H + h;
+    const float c = p.scale * kFaLog2e;
+    for (int j = 0; j < nq; ++j) {
+      const int u = j & 1;
+      {  // stage lse / delta of this query block (padded queries: lse = +inf -> P = 0)
+        const int qi = j * 64 + (tid & 63);
+        if (tid < 64) s_lse[u * 64 + tid] = qi < p.N ? p.lse[bh * p.N + qi] * kFaLog2e : INFINITY;
+        else s_del[u * 64 + (tid & 63)] = qi < p.N ? p.delta[bh * p.N + qi] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sp_full, j & 1);
+      tc_fence_after();
+      uint32_t a0[32], a1[32], d0[32], d1[32];
+      const uint32_t s_addr = tmem_base + lane_addr + kColS;
+      tmem_ld_32x32b_x32(s_addr, a0);
+      tmem_ld_32x32b_x32(s_addr + 32, a1);
+      tmem_ld_32x32b_x32(s_addr + 64, d0);
+      tmem_ld_32x32b_x32(s_addr + 96, d1);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      float pt[64], ds[64];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float p0 = fast_exp2(__uint_as_float(a0[i]) * c - s_lse[u * 64 + i]);
+        const float p1 = fast_exp2(__uint_as_float(a1[i]) * c - s_lse[u * 64 + 32 + i]);
+        pt[i] = p0;
+        pt[32 + i] = p1;
+        ds[i] = p0 * (__uint_as_float(d0[i]) - s_del[u * 64 + i]);
+        ds[32 + i] = p1 * (__uint_as_float(d1[i]) - s_del[u * 64 + 32 + i]);
+      }
+      if (j > 0) mbar_wait(pds_free, (j - 1) & 1);  // dV / dK MMAs of block j-1 no longer read the smem tiles
+      store_row_bf16_sw128(sPT + r * 128, r, pt);
+      store_row_bf16_sw128(sdST + r * 128, r, ds);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* kr = p.dk + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
+    __nv_bfloat16* vr = p.dv + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
+#pragma unroll 1
+    for (int cc = 0; cc < DH; cc += 32) {
+      uint32_t ov[32], ok[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + cc, ov);
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + DH + cc, ok);
+      tc_wait_ld();
+      if (krow < p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(ov[i]), __uint_as_float(ov[i + 1]));
+          w.y = pack_bf16x2(__uint_as_float(ov[i + 2]), __uint_as_float(ov[i + 3]));
+          w.z = pack_bf16x2(__uint_as_float(ov[i + 4]), __uint_as_float(ov[i + 5]));
+          w.w = pack_bf16x2(__uint_as_float(ov[i + 6]), __uint_as_float(ov[i + 7]));
+          *reinterpret_cast<uint4*>(vr + cc + i) = w;
+          w.x = pack_bf16x2(__uint_as_float(ok[i]) * p.scale, __uint_as_float(ok[i + 1]) * p.scale);
+          w.y = pack_bf16x2(__uint_as_float(ok[i + 2]) * p.scale, __uint_as_float(ok[i + 3]) * p.scale);
+          w.z = pack_bf16x2(__uint_as_float(ok[i + 4]) * p.scale, __uint_as_float(ok[i + 5]) * p.scale);
+          w.w = pack_bf16x2(__uint_as_float(ok[i + 6]) * p.scale, __uint_as_float(ok[i + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(kr + cc + i) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+__global__ void __launch_bounds__(256) fa_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                      float* __restrict__ delta, int B, int H, int N, int DH, long long o_bs,
+                                                      long long o_hs, long long o_rs) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)B * H * N) return;
+  const int i = (int)(warp % N);
+  const long long bh = warp / N;
+  const long long off = (bh / H) * o_bs + (bh % H) * o_hs + (long long)i * o_rs;
+  float s = 0.f;
+  for (int d = lane * 2; d < DH; d += 64) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + off + d));
+    const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + off + d));
+    s += a.x * g.x + a.y * g.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) delta[warp] = s;
+}
+
+template <int DH>
+static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
+  using Cfg = FaBwdCfg<DH>;
+  const long long E = (long long)a.H * DH;
+  if (a.k - a.q != E || a.v - a.q != 2 * E || a.qkv_hs != DH || a.o_hs != DH) return S3D_ERR_UNSUPPORTED;
+  if (a.dk - a.dq != E || a.dv - a.dq != 2 * E) return S3D_ERR_UNSUPPORTED;
+  FaBwdParams p{};
+  long long rows_total, width, o_width;
+  if (a.qkv_rs == 3 * E && (a.qkv_bs == (long long)a.N * 3 * E || a.B == 1) && a.o_rs == E &&
+      (a.o_bs == (long long)a.N * E || a.B == 1)) {  // timm
+    rows_total = (long long)a.B * a.N;
+    width = 3 * E;
+    o_width = E;
+    p.row_bs = a.N;
+    p.col_bs = 0;
+    p.o_row_bs = a.N;
+    p.o_col_bs = 0;
+  } else if (a.qkv_bs == 3 * E && a.qkv_rs == (long long)a.B * 3 * E && a.o_bs == E && a.o_rs == (long long)a.B * E) {
+    rows_total = a.N;  // sequence-first
+    width = (long long)a.B * 3 * E;
+    o_width = (long long)a.B * E;
+    p.row_bs = 0;
+    p.col_bs = 3 * E;
+    p.o_row_bs = 0;
+    p.o_col_bs = E;
+  } else {
+    return S3D_ERR_UNSUPPORTED;
+  }
+  if (a.B > 65535 || a.H > 65535) return S3D_ERR_BAD_SHAPE;
+  CUtensorMap t128, t64, d128, d64;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&t128, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&t64, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&d128, a.dout, (uint64_t)o_width, (uint64_t)rows_total, (uint64_t)a.o_rs, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&d64, a.dout, (uint64_t)o_width, (uint64_t)rows_total, (uint64_t)a.o_rs, 64, 64))) return rc;
+  p.dq = a.dq;
+  p.dk = a.dk;
+  p.dv = a.dv;
+  p.lse = a.lse;
+  p.delta = a.delta;
+  p.N = a.N;
+  p.H = a.H;
+  p.col_q = 0;
+  p.col_k = (int)E;
+  p.col_v = (int)(2 * E);
+  p.qkv_bs = a.qkv_bs;
+  p.qkv_hs = a.qkv_hs;
+  p.qkv_rs = a.qkv_rs;
+  p.scale = a.scale;
+  {
+    const long long rows = (long long)a.B * a.H * a.N;
+    fa_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a.o, a.dout, a.delta, a.B, a.H, a.N, DH, a.o_bs, a.o_hs, a.o_rs);
+    S3D_LAUNCH_OK();
+  }
+  auto kq = fa_bwd_dq_tc_kernel<DH>;
+  auto kkv = fa_bwd_dkv_tc_kernel<DH>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    S3D_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    S3D_CUDA_OK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((a.N + 127) / 128, a.H, a.B);
+  kkv<<<grid, kFaBwdThreads, Cfg::kSmemBytes, stream>>>(t128, t64, d64, p);
+  S3D_LAUNCH_OK();
+  kq<<<grid, kFaBwdThreads, Cfg::kSmemBytes, stream>>>(t128, t64, d128, p);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+int attn_bwd_tc(const AttnParams& p, int DH, cudaStream_t stream) {
+  if (p.B <= 0 || p.H <= 0 || p.N <= 0) return S3D_ERR_BAD_SHAPE;
+  switch (DH) {
+    case 192: return fa_bwd_launch<192>(p, stream);
+    case 64: return fa_bwd_launch<64>(p, stream);
+    default: return S3D_ERR_UNSUPPORTED;
+  }
+}
+
 int attn_fwd_tc(const AttnParams& p, int DH, cudaStream_t stream) {
   if (p.B <= 0 || p.H <= 0 || p.N <= 0) return S3D_ERR_BAD_SHAPE;
   switch (DH) {

@@ -73,6 +73,7 @@ int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream);
 int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream);
 // attention_tcgen05.cu (long sequences, dh in {64, 192}); S3D_ERR_UNSUPPORTED -> caller falls back to the mma.sync kernels
 int attn_fwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
+int attn_bwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
 
 // pointops.cu
 int knn(const float* xyz, const float* query, long long* idx, float* dist, int B, int N, int S, int K,

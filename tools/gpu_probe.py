@@ -251,19 +251,55 @@ def g_attn_tc():
         report(f"attn fwd out B{B} N{N} H{H} dh{dh} {layout}", rel_err(perm(out), ro), 1.5e-2)
         report(f"attn fwd lse B{B} N{N} H{H} dh{dh} {layout}", rel_err(lse, rl), 1e-3)
         del ro, rl
+    # backward
+    for (B, N, H, dh, layout) in [(2, 1024, 4, 192, "seqfirst"), (3, 700, 4, 192, "seqfirst"), (1, 12544, 4, 192, "seqfirst"),
+                                  (2, 513, 3, 64, "timm"), (3, 640, 2, 192, "timm")]:
+        qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
+        lse = torch.empty(B, H, N, device="cuda")
+        delta = torch.empty(B, H, N, device="cuda")
+        scale = dh ** -0.5
+        L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale)
+        dout = torch.randn_like(out.float()).bfloat16()
+        dqkv = torch.zeros_like(qkv)
+        dq, dk, dv = dqkv.select(2, 0), dqkv.select(2, 1), dqkv.select(2, 2)
+        L.attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out, dout, lse, delta, dq.data_ptr(), dk.data_ptr(),
+                   dv.data_ptr(), B, H, N, dh, qs, os_, scale)
+        torch.cuda.synchronize()
+        qr = perm(q).float().detach().requires_grad_(True)
+        kr = perm(k).float().detach().requires_grad_(True)
+        vr = perm(v).float().detach().requires_grad_(True)
+        s = (qr @ kr.transpose(-1, -2)) * scale
+        (s.softmax(-1) @ vr).backward(perm(dout).float())
+        del s
+        report(f"attn bwd dq B{B} N{N} H{H} dh{dh} {layout}", rel_err(perm(dq), qr.grad), 2e-2)
+        report(f"attn bwd dk B{B} N{N} H{H} dh{dh} {layout}", rel_err(perm(dk), kr.grad), 2e-2)
+        report(f"attn bwd dv B{B} N{N} H{H} dh{dh} {layout}", rel_err(perm(dv), vr.grad), 2e-2)
+        del qr, kr, vr
     B, N, H, dh = 15, 12544, 4, 192
     qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, "seqfirst")
     lse = torch.empty(B, H, N, device="cuda")
-    for _ in range(2):
-        L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, dh ** -0.5)
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(5):
-        L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, dh ** -0.5)
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / 5
+    delta = torch.empty(B, H, N, device="cuda")
+    dout = torch.randn_like(out.float()).bfloat16()
+    dqkv = torch.zeros_like(qkv)
+    dq, dk, dv = dqkv.select(2, 0), dqkv.select(2, 1), dqkv.select(2, 2)
+
+    def timeit(fn, reps=5):
+        for _ in range(2):
+            fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+    ms = timeit(lambda: L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, dh ** -0.5))
     print(f"  [PERF] attn fwd group_embed shape B15 H4 S12544 dh192: {ms:.2f} ms  {4.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s", flush=True)
+    ms = timeit(lambda: L.attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out, dout, lse, delta, dq.data_ptr(),
+                                   dk.data_ptr(), dv.data_ptr(), B, H, N, dh, qs, os_, dh ** -0.5))
+    print(f"  [PERF] attn bwd group_embed shape B15 H4 S12544 dh192: {ms:.2f} ms  {10.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s "
+          f"(algorithmic 5 GEMMs; 7 executed)", flush=True)
 
 
 def g_attn_fwd():
