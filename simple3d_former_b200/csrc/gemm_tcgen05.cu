@@ -22,6 +22,7 @@
 #include "kernels.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace s3d {
 
@@ -37,17 +38,124 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = (BN >= 128) ? 8 * 4096 : 0;  // TMA-store staging (BN = 64 stores directly)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+
+// ---------------------------------------- epilogue helpers ----------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// accumulator chunk (32 columns of this thread's row) -> alpha, bias
+__device__ __forceinline__ void epi_load(const GemmParams& p, uint32_t taddr, int n, int split, float (&f)[32]) {
+  uint32_t v[32];
+  tmem_ld_32x32b_x32(taddr, v);
+  tc_wait_ld();
+  const bool full = (n + 32 <= p.N);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+  if (p.bias != nullptr && split == 0 && n < p.N) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+      }
+    } else {
+      for (int j = 0; j < 32 && n + j < p.N; ++j) f[j] += __ldg(p.bias + n + j);
+    }
+  }
+}
+
+// activation / activation-gradient part of the epilogue (GELU's pre-activation save is handled by the caller)
+__device__ __forceinline__ void epi_act(const GemmParams& p, int row, bool row_ok, int n, float (&f)[32]) {
+  const bool full = (n + 32 <= p.N);
+  if (p.epilogue == EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+  } else if (p.epilogue == EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+  } else if ((p.epilogue == EPI_DGELU || p.epilogue == EPI_DRELU) && row_ok && n < p.N) {
+    const __nv_bfloat16* ai = p.aux_in + (long long)row * p.ld_aux_in + n;
+    float a[32];
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(ai + j);
+        const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+        a[j] = a0.x; a[j + 1] = a0.y; a[j + 2] = a1.x; a[j + 3] = a1.y;
+        a[j + 4] = a2.x; a[j + 5] = a2.y; a[j + 6] = a3.x; a[j + 7] = a3.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = (n + j < p.N) ? __bfloat162float(ai[j]) : 0.f;
+    }
+    if (p.epilogue == EPI_DGELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(a[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = a[j] > 0.f ? f[j] : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_residual(const GemmParams& p, long long boff_r, int row, bool row_ok, int n,
+                                             float (&f)[32]) {
+  if (p.residual == nullptr || !row_ok || n >= p.N) return;
+  const float* r = p.residual + boff_r + (long long)row * p.ldr + n;
+  if (n + 32 <= p.N) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 rv = *reinterpret_cast<const float4*>(r + j);
+      f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
+    }
+  } else {
+    for (int j = 0; j < 32 && n + j < p.N; ++j) f[j] += r[j];
+  }
+}
+
+// staging tile of one epilogue warp: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7) (= TMA SWIZZLE_128B)
+__device__ __forceinline__ void stage_bf16(uint8_t* srow, int r, int half, const float (&f)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+    u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+    u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+    u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(srow + (((half * 4 + q) ^ (r & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void stage_f32(uint8_t* srow, int r, const float (&f)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4)) = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+}
 
 template <int BN, int A_MN, int B_MN, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes;  // 8 epilogue warps x 4 KB (TMA-store staging)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;
@@ -212,6 +320,61 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
+      if (BN >= 128 && splits == 1) {
+        // ---- staged epilogue: registers -> swizzled smem -> TMA store (full 128-byte lines, hardware tail clipping)
+        uint8_t* stage = stage_base + e * 4096;
+        uint8_t* srow = stage + lane * 128;
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+        const int step = p.out_fp32 ? 32 : 64;
+        const int m_box = m0 + quad * 32;
+#pragma unroll 1
+        for (int c = 0; c < kColsPerHalf; c += step) {
+          const int col0 = half * kColsPerHalf + c;
+          const int n = n0 + col0;
+          if (n >= p.N) break;  // warp-uniform
+          float f0[32], f1[32];
+          epi_load(p, trow + col0, n, split, f0);
+          if (!p.out_fp32) epi_load(p, trow + col0 + 32, n + 32, split, f1);
+          if (p.epilogue == EPI_GELU && p.aux_out != nullptr) {  // save the pre-activation (bf16) for the backward pass
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+            stage_bf16(srow, lane, 0, f0);
+            stage_bf16(srow, lane, 1, f1);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tma_aux, stage, n, m_box);
+              tma_store_commit();
+            }
+          }
+          epi_act(p, row, row_ok, n, f0);
+          epi_residual(p, boff_r, row, row_ok, n, f0);
+          if (!p.out_fp32) {
+            epi_act(p, row, row_ok, n + 32, f1);
+            epi_residual(p, boff_r, row, row_ok, n + 32, f1);
+          }
+          if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the staging tile
+          __syncwarp();
+          if (p.out_fp32) {
+            stage_f32(srow, lane, f0);
+          } else {
+            stage_bf16(srow, lane, 0, f0);
+            stage_bf16(srow, lane, 1, f1);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.batched) tma_store_3d(&tma_d, stage, n, m_box, batch);
+            else tma_store_2d(&tma_d, stage, n, m_box);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < kColsPerHalf; c += 32) {
         const int col0 = half * kColsPerHalf + c;
@@ -356,6 +519,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (BN >= 128 && lane == 0) tma_store_wait_all();  // bulk stores of this thread are complete before the CTA exits
   }
 
   tc_fence_before();
@@ -413,6 +577,26 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t inner, uint64
   return r == CUDA_SUCCESS ? S3D_OK : S3D_ERR_DRIVER;
 }
 
+// rank-2 / rank-3 tensor map over the output (bf16 or fp32), box {box_inner, 32 rows}, 128B swizzle (staged epilogue)
+static int make_tmap_out(CUtensorMap* map, const void* base, int is_f32, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                         int batch, uint64_t batch_pitch_elems) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return S3D_ERR_DRIVER;
+  const uint64_t es = is_f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_elems * es) % 16 != 0) return S3D_ERR_ALIGNMENT;
+  const cuuint32_t box_inner = is_f32 ? 32 : 64;  // 128 bytes
+  cuuint64_t dims[3] = {inner, outer, (cuuint64_t)(batch > 1 ? batch : 1)};
+  cuuint64_t strides[2] = {pitch_elems * es, batch_pitch_elems * es};
+  cuuint32_t box[3] = {box_inner, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const int rank = batch > 1 ? 3 : 2;
+  if (rank == 3 && (batch_pitch_elems * es) % 16 != 0) return S3D_ERR_ALIGNMENT;
+  CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? S3D_OK : S3D_ERR_DRIVER;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -445,6 +629,18 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     else rc = make_tmap_bf16_2d(&tb, g.B, p.K, p.N, g.ldb, 64, kBBoxRows);
     if (rc) return rc;
   }
+  CUtensorMap td, taux;
+  memset(&td, 0, sizeof(td));
+  memset(&taux, 0, sizeof(taux));
+  if (BN >= 128 && p.splits == 1) {
+    rc = make_tmap_out(&td, p.D, p.out_fp32, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldd, g.batch, (uint64_t)p.batch_stride_d);
+    if (rc) return rc;
+    if (p.aux_out != nullptr) {
+      if (g.batch > 1) return S3D_ERR_UNSUPPORTED;
+      rc = make_tmap_out(&taux, p.aux_out, 0, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ld_aux_out, 1, 0);
+      if (rc) return rc;
+    }
+  }
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CL>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -470,7 +666,7 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  S3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  S3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, taux, p));
   return S3D_OK;
 }
 
