@@ -44,6 +44,12 @@ CONFIGS = {
 }
 
 
+# Default workload: BASELINE.json quotes its metric "@1/2/4/8 B200" and north_star's targets (>= 60 % tensor-pipe on the
+# attention kernel, >= 6x 1->8 scaling) on "deit_base voxel classification at batch 64/GPU" = configs[2] (cfg3), which fits
+# one GPU; configs[1] (cfg2, a 160-us-roofline launch-bound step) is reported alongside it at N=1 as `secondary`.
+DEFAULT_CONFIG = "cfg3"
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -397,7 +403,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, ms, n = run_cpu(cfg, cfg["cpu_B"], steps=50, warmup=1, budget_s=12.0)
+        v, ms, n = run_cpu(cfg, cfg["cpu_B"], steps=50, warmup=1, budget_s=15.0)
         out["cpu_baseline"] = {"value": v, "unit": cfg["unit"], "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"oracle port (torch CPU fp32), batch {cfg['cpu_B']} fwd+bwd+Adam, {n} steps, {ms:.0f} ms/step"}
     return out
@@ -408,7 +414,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(CONFIGS))
+    ap.add_argument("--no-secondary", action="store_true", help="skip the extra cfg2 measurement at N=1")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -442,6 +449,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     out = run_ours(args, cfg, rank, world, local_rank)
+    if world == 1 and args.config == DEFAULT_CONFIG and not args.no_secondary:
+        # configs[1] (cfg2) measured the same way, reported inside the same JSON line
+        import copy
+        a2 = copy.copy(args)
+        a2.config, a2.no_cpu_baseline, a2.steps = "cfg2", True, max(args.steps, 20)
+        torch.cuda.empty_cache()
+        sec = run_ours(a2, CONFIGS["cfg2"], rank, world, local_rank)
+        out["secondary"] = {k: sec[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "gpu_launches", "roofline")}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -250,10 +250,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Branch-free erf (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7): keeps the fused GELU epilogues short -- the
+// library erff() expands to ~40 instructions with two branches per element, which made every GEMM kernel > 150 KB of SASS.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float y = 1.0f - poly * fast_exp2(-1.4426950408889634f * ax * ax);
+  return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * fast_exp2(-0.72134752044448170f * x * x);
   return cdf + x * pdf;
 }
 

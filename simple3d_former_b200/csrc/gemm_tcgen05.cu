@@ -320,53 +320,76 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
-      if (BN >= 128 && splits == 1) {
-        // ---- staged epilogue: registers -> swizzled smem -> TMA store (full 128-byte lines, hardware tail clipping)
-        uint8_t* stage = stage_base + e * 4096;
-        uint8_t* srow = stage + lane * 128;
+      if constexpr (BN >= 128) {
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-        const int step = p.out_fp32 ? 32 : 64;
-        const int m_box = m0 + quad * 32;
+        if (splits == 1) {
+          // ---- staged epilogue: registers -> swizzled smem -> TMA store (full 128-byte lines, hardware tail clipping).
+          // One 32-column chunk is live at a time (small code: short launches are instruction-fetch sensitive).
+          uint8_t* stage = stage_base + e * 4096;
+          uint8_t* srow = stage + lane * 128;
+          const int nh = p.out_fp32 ? 1 : 2;  // 32-column chunks per 128-byte staging row
+          const int m_box = m0 + quad * 32;
 #pragma unroll 1
-        for (int c = 0; c < kColsPerHalf; c += step) {
-          const int col0 = half * kColsPerHalf + c;
-          const int n = n0 + col0;
-          if (n >= p.N) break;  // warp-uniform
-          float f0[32], f1[32];
-          epi_load(p, trow + col0, n, split, f0);
-          if (!p.out_fp32) epi_load(p, trow + col0 + 32, n + 32, split, f1);
-          if (p.epilogue == EPI_GELU && p.aux_out != nullptr) {  // save the pre-activation (bf16) for the backward pass
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-            stage_bf16(srow, lane, 0, f0);
-            stage_bf16(srow, lane, 1, f1);
+          for (int c = 0; c < kColsPerHalf; c += 32 * nh) {
+            const int col0 = half * kColsPerHalf + c;
+            const int n = n0 + col0;
+            if (n >= p.N) break;  // warp-uniform
+            if (p.epilogue == EPI_GELU && p.aux_out != nullptr) {  // pre-activation (bf16) saved for the backward pass
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+#pragma unroll 1
+              for (int hh = 0; hh < 2; ++hh) {
+                float f[32];
+                epi_load(p, trow + col0 + 32 * hh, n + 32 * hh, split, f);
+                stage_bf16(srow, lane, hh, f);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tma_aux, stage, n, m_box);
+                tma_store_commit();
+              }
+            }
+#pragma unroll 1
+            for (int hh = 0; hh < nh; ++hh) {
+              float f[32];
+              const int nn = n + 32 * hh;
+              epi_load(p, trow + col0 + 32 * hh, nn, split, f);
+              epi_act(p, row, row_ok, nn, f);
+              epi_residual(p, boff_r, row, row_ok, nn, f);
+              if (hh == 0) {  // the previous store has finished reading the staging tile
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+              }
+              if (p.out_fp32) stage_f32(srow, lane, f);
+              else stage_bf16(srow, lane, hh, f);
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tma_aux, stage, n, m_box);
+              if (p.batched) tma_store_3d(&tma_d, stage, n, m_box, batch);
+              else tma_store_2d(&tma_d, stage, n, m_box);
               tma_store_commit();
             }
           }
-          epi_act(p, row, row_ok, n, f0);
-          epi_residual(p, boff_r, row, row_ok, n, f0);
-          if (!p.out_fp32) {
-            epi_act(p, row, row_ok, n + 32, f1);
-            epi_residual(p, boff_r, row, row_ok, n + 32, f1);
-          }
-          if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the staging tile
-          __syncwarp();
-          if (p.out_fp32) {
-            stage_f32(srow, lane, f0);
-          } else {
-            stage_bf16(srow, lane, 0, f0);
-            stage_bf16(srow, lane, 1, f1);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (p.batched) tma_store_3d(&tma_d, stage, n, m_box, batch);
-            else tma_store_2d(&tma_d, stage, n, m_box);
-            tma_store_commit();
+        } else if (kb1 > kb0) {
+          // ---- split-K: reduce the fp32 partial tile into D (zeroed or accumulating) with vector red.add
+#pragma unroll 1
+          for (int c = 0; c < kColsPerHalf; c += 32) {
+            const int col0 = half * kColsPerHalf + c;
+            const int n = n0 + col0;
+            if (n >= p.N) break;
+            float f[32];
+            epi_load(p, trow + col0, n, split, f);
+            if (row_ok) {
+              float* d = reinterpret_cast<float*>(p.D) + boff_d + (long long)row * p.ldd + n;
+              if (n + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) red_add_f32x4(d + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+                for (int j = 0; j < 32 && n + j < p.N; ++j) atomicAdd(d + j, f[j]);
+              }
+            }
           }
         }
         tc_fence_before();

@@ -11,7 +11,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-GROUPS = ["attn_tc", "gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
+GROUPS = ["attn_tc", "gemm_small", "gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
 
 
 def rel_err(a, b):
@@ -56,6 +56,55 @@ def g_gemm_perf():
             torch.cuda.synchronize()
             ms = s.elapsed_time(e) / reps
             print(f"  [PERF] {name} M{M} N{N} K{K} BN{bn} cl{cl} split{sp}: {ms * 1e3:9.1f} us  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s", flush=True)
+
+
+def g_gemm_small():
+    """GPU time per launch of small GEMMs (CUDA graph of 50 launches: no CPU launch overhead), vs cuBLAS in a graph."""
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(0)
+
+    def graph_time(fn, n=50):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                fn()
+        g.replay()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(4):
+            g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / (4 * n) * 1e3
+
+    for (name, M, N, K, amn, bmn, f32) in [("1 tile 1 kblock", 128, 128, 64, False, False, False),
+                                           ("1 tile 6 kblocks", 128, 128, 384, False, False, False),
+                                           ("fwd qkv cfg2", 1664, 1152, 384, False, False, False),
+                                           ("fwd fc1 cfg2", 1664, 1536, 384, False, False, False),
+                                           ("fwd fc2 cfg2 f32", 1664, 384, 1536, False, False, True),
+                                           ("dX fc2 cfg2", 1664, 1536, 384, False, True, False),
+                                           ("dW fc1 cfg2 f32", 1536, 384, 1664, True, True, True)]:
+        a = torch.randn((K, M) if amn else (M, K), device="cuda").bfloat16()
+        b = torch.randn((K, N) if bmn else (N, K), device="cuda").bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+        res = []
+        for (bn, cl, sp) in [(0, 0, 0), (128, 1, 1), (64, 1, 1), (256, 1, 1)]:
+            if bn > N and bn != 0:
+                continue
+            us = graph_time(lambda: L.gemm(a, b, a_mn=amn, b_mn=bmn, out=out, force_bn=bn, force_cluster=cl, force_splits=sp))
+            res.append(f"BN{bn}/cl{cl}/sp{sp}: {us:6.1f} us")
+        am = a.t() if amn else a
+        bm = b if bmn else b.t()
+        ref = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        us = graph_time(lambda: torch.matmul(am, bm, out=ref))
+        print(f"  [PERF] {name:18s} M{M} N{N} K{K}: " + " | ".join(res) + f" | cuBLAS {us:6.1f} us", flush=True)
 
 
 def g_gemm_k():
