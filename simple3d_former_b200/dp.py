@@ -62,6 +62,9 @@ class FlatGradBuckets:
                 self.buckets.append([start, end, count])
                 start, count = end, 0
         self._pending = [b[2] for b in self.buckets]
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._uses = [0] * len(self.params)      # in-place gradient writes seen this step (gradient sinks)
+        self._expected = None                    # learned in the first step: writes per parameter per step
         self._comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and dev.type == "cuda") else None
         self._handles = []
         self.launch_order = []  # bucket ids in the order their collectives were enqueued (observability / tests)
@@ -70,6 +73,22 @@ class FlatGradBuckets:
             dist.broadcast(self.flat_p, src=0, group=self.group)
             for i, p in enumerate(self.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def enable_sinks(self):
+        """Kernels accumulate parameter gradients straight into the flat buffer (functional._wgrad/_bgrad/_ln_bwd) and
+        report each write through note_write(); autograd then never materialises or adds those gradients."""
+        for p in self.params:
+            p._s3d_grad_sink = p.grad
+            p._s3d_owner = self
+
+    def note_write(self, p):
+        i = self._index[id(p)]
+        self._uses[i] += 1
+        if self.world > 1 and self._expected is not None and self._uses[i] == self._expected[i]:
+            b = self._bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch_bucket(b)
 
     def _make_hook(self, i):
         b = self._bucket_of[i]
@@ -97,6 +116,7 @@ class FlatGradBuckets:
     def zero_grad(self):
         self.flat_g.zero_()
         self._pending = [b[2] for b in self.buckets]
+        self._uses = [0] * len(self.params)
         self.launch_order = []
 
     def sync_gradients(self):
@@ -112,6 +132,8 @@ class FlatGradBuckets:
         self._handles = []
         if self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
+        if self._expected is None and any(self._uses):
+            self._expected = list(self._uses)  # shared blocks (group_embed mode) are written twice per step
 
 
 class DataParallelTrainer:
@@ -139,6 +161,7 @@ class DataParallelTrainer:
             n = p.numel()
             p._s3d_shadow = self.flat_s[o:o + n].view(p.shape[0], -1) if p.dim() >= 2 else self.flat_s[o:o + n]
         L.cast_bf16(f.flat_p, out=self.flat_s)
+        f.enable_sinks()
         self.step_count = 0
         self.step_t = torch.zeros(1, device=dev, dtype=torch.int32)  # device-side counter (CUDA-graph replays)
 

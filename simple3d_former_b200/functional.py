@@ -38,6 +38,50 @@ def shadow(p: torch.Tensor) -> torch.Tensor:
     return s16
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# gradient sinks: under DataParallelTrainer every parameter owns a view of the flat fp32 gradient buffer
+# (`p._s3d_grad_sink`); weight / bias / LayerNorm gradients are then accumulated IN PLACE by the producing kernel
+# (GEMM epilogue accumulate or split-K red.add, colsum accumulate, LN-bwd atomics) and backward() returns None for them:
+# no temporary dW tensors, no autograd AccumulateGrad add kernels, no zero-fill kernels.
+# ----------------------------------------------------------------------------------------------------------------
+def _sink(p):
+    return getattr(p, "_s3d_grad_sink", None) if p is not None else None
+
+
+def _wgrad(w, a16, b16, alpha=1.0):
+    """dW (+)= alpha * a16^T @ b16 (both operands consumed MN-major)."""
+    sk = _sink(w)
+    if sk is None:
+        return L.gemm(a16, b16, a_mn=True, b_mn=True, alpha=alpha, out_dtype=torch.float32).view(w.shape)
+    s2 = sk.view(sk.shape[0], -1)
+    L.gemm(a16, b16, a_mn=True, b_mn=True, alpha=alpha, out=s2, residual=s2)
+    w._s3d_owner.note_write(w)
+    return None
+
+
+def _bgrad(b, x16):
+    """db (+)= column sums of x16."""
+    if b is None:
+        return None
+    sk = _sink(b)
+    if sk is None:
+        return L.colsum(x16)
+    L.colsum(x16, out=sk, accumulate=True)
+    b._s3d_owner.note_write(b)
+    return None
+
+
+def _ln_bwd(dy, x, gamma, beta, mean, rstd, **kw):
+    """LayerNorm backward; returns (dx, dx16, dgamma, dbeta) with None parameter gradients when they went to sinks."""
+    sg, sb = _sink(gamma), _sink(beta)
+    if sg is not None and sb is not None:
+        dx, dx16, _, _ = L.layernorm_bwd(dy, x, gamma, mean, rstd, dgamma=sg, dbeta=sb, **kw)
+        gamma._s3d_owner.note_write(gamma)
+        beta._s3d_owner.note_write(beta)
+        return dx, dx16, None, None
+    return L.layernorm_bwd(dy, x, gamma, mean, rstd, **kw)
+
+
 def _w2d(w16: torch.Tensor) -> torch.Tensor:
     return w16.reshape(w16.shape[0], -1)
 
@@ -59,6 +103,7 @@ class LinearFn(torch.autograd.Function):
         y = L.gemm(x16, w16, bias=bias, out_dtype=torch.float32)
         ctx.save_for_backward(x16, weight)
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         ctx.in_shape = x.shape
         return y.reshape(*x.shape[:-1], w16.shape[0])
 
@@ -68,8 +113,8 @@ class LinearFn(torch.autograd.Function):
         w16 = _w2d(shadow(weight))
         dy16 = L.cast_bf16(dy.reshape(-1, dy.shape[-1]).contiguous())
         dx = L.gemm(dy16, w16, b_mn=True, out_dtype=torch.float32).reshape(ctx.in_shape)
-        dw = L.gemm(dy16, x16, a_mn=True, b_mn=True, out_dtype=torch.float32).reshape(weight.shape)
-        db = L.colsum(dy16) if ctx.has_bias else None
+        dw = _wgrad(weight, dy16, x16)
+        db = _bgrad(ctx.bias_ref, dy16) if ctx.has_bias else None
         return dx, dw, db
 
 
@@ -181,6 +226,7 @@ class BlockFn(torch.autograd.Function):
                               n2w, fc1_w, fc2_w)
         ctx.meta = (B, N, D, num_heads, dh, scale, qkv_b is not None, proj_b is not None, fc1_b is not None,
                     fc2_b is not None)
+        ctx.refs = (n1b, qkv_b, proj_b, n2b, fc1_b, fc2_b)  # bias-type parameters (gradient sinks are looked up on them)
         return y.view(B, N, D)
 
     @staticmethod
@@ -191,23 +237,24 @@ class BlockFn(torch.autograd.Function):
         T = B * N
         dy2 = dy.reshape(T, D).contiguous()
         dy16 = L.cast_bf16(dy2)
+        n1b, qkv_b, proj_b, n2b, fc1_b, fc2_b = ctx.refs
         # MLP
-        dfc2_w = L.gemm(dy16, a16, a_mn=True, b_mn=True, out_dtype=torch.float32)
-        dfc2_b = L.colsum(dy16) if has_b2 else None
+        dfc2_w = _wgrad(fc2_w, dy16, a16)
+        dfc2_b = _bgrad(fc2_b, dy16)
         dpre = L.gemm(dy16, shadow(fc2_w), b_mn=True, epilogue=L.EPI_DGELU, aux_in=pre)
-        dfc1_w = L.gemm(dpre, g16, a_mn=True, b_mn=True, out_dtype=torch.float32)
-        dfc1_b = L.colsum(dpre) if has_b1 else None
+        dfc1_w = _wgrad(fc1_w, dpre, g16)
+        dfc1_b = _bgrad(fc1_b, dpre)
         dg = L.gemm(dpre, shadow(fc1_w), b_mn=True)
-        dx1, dx1_16, dn2w, dn2b = L.layernorm_bwd(dg, x1, n2w, mean2, rstd2, dres=dy2, want_bf16=True)
+        dx1, dx1_16, dn2w, dn2b = _ln_bwd(dg, x1, n2w, n2b, mean2, rstd2, dres=dy2, want_bf16=True)
         # attention
-        dproj_w = L.gemm(dx1_16, o16.view(T, D), a_mn=True, b_mn=True, out_dtype=torch.float32)
-        dproj_b = L.colsum(dx1_16) if has_pb else None
+        dproj_w = _wgrad(proj_w, dx1_16, o16.view(T, D))
+        dproj_b = _bgrad(proj_b, dx1_16)
         do16 = L.gemm(dx1_16, shadow(proj_w), b_mn=True)
         dqkv = _attn_core_bwd(qkv, o16, do16.view(B, N, D), lse, B, N, H, dh, scale)
-        dqkv_w = L.gemm(dqkv, h16, a_mn=True, b_mn=True, out_dtype=torch.float32)
-        dqkv_b = L.colsum(dqkv) if has_qb else None
+        dqkv_w = _wgrad(qkv_w, dqkv, h16)
+        dqkv_b = _bgrad(qkv_b, dqkv)
         dh_ = L.gemm(dqkv, shadow(qkv_w), b_mn=True)
-        dx, _, dn1w, dn1b = L.layernorm_bwd(dh_, x2, n1w, mean1, rstd1, dres=dx1)
+        dx, _, dn1w, dn1b = _ln_bwd(dh_, x2, n1w, n1b, mean1, rstd1, dres=dx1)
         return (dx.view(B, N, D), dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w,
                 dfc2_b, None, None, None, None)
 
@@ -222,13 +269,14 @@ class LayerNormFn(torch.autograd.Function):
         x2 = x.reshape(-1, shape[-1]).contiguous()
         _, y, _, mean, rstd = L.layernorm_fwd(x2, weight, bias, eps, want_bf16=False, want_f32=True)
         ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.bias_ref = bias
         return y.view(shape)
 
     @staticmethod
     def backward(ctx, dy):
         x2, weight, mean, rstd = ctx.saved_tensors
         dy2 = dy.reshape(x2.shape).contiguous()
-        dx, _, dg, db = L.layernorm_bwd(dy2, x2, weight, mean, rstd)
+        dx, _, dg, db = _ln_bwd(dy2, x2, weight, ctx.bias_ref, mean, rstd)
         return dx.view(dy.shape), dg, db, None
 
 
@@ -307,6 +355,7 @@ class GroupEmbedFn(torch.autograd.Function):
         ctx.save_for_backward(x16, qkv, o16, lse, sa, mean1, rstd1, y1_16, h16, f, mean2, rstd2, in_w, out_w, l1_w, l2_w,
                               n1w, n2w)
         ctx.meta = (S, Nb, E, nhead, dh, scale, qs, os_)
+        ctx.refs = (in_b, out_b, l1_b, l2_b, n1b, n2b)
         return y2.view(S, Nb, E)
 
     @staticmethod
@@ -316,24 +365,25 @@ class GroupEmbedFn(torch.autograd.Function):
         S, Nb, E, nhead, dh, scale, qs, os_ = ctx.meta
         T = S * Nb
         dy2 = dy.reshape(T, E).contiguous()
-        df, df16, dn2w, dn2b = L.layernorm_bwd(dy2, f, n2w, mean2, rstd2, want_bf16=True)
-        dl2_w = L.gemm(df16, h16, a_mn=True, b_mn=True, out_dtype=torch.float32)
-        dl2_b = L.colsum(df16)
+        in_b, out_b, l1_b, l2_b, n1b, n2b = ctx.refs
+        df, df16, dn2w, dn2b = _ln_bwd(dy2, f, n2w, n2b, mean2, rstd2, want_bf16=True)
+        dl2_w = _wgrad(l2_w, df16, h16)
+        dl2_b = _bgrad(l2_b, df16)
         dh16 = L.gemm(df16, shadow(l2_w), b_mn=True, epilogue=L.EPI_DRELU, aux_in=h16)
-        dl1_w = L.gemm(dh16, y1_16, a_mn=True, b_mn=True, out_dtype=torch.float32)
-        dl1_b = L.colsum(dh16)
+        dl1_w = _wgrad(l1_w, dh16, y1_16)
+        dl1_b = _bgrad(l1_b, dh16)
         dy1 = L.gemm(dh16, shadow(l1_w), b_mn=True, residual=df, out_dtype=torch.float32)  # + residual branch of y1
-        dsa, dsa16, dn1w, dn1b = L.layernorm_bwd(dy1, sa, n1w, mean1, rstd1, want_bf16=True)
-        dout_w = L.gemm(dsa16, o16, a_mn=True, b_mn=True, out_dtype=torch.float32)
-        dout_b = L.colsum(dsa16)
+        dsa, dsa16, dn1w, dn1b = _ln_bwd(dy1, sa, n1w, n1b, mean1, rstd1, want_bf16=True)
+        dout_w = _wgrad(out_w, dsa16, o16)
+        dout_b = _bgrad(out_b, dsa16)
         do16 = L.gemm(dsa16, shadow(out_w), b_mn=True)
         dqkv = torch.empty_like(qkv)
         delta = torch.empty_like(lse)
         base, dbase = qkv.data_ptr(), dqkv.data_ptr()
         L.attn_bwd(base, base + 2 * E, base + 4 * E, o16, do16, lse, delta, dbase, dbase + 2 * E, dbase + 4 * E, Nb, nhead,
                    S, dh, qs, os_, scale)
-        din_w = L.gemm(dqkv, x16, a_mn=True, b_mn=True, out_dtype=torch.float32)
-        din_b = L.colsum(dqkv)
+        din_w = _wgrad(in_w, dqkv, x16)
+        din_b = _bgrad(in_b, dqkv)
         dx = L.gemm(dqkv, shadow(in_w), b_mn=True, residual=dsa, out_dtype=torch.float32)
         return (dx.view(S, Nb, E), din_w, din_b, dout_w, dout_b, dl1_w, dl1_b, dl2_w, dl2_b, dn1w, dn1b, dn2w, dn2b, None,
                 None)

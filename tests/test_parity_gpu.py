@@ -202,3 +202,39 @@ def test_convert_swaps_reference_style_modules():
     with torch.no_grad():
         got = fused(x.to(_dev())).cpu()
     assert (got - want).abs().max().item() <= 1e-2
+
+
+def test_trainer_gradient_sinks_match_autograd(golden):
+    """DataParallelTrainer accumulates parameter gradients in place into its flat buffer (gradient sinks); they must
+    equal the gradients autograd produces without the trainer, and one fused Adam step must match torch.optim.Adam."""
+    from simple3d_former_b200.dp import DataParallelTrainer
+    fix = golden("cfg3_small_deit_base_group36")  # group_embed mode: the 12 blocks are applied twice per step
+    x, y = O.synthetic_voxels(fix["B"], fix["V"], seed=fix["input_seed"], n_classes=fix["n_classes"])
+    x, y = x.to(_dev()), y.to(_dev())
+    ref_model = _build_voxel(fix).train()
+    ref_model.freeze_image_branch()
+    F.cross_entropy(ref_model(x), y).backward()
+    ref_grads = {n: p.grad.detach().clone() for n, p in ref_model.named_parameters() if p.grad is not None}
+    opt = torch.optim.Adam([p for p in ref_model.parameters() if p.requires_grad], lr=1e-3)
+    opt.step()
+    model = _build_voxel(fix).train()
+    model.freeze_image_branch()
+    trainer = DataParallelTrainer(model, lr=1e-3)
+    trainer.zero_grad()
+    F.cross_entropy(model(x), y).backward()
+    trainer.sync_gradients()
+    torch.cuda.synchronize()
+    named = dict(model.named_parameters())
+    assert set(ref_grads) == {n for n, p in named.items() if p.requires_grad}
+    for n, g in ref_grads.items():
+        got = named[n].grad
+        scale = g.abs().max().item() + 1e-12
+        assert (got - g).abs().max().item() <= 2e-3 * scale + 1e-9, n  # same kernels, different summation order
+    trainer.optimizer_step()
+    torch.cuda.synchronize()
+    ref_named = dict(ref_model.named_parameters())
+    for n, p in named.items():
+        if p.requires_grad:
+            assert (p - ref_named[n]).abs().max().item() <= 2e-5, n
+            sh = p._s3d_shadow.reshape(p.shape).float()
+            assert (sh - p).abs().max().item() <= 8e-3 * (p.abs().max().item() + 1e-6), n
