@@ -749,7 +749,9 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
                         (p.residual == nullptr || p.residual == p.D) && nb == 1;
   int splits = 1;
   if (g.force_splits > 0) splits = split_ok ? g.force_splits : 1;
-  else if (split_ok && tiles * 2 <= sms && num_kb >= 8) {
+  else if (split_ok && g.a_mn && g.b_mn && tiles * 2 <= sms && num_kb >= 8) {
+    // automatic split-K only for weight-gradient GEMMs (both operands MN-major, K = tokens): red.add makes the fp32
+    // summation order non-deterministic, which forward / activation-gradient GEMMs must not be
     splits = (int)((2LL * sms + tiles - 1) / tiles);
     if (splits > num_kb / 4) splits = num_kb / 4;
     if (splits < 1) splits = 1;
