@@ -49,6 +49,10 @@ CONFIGS = {
 # one GPU; configs[1] (cfg2, a 160-us-roofline launch-bound step) is reported alongside it at N=1 as `secondary`.
 DEFAULT_CONFIG = "cfg3"
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of exactly these launches
+# (profiles/, filled in by hand after each profiling run; None = not captured yet)
+NCU_TRAFFIC = {}
+
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -244,18 +248,30 @@ class KernelProfile:
             return 0.0, a[11] * a[12] * 14.0
         return 0.0, 0.0
 
+    @staticmethod
+    def shape_key(name, a):
+        if name == "s3d_gemm_bf16":
+            return f"{name}[M={a[3]},N={a[4]},K={a[5]},a_mn={a[9]},b_mn={a[10]},epi={a[16]},f32={a[11]}]"
+        if name == "s3d_attn_fwd":
+            return f"{name}[B={a[5]},H={a[6]},N={a[7]},dh={a[8]}]"
+        if name == "s3d_attn_bwd":
+            return f"{name}[B={a[10]},H={a[11]},N={a[12]},dh={a[13]}]"
+        return name
+
     def summary(self):
+        """Returns (per-family totals, per-(kernel, shape) totals)."""
         torch.cuda.synchronize()
-        fam = {}
+        fam, shapes = {}, {}
         for name, args, s, e in self.records:
             ms = s.elapsed_time(e)
             fl, by = self.work(name, args)
-            f = fam.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-            f["ms"] += ms
-            f["flops"] += fl
-            f["bytes"] += by
-            f["launches"] += 1
-        return fam
+            for table, key in ((fam, name), (shapes, self.shape_key(name, args))):
+                f = table.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+                f["ms"] += ms
+                f["flops"] += fl
+                f["bytes"] += by
+                f["launches"] += 1
+        return fam, shapes
 
 
 def run_ours(args, cfg, rank, world, local_rank):
@@ -364,25 +380,30 @@ def run_ours(args, cfg, rank, world, local_rank):
     try:
         for _ in range(2):
             eager_step()
-        fam = prof.summary()
+        fam, shapes = prof.summary()
     finally:
         L.call = orig
     if rank != 0:
         return None
     pk = peaks()
-    dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
-    name, f = dom
+    # dominant kernel = the (kernel, shape) group with the largest share of the step's kernel time
+    name, f = max(shapes.items(), key=lambda kv: kv[1]["ms"])
     tensor_bound = f["flops"] > 0
     achieved = (f["flops"] / (f["ms"] * 1e-3) / 1e12) if tensor_bound else (f["bytes"] / (f["ms"] * 1e-3) / 1e9)
     peak = pk["tf_sustained"] if tensor_bound else pk["hbm"]
     step_kernel_ms = sum(v["ms"] for v in fam.values())
+    gemm = fam.get("s3d_gemm_bf16")
     roofline = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": round(achieved, 2),
                 "peak": peak, "peak_source": pk["src"] + (" sustained bf16" if tensor_bound else " copy"),
-                "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": NCU_TRAFFIC.get(name),
+                "algorithmic_per_launch": round((f["flops"] if tensor_bound else f["bytes"]) / f["launches"], 1),
                 "launches_per_step": f["launches"] // 2, "avg_launch_us": round(1e3 * f["ms"] / f["launches"], 2),
                 "share_of_kernel_time": round(f["ms"] / step_kernel_ms, 3),
                 "timing": "cuda events around every C-ABI launch, instrumented eager pass of 2 steps after the timed region",
-                "families_ms_per_step": {k: round(v["ms"] / 2, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
+                "gemm_family_tflops": round(gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12, 1) if gemm else None,
+                "families_ms_per_step": {k: round(v["ms"] / 2, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+                "top_shapes_ms_per_step": {k: round(v["ms"] / 2, 3) for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:6]}}
     samples = B * world * args.steps
     value = samples * cfg["per_sample"] / (dev_ms * 1e-3)
     e2e_value = samples * cfg["per_sample"] / (e2e_ms * 1e-3)

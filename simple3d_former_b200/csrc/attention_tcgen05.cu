@@ -79,7 +79,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 4);  // one arrive per softmax warp
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -115,31 +115,38 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------- MMA issuer ----------------------------------------------
-    if (lane == 0) {
+    // The whole warp runs the control flow (waits are warp-uniform); one elected lane issues. Descriptor low words are
+    // precomputed so each tcgen05.mma costs a couple of integer adds (at N = 64 an MMA lasts only ~40 cycles, so the
+    // issue path must stay far below that).
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(kFaBM, kFaBN, 0, 0);  // S = Q K^T : both K-major
       constexpr uint32_t idesc_o = make_idesc_bf16(kFaBM, DH, 0, 1);     // O = P V   : V is MN-major
+      constexpr uint32_t hi = smem_desc_hi_sw128(1024);
+      const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16), k_lo = smem_desc_lo(smem_u32(sK), 16);
+      const uint32_t p_lo = smem_desc_lo(smem_u32(sP), 16), v_lo = smem_desc_lo(smem_u32(sV), kFaBN * 128);
       auto issue_s = [&](int t, int st) {
-        const uint32_t a0 = smem_u32(sQ + t * Cfg::kQBytes);
-        const uint32_t b0 = smem_u32(sK + st * Cfg::kKVBytes);
+        const uint32_t a = q_lo + t * (Cfg::kQBytes >> 4), b = k_lo + st * (Cfg::kKVBytes >> 4);
         const uint32_t d = tmem_base + Cfg::kColS + t * kFaBN;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint64_t ad = make_smem_desc_sw128(a0 + (kk >> 2) * (kFaBM * 128) + (kk & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc_sw128(b0 + (kk >> 2) * (kFaBN * 128) + (kk & 3) * 32, 16, 1024);
-          umma_f16_ss(d, ad, bd, idesc_s, kk != 0);
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_f16_ss2(d, a + (((kk >> 2) * (kFaBM * 128) + (kk & 3) * 32) >> 4), hi,
+                         b + (((kk >> 2) * (kFaBN * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
+          umma_commit(&s_full[t]);
         }
-        umma_commit(&s_full[t]);
+        __syncwarp();
       };
-      auto issue_pv = [&](int t, int st, int j) {
-        const uint32_t a0 = smem_u32(sP + t * Cfg::kPBytes);
-        const uint32_t b0 = smem_u32(sV + st * Cfg::kKVBytes);
+      auto issue_pv = [&](int t, int st, int j, uint64_t* done0, uint64_t* done1) {
+        const uint32_t a = p_lo + t * (Cfg::kPBytes >> 4), b = v_lo + st * (Cfg::kKVBytes >> 4);
         const uint32_t d = tmem_base + t * DH;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kFaBN / 16; ++kk) {
-          const uint64_t ad = make_smem_desc_sw128(a0 + kk * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc_sw128(b0 + kk * 2048, kFaBN * 128, 1024);
-          umma_f16_ss(d, ad, bd, idesc_o, (j > 0) || (kk != 0));
+          for (int kk = 0; kk < kFaBN / 16; ++kk)
+            umma_f16_ss2(d, a + ((kk * 32) >> 4), hi, b + ((kk * 2048) >> 4), hi, idesc_o, (j > 0) || (kk != 0));
+          if (done0 != nullptr) umma_commit(done0);
+          if (done1 != nullptr) umma_commit(done1);
         }
+        __syncwarp();
       };
       mbar_wait(&k_full[0], 0);
       mbar_wait(&q_full[0], 0);
@@ -151,24 +158,21 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
         const uint32_t ph = j & 1;
+        const bool last = (j + 1 == nkv);
         mbar_wait(&v_full[st], (j >> 1) & 1);
-        if (j + 1 < nkv) mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
+        if (!last) mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
         // tile A
         mbar_wait(&p_full[0], ph);
         tc_fence_after();
-        issue_pv(0, st, j);
-        if (j + 1 < nkv) issue_s(0, st ^ 1);
-        else umma_commit(&o_full[0]);
-        // tile B
+        issue_pv(0, st, j, last ? &o_full[0] : nullptr, nullptr);
+        if (!last) issue_s(0, st ^ 1);
+        // tile B (its P V is the last reader of K/V stage `st`: the commit frees the stage when those MMAs retire)
         mbar_wait(&p_full[1], ph);
         tc_fence_after();
-        issue_pv(1, st, j);
-        umma_commit(&kv_empty[st]);  // every MMA that reads stage `st` has been issued; frees it when they retire
-        if (j + 1 < nkv) issue_s(1, st ^ 1);
-        else umma_commit(&o_full[1]);
+        issue_pv(1, st, j, &kv_empty[st], last ? &o_full[1] : nullptr);
+        if (!last) issue_s(1, st ^ 1);
       }
     }
-    __syncwarp();
   } else {
     // ----------------------------------------------- softmax -----------------------------------------------
     const int t = (warp - 2) >> 2;     // tile 0 (A) / 1 (B)
@@ -196,9 +200,15 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         for (int i = 0; i < 64; ++i)
           if (key0 + i >= p.N) s[i] = -INFINITY;
       }
-      float mx = s[0];
+      float mx4[4] = {s[0], s[1], s[2], s[3]};  // 4 independent chains instead of one 64-long dependent chain
 #pragma unroll
-      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 4; i < 64; i += 4) {
+        mx4[0] = fmaxf(mx4[0], s[i]);
+        mx4[1] = fmaxf(mx4[1], s[i + 1]);
+        mx4[2] = fmaxf(mx4[2], s[i + 2]);
+        mx4[3] = fmaxf(mx4[3], s[i + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // lazy rescale: keep the reference max unless it grew by more than 2^8 (P stays <= 256, exact in the row sums)
       const bool need = (mx - m_ref) * c > 8.0f;
       if (__any_sync(0xffffffffu, need)) {
@@ -218,14 +228,15 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         if (need) { l *= f; m_ref = mx; }
       }
       const float mc = m_ref * c;
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         float e[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          e[i] = fast_exp2(s[ch * 8 + i] * c - mc);
-          sum += e[i];
+          const float xs = fmaf(s[ch * 8 + i], c, -mc);
+          e[i] = (i & 1) ? poly_exp2(xs) : fast_exp2(xs);  // half on MUFU, half on the FMA pipe
+          sum4[i & 3] += e[i];
         }
         uint4 u;
         u.x = pack_bf16x2(e[0], e[1]);
@@ -234,10 +245,11 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         u.w = pack_bf16x2(e[6], e[7]);
         *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = u;
       }
-      l += sum;
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(&p_full[t]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
     }
     // epilogue: O / l -> bf16, lse
     mbar_wait(&o_full[t], 0);
@@ -418,7 +430,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&sp_full[i], 1);
-      mbar_init(&ds_full[i], 128);
+      mbar_init(&ds_full[i], 4);
     }
     fence_barrier_init();
   }
@@ -451,52 +463,55 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_q = make_idesc_bf16(128, DH, 0, 1);
-      auto issue_s_dp = [&](int u, int st) {
-        const uint32_t aq = smem_u32(sQ), ao = smem_u32(sdO);
-        const uint32_t bk = smem_u32(sK + st * Cfg::kBlkBytes), bv = smem_u32(sV + st * Cfg::kBlkBytes);
-        const uint32_t ds_ = tmem_base + kColS + u * 128, dp_ = ds_ + 64;
+    // warp-converged control flow, one elected lane issues; precomputed descriptor low words (see the forward kernel)
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_q = make_idesc_bf16(128, DH, 0, 1);
+    constexpr uint32_t hi = smem_desc_hi_sw128(1024);
+    const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16), do_lo = smem_desc_lo(smem_u32(sdO), 16);
+    const uint32_t k_lo = smem_desc_lo(smem_u32(sK), 16), v_lo = smem_desc_lo(smem_u32(sV), 16);
+    const uint32_t ds_lo = smem_desc_lo(smem_u32(sdS), 16), kmn_lo = smem_desc_lo(smem_u32(sK), 64 * 128);
+    auto issue_s_dp = [&](int u, int st) {
+      const uint32_t bk = k_lo + st * (Cfg::kBlkBytes >> 4), bv = v_lo + st * (Cfg::kBlkBytes >> 4);
+      const uint32_t ds_ = tmem_base + kColS + u * 128, dp_ = ds_ + 64;
+      if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint32_t offa = (kk >> 2) * (128 * 128) + (kk & 3) * 32, offb = (kk >> 2) * (64 * 128) + (kk & 3) * 32;
-          umma_f16_ss(ds_, make_smem_desc_sw128(aq + offa, 16, 1024), make_smem_desc_sw128(bk + offb, 16, 1024), idesc_s, kk != 0);
-        }
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_f16_ss2(ds_, q_lo + (((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), hi,
+                       bk + (((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint32_t offa = (kk >> 2) * (128 * 128) + (kk & 3) * 32, offb = (kk >> 2) * (64 * 128) + (kk & 3) * 32;
-          umma_f16_ss(dp_, make_smem_desc_sw128(ao + offa, 16, 1024), make_smem_desc_sw128(bv + offb, 16, 1024), idesc_s, kk != 0);
-        }
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_f16_ss2(dp_, do_lo + (((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), hi,
+                       bv + (((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
         umma_commit(&sp_full[u]);
-      };
-      mbar_wait(qdo_full, 0);
-      mbar_wait(&k_full[0], 0);
-      mbar_wait(&v_full[0], 0);
-      tc_fence_after();
-      issue_s_dp(0, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const int u = j & 1, st = j & 1;
-        if (j + 1 < nkv) {
-          mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
-          mbar_wait(&v_full[st ^ 1], ((j + 1) >> 1) & 1);
-          // TMEM buffer u^1 was released by ds_full[u^1] of block j-1 (waited below in the previous iteration)
-          tc_fence_after();
-          issue_s_dp(u ^ 1, st ^ 1);
-        }
-        mbar_wait(&ds_full[u], (j >> 1) & 1);
+      }
+      __syncwarp();
+    };
+    mbar_wait(qdo_full, 0);
+    mbar_wait(&k_full[0], 0);
+    mbar_wait(&v_full[0], 0);
+    tc_fence_after();
+    issue_s_dp(0, 0);
+    for (int j = 0; j < nkv; ++j) {
+      const int u = j & 1, st = j & 1;
+      if (j + 1 < nkv) {
+        mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
+        mbar_wait(&v_full[st ^ 1], ((j + 1) >> 1) & 1);
+        // TMEM buffer u^1 was released by ds_full[u^1] of block j-1 (waited below in the previous iteration)
         tc_fence_after();
-        const uint32_t a0 = smem_u32(sdS + u * Cfg::kSBytes);
-        const uint32_t b0 = smem_u32(sK + st * Cfg::kBlkBytes);
+        issue_s_dp(u ^ 1, st ^ 1);
+      }
+      mbar_wait(&ds_full[u], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a = ds_lo + u * (Cfg::kSBytes >> 4), b = kmn_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_f16_ss(tmem_base, make_smem_desc_sw128(a0 + kk * 32, 16, 1024),
-                      make_smem_desc_sw128(b0 + kk * 2048, 64 * 128, 1024), idesc_q, (j > 0) || (kk != 0));
+          umma_f16_ss2(tmem_base, a + ((kk * 32) >> 4), hi, b + ((kk * 2048) >> 4), hi, idesc_q, (j > 0) || (kk != 0));
         umma_commit(&kv_empty[st]);
+        if (j + 1 == nkv) umma_commit(dq_full);
       }
-      umma_commit(dq_full);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
@@ -521,15 +536,17 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
       const int key0 = j * 64;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float p0 = (key0 + i < p.N) ? fast_exp2(__uint_as_float(a0[i]) * c - lse2) : 0.f;
-        const float p1 = (key0 + 32 + i < p.N) ? fast_exp2(__uint_as_float(a1[i]) * c - lse2) : 0.f;
+        const float x0 = fmaf(__uint_as_float(a0[i]), c, -lse2), x1 = fmaf(__uint_as_float(a1[i]), c, -lse2);
+        const float p0 = (key0 + i < p.N) ? fast_exp2(x0) : 0.f;       // MUFU pipe
+        const float p1 = (key0 + 32 + i < p.N) ? poly_exp2(x1) : 0.f;  // FMA pipe
         e[i] = p0 * (__uint_as_float(d0[i]) - del);
         e[32 + i] = p1 * (__uint_as_float(d1[i]) - del);
       }
       store_row_bf16_sw128(sdS + u * Cfg::kSBytes + r * 128, r, e);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&ds_full[u]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[u]);
     }
     mbar_wait(dq_full, 0);
     tc_fence_after();
@@ -606,8 +623,8 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     tma_prefetch_desc(&tma_do64);
     mbar_init(kv_full, 1);
     mbar_init(sp_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(pds_full, 128);
+    mbar_init(s_free, 4);
+    mbar_init(pds_full, 4);
     mbar_init(pds_free, 1);
     mbar_init(acc_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -646,57 +663,59 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_a = make_idesc_bf16(128, DH, 0, 1);
-      auto issue_st_dpt = [&](int st) {
-        const uint32_t ak = smem_u32(sK), av = smem_u32(sV);
-        const uint32_t bq = smem_u32(sQ + st * Cfg::kBlkBytes), bo = smem_u32(sdO + st * Cfg::kBlkBytes);
-        const uint32_t dst = tmem_base + kColS, ddp = dst + 64;
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_a = make_idesc_bf16(128, DH, 0, 1);
+    constexpr uint32_t hi = smem_desc_hi_sw128(1024);
+    const uint32_t k_lo = smem_desc_lo(smem_u32(sK), 16), v_lo = smem_desc_lo(smem_u32(sV), 16);
+    const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16), do_lo = smem_desc_lo(smem_u32(sdO), 16);
+    const uint32_t qmn_lo = smem_desc_lo(smem_u32(sQ), 64 * 128), domn_lo = smem_desc_lo(smem_u32(sdO), 64 * 128);
+    const uint32_t pt_lo = smem_desc_lo(smem_u32(sPT), 16), dst_lo = smem_desc_lo(smem_u32(sdST), 16);
+    auto issue_st_dpt = [&](int st) {
+      const uint32_t bq = q_lo + st * (Cfg::kBlkBytes >> 4), bo = do_lo + st * (Cfg::kBlkBytes >> 4);
+      const uint32_t dst = tmem_base + kColS, ddp = dst + 64;
+      if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint32_t offa = (kk >> 2) * (128 * 128) + (kk & 3) * 32, offb = (kk >> 2) * (64 * 128) + (kk & 3) * 32;
-          umma_f16_ss(dst, make_smem_desc_sw128(ak + offa, 16, 1024), make_smem_desc_sw128(bq + offb, 16, 1024), idesc_s, kk != 0);
-        }
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_f16_ss2(dst, k_lo + (((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), hi,
+                       bq + (((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint32_t offa = (kk >> 2) * (128 * 128) + (kk & 3) * 32, offb = (kk >> 2) * (64 * 128) + (kk & 3) * 32;
-          umma_f16_ss(ddp, make_smem_desc_sw128(av + offa, 16, 1024), make_smem_desc_sw128(bo + offb, 16, 1024), idesc_s, kk != 0);
-        }
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_f16_ss2(ddp, v_lo + (((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), hi,
+                       bo + (((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
         umma_commit(sp_full);
-      };
-      mbar_wait(kv_full, 0);
-      mbar_wait(&q_full[0], 0);
-      mbar_wait(&do_full[0], 0);
-      tc_fence_after();
-      issue_st_dpt(0);
-      for (int j = 0; j < nq; ++j) {
-        const int st = j & 1;
-        if (j + 1 < nq) {
-          mbar_wait(&q_full[st ^ 1], ((j + 1) >> 1) & 1);
-          mbar_wait(&do_full[st ^ 1], ((j + 1) >> 1) & 1);
-          mbar_wait(s_free, j & 1);  // S^T / dP^T of block j are in registers: the TMEM columns can be overwritten
-          tc_fence_after();
-          issue_st_dpt(st ^ 1);
-        }
-        mbar_wait(pds_full, j & 1);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    mbar_wait(&q_full[0], 0);
+    mbar_wait(&do_full[0], 0);
+    tc_fence_after();
+    issue_st_dpt(0);
+    for (int j = 0; j < nq; ++j) {
+      const int st = j & 1;
+      if (j + 1 < nq) {
+        mbar_wait(&q_full[st ^ 1], ((j + 1) >> 1) & 1);
+        mbar_wait(&do_full[st ^ 1], ((j + 1) >> 1) & 1);
+        mbar_wait(s_free, j & 1);  // S^T / dP^T of block j are in registers: the TMEM columns can be overwritten
         tc_fence_after();
-        const uint32_t ap = smem_u32(sPT), as_ = smem_u32(sdST);
-        const uint32_t bo = smem_u32(sdO + st * Cfg::kBlkBytes), bq = smem_u32(sQ + st * Cfg::kBlkBytes);
+        issue_st_dpt(st ^ 1);
+      }
+      mbar_wait(pds_full, j & 1);
+      tc_fence_after();
+      const uint32_t bo = domn_lo + st * (Cfg::kBlkBytes >> 4), bq = qmn_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO
-          umma_f16_ss(tmem_base, make_smem_desc_sw128(ap + kk * 32, 16, 1024),
-                      make_smem_desc_sw128(bo + kk * 2048, 64 * 128, 1024), idesc_a, (j > 0) || (kk != 0));
+          umma_f16_ss2(tmem_base, pt_lo + ((kk * 32) >> 4), hi, bo + ((kk * 2048) >> 4), hi, idesc_a, (j > 0) || (kk != 0));
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q
-          umma_f16_ss(tmem_base + DH, make_smem_desc_sw128(as_ + kk * 32, 16, 1024),
-                      make_smem_desc_sw128(bq + kk * 2048, 64 * 128, 1024), idesc_a, (j > 0) || (kk != 0));
+          umma_f16_ss2(tmem_base + DH, dst_lo + ((kk * 32) >> 4), hi, bq + ((kk * 2048) >> 4), hi, idesc_a, (j > 0) || (kk != 0));
         umma_commit(&qdo_empty[st]);
         umma_commit(pds_free);
+        if (j + 1 == nq) umma_commit(acc_full);
       }
-      umma_commit(acc_full);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;        // key row within the tile
@@ -723,12 +742,13 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
       tmem_ld_32x32b_x32(s_addr + 96, d1);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(s_free);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
       float pt[64], ds[64];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float p0 = fast_exp2(__uint_as_float(a0[i]) * c - s_lse[u * 64 + i]);
-        const float p1 = fast_exp2(__uint_as_float(a1[i]) * c - s_lse[u * 64 + 32 + i]);
+        const float p0 = fast_exp2(fmaf(__uint_as_float(a0[i]), c, -s_lse[u * 64 + i]));       // MUFU pipe
+        const float p1 = poly_exp2(fmaf(__uint_as_float(a1[i]), c, -s_lse[u * 64 + 32 + i]));  // FMA pipe
         pt[i] = p0;
         pt[32 + i] = p1;
         ds[i] = p0 * (__uint_as_float(d0[i]) - s_del[u * 64 + i]);
@@ -739,7 +759,8 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
       store_row_bf16_sw128(sdST + r * 128, r, ds);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();

@@ -233,6 +233,29 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// Split form of the same descriptor: the high word is a compile-time constant and the low word is
+// (start address >> 4) | (LBO >> 4) << 16, so stepping along K inside the MMA issue loop is one 32-bit add.
+__host__ __device__ __forceinline__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ void umma_f16_ss2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                          // D format = F32
@@ -250,6 +273,18 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, rel. err ~1e-4 -- below bf16 resolution):
+// used for half of the softmax exponentials so the MUFU pipe (16 ex2/clk/SM) is not the attention bottleneck.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.0f);
+  const float fl = floorf(x);
+  const float fr = x - fl;
+  float p = fmaf(0.0771190f, fr, 0.2275643f);
+  p = fmaf(p, fr, 0.6951461f);
+  p = fmaf(p, fr, 1.0f);
+  return __int_as_float(__float_as_int(p) + (static_cast<int>(fl) << 23));
+}
+
 // Branch-free erf (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7): keeps the fused GELU epilogues short -- the
 // library erff() expands to ~40 instructions with two branches per element, which made every GEMM kernel > 150 KB of SASS.
 __device__ __forceinline__ float erf_as(float x) {

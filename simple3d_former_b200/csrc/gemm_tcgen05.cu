@@ -268,8 +268,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------- MMA issuer -------------------------------------------
-    if (lane == 0) {
+    // warp-converged control flow, one elected lane issues; descriptor low words precomputed per stage
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      const uint32_t hi_a = smem_desc_hi_sw128(A_MN ? p.mn_sbo : p.k_sbo), hi_b = smem_desc_hi_sw128(B_MN ? p.mn_sbo : p.k_sbo);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), A_MN ? p.mn_lbo : p.k_lbo);
+      const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem) + Cfg::kABytes, B_MN ? p.mn_lbo : p.k_lbo);
+      constexpr uint32_t kStepA = (A_MN ? 2048 : 32) >> 4, kStepB = (B_MN ? 2048 : 32) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -283,26 +288,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t a_lo = a_lo0 + stage * (Cfg::kStageBytes >> 4), b_lo = b_lo0 + stage * (Cfg::kStageBytes >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, p.mn_lbo, p.mn_sbo)
-                                        : make_smem_desc_sw128(sa + k * 32, p.k_lbo, p.k_sbo);
-            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, p.mn_lbo, p.mn_sbo)
-                                        : make_smem_desc_sw128(sb + k * 32, p.k_lbo, p.k_sbo);
-            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0) || (k != 0));
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss2(d_tmem, a_lo + k * kStepA, hi_a, b_lo + k * kStepB, hi_b, idesc, (kb > kb0) || (k != 0));
+            // frees the smem slot (in every CTA of the cluster) once these MMAs retire
+            if (CL > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
+            else umma_commit(&empty_bar[stage]);
+            if (kb + 1 == kb1) umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
           }
-          // frees the smem slot (in every CTA of the cluster) once these MMAs retire
-          if (CL > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        if (kb1 <= kb0) {  // empty split range: still hand the (unused) accumulator stage to the epilogue
+          if (elect_one()) umma_commit(&tmem_full[as]);
+          __syncwarp();
+        }
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp >= kEpiWarp0) {
     // -------------------------------------------- epilogue --------------------------------------------
     const int e = warp - kEpiWarp0;  // 0..7

@@ -236,7 +236,11 @@ class BlockFn(torch.autograd.Function):
         B, N, D, H, dh, scale, has_qb, has_pb, has_b1, has_b2 = ctx.meta
         T = B * N
         dy2 = dy.reshape(T, D).contiguous()
-        dy16 = L.cast_bf16(dy2)
+        # the downstream block's backward leaves a bf16 copy of this gradient on the tensor object (see below); autograd
+        # hands the same object through when it did not have to accumulate, which saves one cast pass per block
+        dy16 = getattr(dy, "_s3d_bf16", None)
+        if dy16 is None or dy16.shape != (T, D) or getattr(dy, "_s3d_bf16_src", None) != dy.data_ptr():
+            dy16 = L.cast_bf16(dy2)
         n1b, qkv_b, proj_b, n2b, fc1_b, fc2_b = ctx.refs
         # MLP
         dfc2_w = _wgrad(fc2_w, dy16, a16)
@@ -254,8 +258,11 @@ class BlockFn(torch.autograd.Function):
         dqkv_w = _wgrad(qkv_w, dqkv, h16)
         dqkv_b = _bgrad(qkv_b, dqkv)
         dh_ = L.gemm(dqkv, shadow(qkv_w), b_mn=True)
-        dx, _, dn1w, dn1b = _ln_bwd(dh_, x2, n1w, n1b, mean1, rstd1, dres=dx1)
-        return (dx.view(B, N, D), dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w,
+        dx, dx16, dn1w, dn1b = _ln_bwd(dh_, x2, n1w, n1b, mean1, rstd1, dres=dx1, want_bf16=True)
+        dx = dx.view(B, N, D)
+        dx._s3d_bf16 = dx16
+        dx._s3d_bf16_src = dx.data_ptr()
+        return (dx, dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w,
                 dfc2_b, None, None, None, None)
 
 
