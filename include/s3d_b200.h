@@ -96,10 +96,15 @@ int s3d_transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int 
                           void* stream);
 /* out[c] (+)= sum_t in[t, c]; Linear bias gradients */
 int s3d_colsum_bf16(const void* in, float* out, int T, int C, int64_t ld, int accumulate, void* stream);
-/* Conv3d(k = s = cell) operand: x f32 [B,1,V,V,V] -> P bf16 [B*p*p*(zsum?1:p), Kpad]; zsum sums the pz patches of a
- * column first (VoxelEmbed's mean over dim 4, embed_layer_3d_modality.py:38). */
-int s3d_voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
+/* Conv3d(k = s = cell) operand: x [B,1,V,V,V] -> P bf16 [B*p*p*(zsum?1:p), Kpad]; zsum sums the pz patches of a
+ * column first (VoxelEmbed's mean over dim 4, embed_layer_3d_modality.py:38). in_dtype: 0 = f32, 1 = uint8/bool,
+ * 2 = int32 (the dtype the reference's binvox loaders yield, data/modelnet40.py:40) -- no host-side .float() needed. */
+int s3d_voxel_patch_gather(const void* x, int in_dtype, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
                            void* stream);
+/* torch.optim.SGD(momentum) step (train_cls.py:91, train_partseg.py:95); same conventions as s3d_adam_step. */
+int s3d_sgd_momentum_step(float* param, const float* grad, float* momentum_buf, void* shadow_bf16, int64_t n, float lr,
+                          float momentum, float weight_decay, int step, const int* step_device, float grad_scale,
+                          void* stream);
 /* torch.optim.Adam step (train_cls_voxel.py:195) over a flat f32 segment; refreshes the bf16 shadow; grad_scale folds
  * the 1/world_size of the DDP gradient average (train_cls_voxel.py:154-165). step_device (optional, int32 on the
  * device) overrides `step` so a captured CUDA graph advances the bias correction on replay. */

@@ -33,7 +33,8 @@ SIGNATURES = {
     "s3d_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
     "s3d_transpose_to_bf16": (c_int, [_P, c_int, _P, c_int, c_int, c_int64, c_int64, _P]),
     "s3d_colsum_bf16": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, _P]),
-    "s3d_voxel_patch_gather": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s3d_voxel_patch_gather": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s3d_sgd_momentum_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_int, _P, c_float, _P]),
     "s3d_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, _P,
                               c_float, _P]),
     "s3d_knn": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
@@ -224,14 +225,23 @@ def colsum(x, out=None, accumulate=False):
     return out
 
 
+_VOXEL_DTYPES = {torch.float32: 0, torch.uint8: 1, torch.bool: 1, torch.int32: 2}
+
+
 def voxel_patch_gather(x, cell, patch, kpad, zsum):
     _need_cuda(x)
-    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5 and x.shape[1] == 1
+    assert x.dtype in _VOXEL_DTYPES and x.is_contiguous() and x.dim() == 5 and x.shape[1] == 1
     B, _, V, _, _ = x.shape
     rows = B * patch * patch * (1 if zsum else patch)
     P = torch.empty((rows, kpad), device=x.device, dtype=torch.bfloat16)
-    call("s3d_voxel_patch_gather", ptr(x), ptr(P), B, V, cell, patch, kpad, int(zsum), stream())
+    call("s3d_voxel_patch_gather", ptr(x), _VOXEL_DTYPES[x.dtype], ptr(P), B, V, cell, patch, kpad, int(zsum), stream())
     return P
+
+
+def sgd_momentum_step(p, g, buf, shadow, lr, momentum, weight_decay, step, grad_scale=1.0, step_tensor=None):
+    _need_cuda(p, g, buf)
+    call("s3d_sgd_momentum_step", ptr(p), ptr(g), ptr(buf), ptr(shadow), p.numel(), float(lr), float(momentum),
+         float(weight_decay), int(step), ptr(step_tensor), float(grad_scale), stream())
 
 
 def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, step_tensor=None):

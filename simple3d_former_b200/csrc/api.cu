@@ -134,9 +134,15 @@ int s3d_transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int 
 int s3d_colsum_bf16(const void* in, float* out, int T, int C, int64_t ld, int accumulate, void* stream) {
   return s3d::colsum_bf16(in, out, T, C, ld, accumulate, as_stream(stream));
 }
-int s3d_voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
+int s3d_voxel_patch_gather(const void* x, int in_dtype, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
                            void* stream) {
-  return s3d::voxel_patch_gather(x, P, B, V, cell, patch, Kpad, zsum, as_stream(stream));
+  return s3d::voxel_patch_gather(x, in_dtype, P, B, V, cell, patch, Kpad, zsum, as_stream(stream));
+}
+int s3d_sgd_momentum_step(float* param, const float* grad, float* momentum_buf, void* shadow_bf16, int64_t n, float lr,
+                          float momentum, float weight_decay, int step, const int* step_device, float grad_scale,
+                          void* stream) {
+  return s3d::sgd_momentum_step(param, grad, momentum_buf, shadow_bf16, n, lr, momentum, weight_decay, step, step_device,
+                                grad_scale, as_stream(stream));
 }
 int s3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, const int* step_device,

@@ -287,22 +287,31 @@ __device__ __forceinline__ float poly_exp2(float x) {
 
 // Branch-free erf (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7): keeps the fused GELU epilogues short -- the
 // library erff() expands to ~40 instructions with two branches per element, which made every GEMM kernel > 150 KB of SASS.
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+// GELU(x) = x * Phi(x), Phi(x) = 0.5 * (1 + erf(x / sqrt2)). With z = |x| / sqrt2, t = 1 / (1 + p z):
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) * exp(-z^2),   exp(-z^2) = exp(-x^2 / 2) is also the Gaussian pdf factor,
+// so value and derivative share one exponential (evaluated on the FMA pipe) and one MUFU reciprocal.
+struct GeluParts {
+  float cdf;  // Phi(x)
+  float e;    // exp(-x^2 / 2)
+};
+__device__ __forceinline__ GeluParts gelu_parts(float x) {
+  const float az = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float y = 1.0f - poly * fast_exp2(-1.4426950408889634f * ax * ax);
-  return copysignf(y, x);
+  const float e = poly_exp2(-0.72134752044448170f * x * x);
+  const float half_tail = 0.5f * poly * t * e;  // 0.5 * (1 - erf(z))
+  GeluParts r;
+  r.cdf = x >= 0.f ? 1.0f - half_tail : half_tail;
+  r.e = e;
+  return r;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_parts(x).cdf; }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * fast_exp2(-0.72134752044448170f * x * x);
-  return cdf + x * pdf;
+  const GeluParts g = gelu_parts(x);
+  return fmaf(x * 0.3989422804014327f, g.e, g.cdf);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

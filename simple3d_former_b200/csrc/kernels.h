@@ -50,8 +50,10 @@ int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t strea
 int transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int C, long long ld_in, long long ld_out,
                       cudaStream_t stream);
 int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accumulate, cudaStream_t stream);
-int voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
+int voxel_patch_gather(const void* x, int in_dtype, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
                        cudaStream_t stream);
+int sgd_momentum_step(float* p, const float* g, float* buf, void* shadow_bf16, long long n, float lr, float momentum,
+                      float weight_decay, int step, const int* step_dev, float grad_scale, cudaStream_t stream);
 int adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
               float beta2, float eps, float weight_decay, int step, const int* step_dev, float grad_scale,
               cudaStream_t stream);

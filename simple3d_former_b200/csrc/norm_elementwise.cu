@@ -386,7 +386,8 @@ int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accu
 // (VoxelEmbed's mean over dim 4, :38, commutes with the linear map; the 1/p factor is applied in the GEMM epilogue).
 // Occupancy values are 0/1 so sums <= p are exact in bf16.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) voxel_patch_gather_kernel(const float* __restrict__ x,
+template <typename TIn>
+__global__ void __launch_bounds__(256) voxel_patch_gather_kernel(const TIn* __restrict__ x,
                                                                 __nv_bfloat16* __restrict__ P, int B, int V, int c,
                                                                 int p, int Kpad, int zsum) {
   const int K = c * c * c;
@@ -416,10 +417,10 @@ __global__ void __launch_bounds__(256) voxel_patch_gather_kernel(const float* __
         const size_t base = (((size_t)b * V + (size_t)(px * c + dx)) * V + (size_t)(py * c + dy)) * V;
         if (zsum) {
           float s = 0.f;
-          for (int z = 0; z < p; ++z) s += x[base + (size_t)(z * c + dz)];
+          for (int z = 0; z < p; ++z) s += (float)x[base + (size_t)(z * c + dz)];
           v[e] = s;
         } else {
-          v[e] = x[base + (size_t)(pz * c + dz)];
+          v[e] = (float)x[base + (size_t)(pz * c + dz)];
         }
       }
     }
@@ -427,18 +428,26 @@ __global__ void __launch_bounds__(256) voxel_patch_gather_kernel(const float* __
   }
 }
 
-int voxel_patch_gather(const float* x, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
+// in_dtype: 0 = float32, 1 = uint8 / bool occupancy, 2 = int32 (what the reference's binvox loaders yield,
+// data/modelnet40.py:40, before `.float()` at train_cls_voxel.py:276)
+int voxel_patch_gather(const void* x, int in_dtype, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
                        cudaStream_t stream) {
   if (B <= 0 || V <= 0 || cell <= 0 || patch <= 0 || patch * cell > V || Kpad < cell * cell * cell || Kpad % 8 != 0)
     return S3D_ERR_BAD_SHAPE;
   if (x == nullptr || P == nullptr) return S3D_ERR_NULL;
+  if (in_dtype < 0 || in_dtype > 2) return S3D_ERR_UNSUPPORTED;
   const long long rows = (long long)B * patch * patch * (zsum ? 1 : patch);
   const long long total = rows * (Kpad / 2);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  voxel_patch_gather_kernel<<<(int)blocks, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(P), B, V, cell,
-                                                             patch, Kpad, zsum);
+  auto out = reinterpret_cast<__nv_bfloat16*>(P);
+  if (in_dtype == 0)
+    voxel_patch_gather_kernel<float><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(x), out, B, V, cell, patch, Kpad, zsum);
+  else if (in_dtype == 1)
+    voxel_patch_gather_kernel<uint8_t><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(x), out, B, V, cell, patch, Kpad, zsum);
+  else
+    voxel_patch_gather_kernel<int><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const int*>(x), out, B, V, cell, patch, Kpad, zsum);
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -486,6 +495,40 @@ int adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, l
   if (blocks > cap) blocks = cap;
   adam_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), (size_t)n,
                                                lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale, step_dev);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused SGD with momentum (torch.optim.SGD semantics, dampening 0, no nesterov): the optimizer of the point scripts
+// (train_cls.py:91, train_partseg.py:95). buf = mu * buf + g (buf = g on the first step); p -= lr * buf.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                 float* __restrict__ buf, __nv_bfloat16* __restrict__ shadow, size_t n,
+                                                 float lr, float momentum, float weight_decay, float grad_scale,
+                                                 int first_step, const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) first_step = (*step_dev <= 1);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    float gi = g[i] * grad_scale;
+    if (weight_decay != 0.f) gi += weight_decay * pi;
+    const float b = first_step ? gi : momentum * buf[i] + gi;
+    buf[i] = b;
+    const float pn = pi - lr * b;
+    p[i] = pn;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16(pn);
+  }
+}
+
+int sgd_momentum_step(float* p, const float* g, float* buf, void* shadow_bf16, long long n, float lr, float momentum,
+                      float weight_decay, int step, const int* step_dev, float grad_scale, cudaStream_t stream) {
+  if (n <= 0 || (step <= 0 && step_dev == nullptr)) return S3D_ERR_BAD_SHAPE;
+  if (p == nullptr || g == nullptr || buf == nullptr) return S3D_ERR_NULL;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  sgd_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, buf, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), (size_t)n, lr, momentum,
+                                              weight_decay, grad_scale, step == 1, step_dev);
   S3D_LAUNCH_OK();
   return S3D_OK;
 }

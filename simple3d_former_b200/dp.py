@@ -138,11 +138,15 @@ class FlatGradBuckets:
 
 class DataParallelTrainer:
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, bucket_mb=25.0,
-                 process_group=None, exclude=()):
+                 process_group=None, exclude=(), optimizer="adam", momentum=0.9):
+        """optimizer: "adam" (train_cls_voxel.py:195) or "sgd" (momentum SGD of train_cls.py:91 / train_partseg.py:95)."""
         from . import _lib as L
         self._L = L
         self.model = model
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        if optimizer not in ("adam", "sgd"):
+            raise ValueError("optimizer must be 'adam' or 'sgd'")
+        self.optimizer, self.momentum = optimizer, momentum
         exclude = set(exclude)
         for n, p in model.named_parameters():
             if n in exclude:
@@ -175,6 +179,11 @@ class DataParallelTrainer:
         self.step_count += 1
         self.step_t += 1
         f = self.flat
+        if self.optimizer == "sgd":
+            self._L.sgd_momentum_step(f.flat_p, f.flat_g, self.flat_m, self.flat_s, self.lr, self.momentum,
+                                      self.weight_decay, self.step_count, grad_scale=1.0 / self.world,
+                                      step_tensor=self.step_t)
+            return
         self._L.adam_step(f.flat_p, f.flat_g, self.flat_m, self.flat_v, self.flat_s, self.lr, self.betas[0],
                           self.betas[1], self.eps, self.weight_decay, self.step_count, grad_scale=1.0 / self.world,
                           step_tensor=self.step_t)

@@ -296,7 +296,9 @@ class VoxelPatchifyFn(torch.autograd.Function):
         D = weight.shape[0]
         K = cell ** 3
         kpad = (K + 63) // 64 * 64
-        P = L.voxel_patch_gather(x.contiguous().float(), cell, patch, kpad, zmean)
+        if x.dtype not in (torch.float32, torch.uint8, torch.bool, torch.int32):
+            x = x.float()
+        P = L.voxel_patch_gather(x.contiguous(), cell, patch, kpad, zmean)  # uint8 / int32 occupancy is read as is
         w16 = _padded_conv_weight(weight, K, kpad)
         alpha = 1.0 / patch if zmean else 1.0
         tok = L.gemm(P, w16, bias=bias, alpha=alpha, out_dtype=torch.float32)  # [B*p*p(*p), D]
