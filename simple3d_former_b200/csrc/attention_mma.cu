@@ -505,6 +505,173 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_dkv_kernel(const AttnPar
   }
 }
 
+// ================================================================================================
+// Backward for tiny sequences (N <= 16), fully fused: one warp owns one (batch, head) and produces delta, dQ, dK and dV
+// from a single read of Q, K, V, dO (smem) and O (global). Replaces the delta + dQ + dK/dV kernel trio for the stage-1
+// sequences of the group-embed model (12544 x 3 heads x 15 tokens x 12 layers): these are HBM-bound, so reading the
+// operands once instead of twice is the whole win.
+// ================================================================================================
+template <int DH, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  constexpr int kTile = 16 * DH * 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long bh = (long long)blockIdx.x * NWARPS + warp;
+  if (bh >= (long long)p.B * p.H) return;  // warp-uniform; only __syncwarp below
+  const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+  const uint32_t sbase = smem_u32(smem_attn) + warp * 4 * kTile;
+  const uint32_t sQ = sbase, sK = sbase + kTile, sV = sbase + 2 * kTile, sdO = sbase + 3 * kTile;
+  const long long qoff = (long long)b * p.qkv_bs + (long long)h * p.qkv_hs;
+  const long long ooff = (long long)b * p.o_bs + (long long)h * p.o_hs;
+  load_tile<DH, 16>(sQ, p.q + qoff, p.qkv_rs, 0, p.N, lane, 32);
+  load_tile<DH, 16>(sK, p.k + qoff, p.qkv_rs, 0, p.N, lane, 32);
+  load_tile<DH, 16>(sV, p.v + qoff, p.qkv_rs, 0, p.N, lane, 32);
+  load_tile<DH, 16>(sdO, p.dout + ooff, p.o_rs, 0, p.N, lane, 32);
+  cp_async_commit();
+
+  // delta_i = sum_d dO[i,d] * O[i,d] straight from global memory (overlaps the cp.async traffic); every lane ends up
+  // with the values of "its" rows (lane/4, lane/4+8) and "its" columns (2*(lane%4)+{0,1} (+8)).
+  const float* glse = p.lse + bh * p.N;
+  float del_r0 = 0.f, del_r1 = 0.f, del_c[4] = {0.f, 0.f, 0.f, 0.f};
+  const int r0 = lane >> 2, r1 = r0 + 8;
+  const int c0 = 2 * (lane & 3);
+  for (int i = 0; i < p.N; ++i) {
+    float s = 0.f;
+    for (int d = lane * 8; d < DH; d += 256) {
+      const uint4 uo = *reinterpret_cast<const uint4*>(p.o + ooff + (long long)i * p.o_rs + d);
+      const uint4 ug = *reinterpret_cast<const uint4*>(p.dout + ooff + (long long)i * p.o_rs + d);
+      const float2 o0 = unpack_bf16x2(uo.x), o1 = unpack_bf16x2(uo.y), o2 = unpack_bf16x2(uo.z), o3 = unpack_bf16x2(uo.w);
+      const float2 g0 = unpack_bf16x2(ug.x), g1 = unpack_bf16x2(ug.y), g2 = unpack_bf16x2(ug.z), g3 = unpack_bf16x2(ug.w);
+      s += (o0.x * g0.x + o0.y * g0.y) + (o1.x * g1.x + o1.y * g1.y) + (o2.x * g2.x + o2.y * g2.y) + (o3.x * g3.x + o3.y * g3.y);
+    }
+    s = warp_sum(s);
+    if (i == r0) del_r0 = s;
+    if (i == r1) del_r1 = s;
+    if (i == c0) del_c[0] = s;
+    if (i == c0 + 1) del_c[1] = s;
+    if (i == c0 + 8) del_c[2] = s;
+    if (i == c0 + 9) del_c[3] = s;
+  }
+  // padded rows / columns: lse = +inf makes P = 0
+  const float lse_r0 = r0 < p.N ? glse[r0] * kLog2e : INFINITY, lse_r1 = r1 < p.N ? glse[r1] * kLog2e : INFINITY;
+  float lse_c[4];
+  lse_c[0] = c0 < p.N ? glse[c0] * kLog2e : INFINITY;
+  lse_c[1] = c0 + 1 < p.N ? glse[c0 + 1] * kLog2e : INFINITY;
+  lse_c[2] = c0 + 8 < p.N ? glse[c0 + 8] * kLog2e : INFINITY;
+  lse_c[3] = c0 + 9 < p.N ? glse[c0 + 9] * kLog2e : INFINITY;
+  const float sc = p.scale * kLog2e;
+  cp_async_wait<0>();
+  __syncwarp();
+
+  // ---- S = Q K^T, dP = dO V^T (rows = queries)
+  float s[2][4] = {}, dp[2][4] = {};
+#pragma unroll
+  for (int ks = 0; ks < DH / 16; ++ks) {
+    uint32_t a0, a1, a2, a3, g0, g1, g2, g3, b0, b1, b2, b3;
+    ldsm_x4(tile_addr<DH>(sQ, lane & 15, ks * 2 + (lane >> 4)), a0, a1, a2, a3);
+    ldsm_x4(tile_addr<DH>(sdO, lane & 15, ks * 2 + (lane >> 4)), g0, g1, g2, g3);
+    const int krow = (lane & 7) + ((lane >> 4) << 3), kch = ks * 2 + ((lane >> 3) & 1);
+    ldsm_x4(tile_addr<DH>(sK, krow, kch), b0, b1, b2, b3);
+    mma16816(s[0], a0, a1, a2, a3, b0, b1);
+    mma16816(s[1], a0, a1, a2, a3, b2, b3);
+    ldsm_x4(tile_addr<DH>(sV, krow, kch), b0, b1, b2, b3);
+    mma16816(dp[0], g0, g1, g2, g3, b0, b1);
+    mma16816(dp[1], g0, g1, g2, g3, b2, b3);
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const int kidx = nt * 8 + c0;
+    const bool v0 = kidx < p.N, v1 = kidx + 1 < p.N;
+    const float p00 = v0 ? exp2f(s[nt][0] * sc - lse_r0) : 0.f, p01 = v1 ? exp2f(s[nt][1] * sc - lse_r0) : 0.f;
+    const float p10 = v0 ? exp2f(s[nt][2] * sc - lse_r1) : 0.f, p11 = v1 ? exp2f(s[nt][3] * sc - lse_r1) : 0.f;
+    s[nt][0] = p00 * (dp[nt][0] - del_r0);
+    s[nt][1] = p01 * (dp[nt][1] - del_r0);
+    s[nt][2] = p10 * (dp[nt][2] - del_r1);
+    s[nt][3] = p11 * (dp[nt][3] - del_r1);
+  }
+  {  // ---- dQ = dS K
+    const uint32_t a0 = pack_bf16x2(s[0][0], s[0][1]), a1 = pack_bf16x2(s[0][2], s[0][3]);
+    const uint32_t a2 = pack_bf16x2(s[1][0], s[1][1]), a3 = pack_bf16x2(s[1][2], s[1][3]);
+    __nv_bfloat16* gdq = p.dq + qoff;
+#pragma unroll
+    for (int dt2 = 0; dt2 < DH / 16; ++dt2) {
+      float acc0[4] = {}, acc1[4] = {};
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(tile_addr<DH>(sK, (lane & 7) + (((lane >> 3) & 1) << 3), dt2 * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma16816(acc0, a0, a1, a2, a3, b0, b1);
+      mma16816(acc1, a0, a1, a2, a3, b2, b3);
+      const int col = dt2 * 16 + c0;
+      if (r0 < p.N) {
+        *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * p.qkv_rs + col) = pack_bf16x2(acc0[0] * p.scale, acc0[1] * p.scale);
+        *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * p.qkv_rs + col + 8) = pack_bf16x2(acc1[0] * p.scale, acc1[1] * p.scale);
+      }
+      if (r1 < p.N) {
+        *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * p.qkv_rs + col) = pack_bf16x2(acc0[2] * p.scale, acc0[3] * p.scale);
+        *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * p.qkv_rs + col + 8) = pack_bf16x2(acc1[2] * p.scale, acc1[3] * p.scale);
+      }
+    }
+  }
+  // ---- transposed products (rows = keys): S^T = K Q^T, dP^T = V dO^T
+  float st[2][4] = {}, dpt[2][4] = {};
+#pragma unroll
+  for (int ks = 0; ks < DH / 16; ++ks) {
+    uint32_t a0, a1, a2, a3, g0, g1, g2, g3, b0, b1, b2, b3;
+    ldsm_x4(tile_addr<DH>(sK, lane & 15, ks * 2 + (lane >> 4)), a0, a1, a2, a3);
+    ldsm_x4(tile_addr<DH>(sV, lane & 15, ks * 2 + (lane >> 4)), g0, g1, g2, g3);
+    const int qrow = (lane & 7) + ((lane >> 4) << 3), qch = ks * 2 + ((lane >> 3) & 1);
+    ldsm_x4(tile_addr<DH>(sQ, qrow, qch), b0, b1, b2, b3);
+    mma16816(st[0], a0, a1, a2, a3, b0, b1);
+    mma16816(st[1], a0, a1, a2, a3, b2, b3);
+    ldsm_x4(tile_addr<DH>(sdO, qrow, qch), b0, b1, b2, b3);
+    mma16816(dpt[0], g0, g1, g2, g3, b0, b1);
+    mma16816(dpt[1], g0, g1, g2, g3, b2, b3);
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const float l0 = lse_c[2 * nt], l1 = lse_c[2 * nt + 1], d0 = del_c[2 * nt], d1 = del_c[2 * nt + 1];
+    const float p00 = exp2f(st[nt][0] * sc - l0), p01 = exp2f(st[nt][1] * sc - l1);
+    const float p10 = exp2f(st[nt][2] * sc - l0), p11 = exp2f(st[nt][3] * sc - l1);
+    st[nt][0] = p00; st[nt][1] = p01; st[nt][2] = p10; st[nt][3] = p11;
+    dpt[nt][0] = p00 * (dpt[nt][0] - d0);
+    dpt[nt][1] = p01 * (dpt[nt][1] - d1);
+    dpt[nt][2] = p10 * (dpt[nt][2] - d0);
+    dpt[nt][3] = p11 * (dpt[nt][3] - d1);
+  }
+  {  // ---- dV = P^T dO, dK = dS^T Q
+    const uint32_t pa0 = pack_bf16x2(st[0][0], st[0][1]), pa1 = pack_bf16x2(st[0][2], st[0][3]);
+    const uint32_t pa2 = pack_bf16x2(st[1][0], st[1][1]), pa3 = pack_bf16x2(st[1][2], st[1][3]);
+    const uint32_t sa0 = pack_bf16x2(dpt[0][0], dpt[0][1]), sa1 = pack_bf16x2(dpt[0][2], dpt[0][3]);
+    const uint32_t sa2 = pack_bf16x2(dpt[1][0], dpt[1][1]), sa3 = pack_bf16x2(dpt[1][2], dpt[1][3]);
+    __nv_bfloat16* gdk = p.dk + qoff;
+    __nv_bfloat16* gdv = p.dv + qoff;
+    const int qrow = (lane & 7) + (((lane >> 3) & 1) << 3);
+#pragma unroll
+    for (int dt2 = 0; dt2 < DH / 16; ++dt2) {
+      float v0[4] = {}, v1[4] = {}, k0[4] = {}, k1[4] = {};
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(tile_addr<DH>(sdO, qrow, dt2 * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma16816(v0, pa0, pa1, pa2, pa3, b0, b1);
+      mma16816(v1, pa0, pa1, pa2, pa3, b2, b3);
+      ldsm_x4_t(tile_addr<DH>(sQ, qrow, dt2 * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma16816(k0, sa0, sa1, sa2, sa3, b0, b1);
+      mma16816(k1, sa0, sa1, sa2, sa3, b2, b3);
+      const int col = dt2 * 16 + c0;
+      if (r0 < p.N) {
+        *reinterpret_cast<uint32_t*>(gdv + (long long)r0 * p.qkv_rs + col) = pack_bf16x2(v0[0], v0[1]);
+        *reinterpret_cast<uint32_t*>(gdv + (long long)r0 * p.qkv_rs + col + 8) = pack_bf16x2(v1[0], v1[1]);
+        *reinterpret_cast<uint32_t*>(gdk + (long long)r0 * p.qkv_rs + col) = pack_bf16x2(k0[0] * p.scale, k0[1] * p.scale);
+        *reinterpret_cast<uint32_t*>(gdk + (long long)r0 * p.qkv_rs + col + 8) = pack_bf16x2(k1[0] * p.scale, k1[1] * p.scale);
+      }
+      if (r1 < p.N) {
+        *reinterpret_cast<uint32_t*>(gdv + (long long)r1 * p.qkv_rs + col) = pack_bf16x2(v0[2], v0[3]);
+        *reinterpret_cast<uint32_t*>(gdv + (long long)r1 * p.qkv_rs + col + 8) = pack_bf16x2(v1[2], v1[3]);
+        *reinterpret_cast<uint32_t*>(gdk + (long long)r1 * p.qkv_rs + col) = pack_bf16x2(k0[2] * p.scale, k0[3] * p.scale);
+        *reinterpret_cast<uint32_t*>(gdk + (long long)r1 * p.qkv_rs + col + 8) = pack_bf16x2(k1[2] * p.scale, k1[3] * p.scale);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host dispatch
 // ------------------------------------------------------------------------------------------------
@@ -555,6 +722,16 @@ static int attn_fwd_dh(const AttnParams& p, cudaStream_t stream) {
 template <int DH>
 static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
   const long long BH = (long long)p.B * p.H;
+  if (p.N <= 16) {  // fused delta + dQ + dK + dV, one warp per (batch, head)
+    constexpr int NW = (DH == 64) ? 4 : 2;
+    constexpr int smem = NW * 4 * 16 * DH * 2;
+    auto kern = attn_bwd_small_kernel<DH, NW>;
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    kern<<<(unsigned)((BH + NW - 1) / NW), NW * 32, smem, stream>>>(p);
+    S3D_LAUNCH_OK();
+    return S3D_OK;
+  }
   {
     const long long rows = BH * p.N;
     attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(p, DH);
