@@ -51,7 +51,7 @@ const char* s3d_error_string(int code);
  *   epilogue order: v = alpha*acc; v += bias[n]; GELU: (aux_out = bf16(v)), v = gelu_erf(v);
  *                   DGELU: v *= gelu_erf'(aux_in[m,n]); RELU: v = max(v,0); DRELU: v = aux_in[m,n] > 0 ? v : 0;
  *                   v += residual[m,n]; D = (out_fp32 ? v : bf16(v)).
- *   residual (fp32) requires out_fp32 = 1 and may alias D (fp32 accumulate). batch > 1 runs `batch` independent problems with element strides.
+ *   residual may alias D (fp32 accumulate). batch > 1 runs `batch` independent problems with element strides.
  *   force_bn / force_cluster / force_splits: 0 = heuristic; otherwise tile N (64/128/256), cluster size along M
  *   (1/2/4, TMA multicast of the B tile) and split-K factor (fp32 outputs without activation epilogue only).
  * ------------------------------------------------------------------------------------------------------------- */

@@ -146,49 +146,6 @@ __device__ __forceinline__ void stage_f32(uint8_t* srow, int r, const float (&f)
     *reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4)) = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
 }
 
-// Coalesced load of a [32 rows x 128 bytes] block of an epilogue operand (dGELU / dReLU input, fp32 residual) for this
-// warp: 8 lanes cover one 128-byte row (4 rows = 4 cache lines per instruction instead of 32 with one row per lane),
-// transposed through the warp's staging tile so that lane r ends up with row r (8 x 16 bytes). Rows >= rows_valid and
-// bytes >= bytes_valid read as zero.
-__device__ __forceinline__ void load_rows_128B(const uint8_t* gblock, long long row_pitch_bytes, int rows_valid,
-                                               int bytes_valid, uint8_t* stage, int lane, uint4 (&out)[8]) {
-  const int ch = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = i * 4 + (lane >> 3);
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row < rows_valid && ch * 16 < bytes_valid) v = *reinterpret_cast<const uint4*>(gblock + (long long)row * row_pitch_bytes + ch * 16);
-    *reinterpret_cast<uint4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 8; ++q) out[q] = *reinterpret_cast<const uint4*>(stage + lane * 128 + ((q ^ (lane & 7)) << 4));
-  __syncwarp();
-}
-
-// activation-gradient epilogues with the auxiliary operand already in registers (32 bf16 = 4 x uint4)
-__device__ __forceinline__ void epi_act_aux(int epilogue, const uint4* aux, float (&f)[32]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float2 a0 = unpack_bf16x2(aux[q].x), a1 = unpack_bf16x2(aux[q].y), a2 = unpack_bf16x2(aux[q].z), a3 = unpack_bf16x2(aux[q].w);
-    const float a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (epilogue == EPI_DGELU) f[q * 8 + j] *= gelu_erf_grad(a[j]);
-      else f[q * 8 + j] = a[j] > 0.f ? f[q * 8 + j] : 0.f;
-    }
-  }
-}
-__device__ __forceinline__ void epi_add_f32(const uint4 (&res)[8], float (&f)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    f[q * 4 + 0] += __uint_as_float(res[q].x);
-    f[q * 4 + 1] += __uint_as_float(res[q].y);
-    f[q * 4 + 2] += __uint_as_float(res[q].z);
-    f[q * 4 + 3] += __uint_as_float(res[q].w);
-  }
-}
-
 template <int BN, int A_MN, int B_MN, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -398,31 +355,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 tma_store_commit();
               }
             }
-            const bool need_aux = (p.epilogue == EPI_DGELU || p.epilogue == EPI_DRELU);
-            const int rows_valid = p.M - m_box;  // may be <= 0 or > 32; the loader clamps
-            uint4 aux[8];
-            if (need_aux) {  // both 32-column halves of the bf16 auxiliary operand in one coalesced 128-byte-row block
-              if (lane == 0) tma_store_wait_read();
-              __syncwarp();
-              load_rows_128B(reinterpret_cast<const uint8_t*>(p.aux_in + (long long)m_box * p.ld_aux_in + n),
-                             p.ld_aux_in * 2, rows_valid, (p.N - n) * 2, stage, lane, aux);
-            }
 #pragma unroll 1
             for (int hh = 0; hh < nh; ++hh) {
               float f[32];
               const int nn = n + 32 * hh;
               epi_load(p, trow + col0 + 32 * hh, nn, split, f);
-              if (need_aux) epi_act_aux(p.epilogue, aux + 4 * hh, f);
-              else epi_act(p, row, row_ok, nn, f);
-              if (hh == 0 || p.residual != nullptr) {  // the previous store has finished reading the staging tile
+              epi_act(p, row, row_ok, nn, f);
+              epi_residual(p, boff_r, row, row_ok, nn, f);
+              if (hh == 0) {  // the previous store has finished reading the staging tile
                 if (lane == 0) tma_store_wait_read();
                 __syncwarp();
-              }
-              if (p.residual != nullptr && nn < p.N) {
-                uint4 res[8];
-                load_rows_128B(reinterpret_cast<const uint8_t*>(p.residual + boff_r + (long long)m_box * p.ldr + nn),
-                               p.ldr * 4, rows_valid, (p.N - nn) * 4, stage, lane, res);
-                epi_add_f32(res, f);
               }
               if (p.out_fp32) stage_f32(srow, lane, f);
               else stage_bf16(srow, lane, hh, f);
@@ -791,9 +733,6 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
     return S3D_ERR_ALIGNMENT;
   if (p.aux_out != nullptr && (p.ld_aux_out % 8 != 0 || (reinterpret_cast<uintptr_t>(p.aux_out) & 15) != 0))
     return S3D_ERR_ALIGNMENT;
-  // the staged epilogue transposes the fp32 residual through the same smem tile it stages the output in, which only
-  // works for 128-byte (fp32) output rows
-  if (p.residual != nullptr && !p.out_fp32) return S3D_ERR_UNSUPPORTED;
   const int sms = num_sms();
   const int nb = g.batch > 1 ? g.batch : 1;
   const int num_m = (p.M + BM - 1) / BM;
