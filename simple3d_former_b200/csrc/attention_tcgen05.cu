@@ -348,7 +348,9 @@ static int fa_fwd_launch(const AttnParams& a, cudaStream_t stream) {
 //          dS = P o (dP - delta) -> bf16 smem,  dQ += dS K  (K block re-read as an MN-major B operand)
 //   dKdV : CTA = 128 key rows; per 64-query block S^T = K Q^T, dP^T = V dO^T,  P^T / dS^T -> bf16 smem,
 //          dV += P^T dO,  dK += dS^T Q  (Q / dO blocks re-read as MN-major B operands)
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 element-wise (one TMEM lane = one row each).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 element-wise: a TMEM lane (= row) is shared by
+// two threads (warps w and w+4 reach the same lane quadrant), each handling 32 of the 64 columns of a block -- the
+// element-wise phase (exp2, dS, bf16 stores) is what paces these kernels, so it gets 8 warps.
 // ================================================================================================
 struct FaBwdParams {
   __nv_bfloat16 *dq, *dk, *dv;  // outputs, qkv strides
@@ -362,7 +364,7 @@ struct FaBwdParams {
   float scale;
 };
 
-constexpr int kFaBwdThreads = 192;
+constexpr int kFaBwdThreads = 320;
 
 template <int DH>
 struct FaBwdCfg {
@@ -372,15 +374,16 @@ struct FaBwdCfg {
   static constexpr int kSmemBytes = 2 * kTileBytes + 4 * kBlkBytes + 2 * kSBytes + 1024 + 1024;
 };
 
-__device__ __forceinline__ void store_row_bf16_sw128(uint8_t* row_base, int r, const float (&e)[64]) {
+// 32 bf16 (half of a 128-byte row) into the 128B-swizzled tile: logical 16-byte chunks half*4 .. half*4+3 of row r
+__device__ __forceinline__ void store_half_row_bf16_sw128(uint8_t* row_base, int r, int half, const float (&e)[32]) {
 #pragma unroll
-  for (int ch = 0; ch < 8; ++ch) {
+  for (int q = 0; q < 4; ++q) {
     uint4 u;
-    u.x = pack_bf16x2(e[ch * 8 + 0], e[ch * 8 + 1]);
-    u.y = pack_bf16x2(e[ch * 8 + 2], e[ch * 8 + 3]);
-    u.z = pack_bf16x2(e[ch * 8 + 4], e[ch * 8 + 5]);
-    u.w = pack_bf16x2(e[ch * 8 + 6], e[ch * 8 + 7]);
-    *reinterpret_cast<uint4*>(row_base + ((ch ^ (r & 7)) << 4)) = u;
+    u.x = pack_bf16x2(e[q * 8 + 0], e[q * 8 + 1]);
+    u.y = pack_bf16x2(e[q * 8 + 2], e[q * 8 + 3]);
+    u.z = pack_bf16x2(e[q * 8 + 4], e[q * 8 + 5]);
+    u.w = pack_bf16x2(e[q * 8 + 6], e[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(row_base + (((half * 4 + q) ^ (r & 7)) << 4)) = u;
   }
 }
 
@@ -430,7 +433,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&sp_full[i], 1);
-      mbar_init(&ds_full[i], 4);
+      mbar_init(&ds_full[i], 8);  // one arrive per element-wise warp
     }
     fence_barrier_init();
   }
@@ -514,6 +517,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
     }
   } else {
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;  // which 32 of the 64 key columns of a block this thread handles
     const int r = quad * 32 + lane;
     const int row = q0 + r;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -525,24 +529,20 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
       const int u = j & 1;
       mbar_wait(&sp_full[u], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t a0[32], a1[32], d0[32], d1[32];
-      const uint32_t s_addr = tmem_base + lane_addr + kColS + u * 128;
+      uint32_t a0[32], d0[32];
+      const uint32_t s_addr = tmem_base + lane_addr + kColS + u * 128 + half * 32;
       tmem_ld_32x32b_x32(s_addr, a0);
-      tmem_ld_32x32b_x32(s_addr + 32, a1);
       tmem_ld_32x32b_x32(s_addr + 64, d0);
-      tmem_ld_32x32b_x32(s_addr + 96, d1);
       tc_wait_ld();
-      float e[64];
-      const int key0 = j * 64;
+      float e[32];
+      const int key0 = j * 64 + half * 32;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float x0 = fmaf(__uint_as_float(a0[i]), c, -lse2), x1 = fmaf(__uint_as_float(a1[i]), c, -lse2);
-        const float p0 = (key0 + i < p.N) ? fast_exp2(x0) : 0.f;       // MUFU pipe
-        const float p1 = (key0 + 32 + i < p.N) ? poly_exp2(x1) : 0.f;  // FMA pipe
+        const float x0 = fmaf(__uint_as_float(a0[i]), c, -lse2);
+        const float p0 = (key0 + i < p.N) ? ((i & 1) ? poly_exp2(x0) : fast_exp2(x0)) : 0.f;  // MUFU / FMA pipes alternate
         e[i] = p0 * (__uint_as_float(d0[i]) - del);
-        e[32 + i] = p1 * (__uint_as_float(d1[i]) - del);
       }
-      store_row_bf16_sw128(sdS + u * Cfg::kSBytes + r * 128, r, e);
+      store_half_row_bf16_sw128(sdS + u * Cfg::kSBytes + r * 128, r, half, e);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -552,7 +552,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
     tc_fence_after();
     __nv_bfloat16* orow = p.dq + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)row * p.qkv_rs;
 #pragma unroll 1
-    for (int cc = 0; cc < DH; cc += 32) {
+    for (int cc = half * (DH / 2); cc < (half + 1) * (DH / 2); cc += 32) {
       uint32_t o[32];
       tmem_ld_32x32b_x32(tmem_base + lane_addr + cc, o);
       tc_wait_ld();
@@ -623,8 +623,8 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     tma_prefetch_desc(&tma_do64);
     mbar_init(kv_full, 1);
     mbar_init(sp_full, 1);
-    mbar_init(s_free, 4);
-    mbar_init(pds_full, 4);
+    mbar_init(s_free, 8);  // one arrive per element-wise warp
+    mbar_init(pds_full, 8);
     mbar_init(pds_free, 1);
     mbar_init(acc_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -718,45 +718,44 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     }
   } else {
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;      // which 32 of the 64 query columns of a block this thread handles
     const int r = quad * 32 + lane;        // key row within the tile
-    const int tid = threadIdx.x - 64;      // 0..127 within the element-wise group
+    const int tid = threadIdx.x - 64;      // 0..255 within the element-wise group
     const int krow = k0 + r;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const long long bh = (long long)b * p.H + h;
     const float c = p.scale * kFaLog2e;
     for (int j = 0; j < nq; ++j) {
       const int u = j & 1;
-      {  // stage lse / delta of this query block (padded queries: lse = +inf -> P = 0)
+      if (tid < 128) {  // stage lse / delta of this query block (padded queries: lse = +inf -> P = 0)
         const int qi = j * 64 + (tid & 63);
         if (tid < 64) s_lse[u * 64 + tid] = qi < p.N ? p.lse[bh * p.N + qi] * kFaLog2e : INFINITY;
         else s_del[u * 64 + (tid & 63)] = qi < p.N ? p.delta[bh * p.N + qi] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sp_full, j & 1);
       tc_fence_after();
-      uint32_t a0[32], a1[32], d0[32], d1[32];
-      const uint32_t s_addr = tmem_base + lane_addr + kColS;
+      uint32_t a0[32], d0[32];
+      const uint32_t s_addr = tmem_base + lane_addr + kColS + half * 32;
       tmem_ld_32x32b_x32(s_addr, a0);
-      tmem_ld_32x32b_x32(s_addr + 32, a1);
       tmem_ld_32x32b_x32(s_addr + 64, d0);
-      tmem_ld_32x32b_x32(s_addr + 96, d1);
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
-      float pt[64], ds[64];
+      float pt[32], ds[32];
+      const float* lrow = s_lse + u * 64 + half * 32;
+      const float* drow = s_del + u * 64 + half * 32;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(a0[i]), c, -s_lse[u * 64 + i]));       // MUFU pipe
-        const float p1 = poly_exp2(fmaf(__uint_as_float(a1[i]), c, -s_lse[u * 64 + 32 + i]));  // FMA pipe
+        const float x0 = fmaf(__uint_as_float(a0[i]), c, -lrow[i]);
+        const float p0 = (i & 1) ? poly_exp2(x0) : fast_exp2(x0);  // MUFU / FMA pipes alternate
         pt[i] = p0;
-        pt[32 + i] = p1;
-        ds[i] = p0 * (__uint_as_float(d0[i]) - s_del[u * 64 + i]);
-        ds[32 + i] = p1 * (__uint_as_float(d1[i]) - s_del[u * 64 + 32 + i]);
+        ds[i] = p0 * (__uint_as_float(d0[i]) - drow[i]);
       }
       if (j > 0) mbar_wait(pds_free, (j - 1) & 1);  // dV / dK MMAs of block j-1 no longer read the smem tiles
-      store_row_bf16_sw128(sPT + r * 128, r, pt);
-      store_row_bf16_sw128(sdST + r * 128, r, ds);
+      store_half_row_bf16_sw128(sPT + r * 128, r, half, pt);
+      store_half_row_bf16_sw128(sdST + r * 128, r, half, ds);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -767,7 +766,7 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     __nv_bfloat16* kr = p.dk + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
     __nv_bfloat16* vr = p.dv + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
 #pragma unroll 1
-    for (int cc = 0; cc < DH; cc += 32) {
+    for (int cc = half * (DH / 2); cc < (half + 1) * (DH / 2); cc += 32) {
       uint32_t ov[32], ok[32];
       tmem_ld_32x32b_x32(tmem_base + lane_addr + cc, ov);
       tmem_ld_32x32b_x32(tmem_base + lane_addr + DH + cc, ok);
