@@ -82,13 +82,10 @@ class FlatGradBuckets:
             p._s3d_owner = self
 
     def note_write(self, p):
-        i = self._index[id(p)]
-        self._uses[i] += 1
-        if self.world > 1 and self._expected is not None and self._uses[i] == self._expected[i]:
-            b = self._bucket_of[i]
-            self._pending[b] -= 1
-            if self._pending[b] == 0:
-                self._launch_bucket(b)
+        """Bookkeeping only. Readiness of a bucket is signalled by autograd's post-accumulate-grad hook, which the engine
+        runs once per parameter after ALL of its uses have been processed -- also for sink parameters whose backward
+        returned None (measured: torch 2.11). Buckets whose hooks did not all fire are launched in sync_gradients()."""
+        self._uses[self._index[id(p)]] += 1
 
     def _make_hook(self, i):
         b = self._bucket_of[i]
@@ -133,7 +130,7 @@ class FlatGradBuckets:
         if self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
         if self._expected is None and any(self._uses):
-            self._expected = list(self._uses)  # shared blocks (group_embed mode) are written twice per step
+            self._expected = list(self._uses)  # observability: in-place writes per parameter per step
 
 
 class DataParallelTrainer:
