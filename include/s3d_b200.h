@@ -129,6 +129,73 @@ int s3d_gather_rows(const float* points, const int64_t* idx, float* out, int B, 
 int s3d_scatter_add_rows(const float* grad_out, const int64_t* idx, float* grad_points, int B, int N, int M, int C,
                          void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Set abstraction / feature propagation of the point tokenizer (reference data/pointnet_util.py:99-138 sample_and_group,
+ * :220-244 PointNetSetAbstraction.forward = [Conv2d 1x1 -> BatchNorm2d -> ReLU] x 2 -> max over the K neighbours,
+ * :381-420 PointNetFeaturePropagation.forward = 3-NN inverse-distance interpolation; models/3DViT/model.py:33-72
+ * TransitionDown / TransitionUp = Linear -> BatchNorm1d -> ReLU). The grouped tensor [B,S,K,3+Cf] is never built:
+ *   z1[b,s,k,:] = uf[b, idx[b,s,k], :] + w1[:, 0:3] (xyz[b, idx[b,s,k]] - cxyz[b,s])        (layer 1, fp32)
+ * with uf = f W1[:, 3:]^T + b1 a per-point GEMM (s3d_gemm_bf16). Rows r = (b*S + s)*K + k, groups g = b*S + s.
+ * BatchNorm statistics go through `partials` f32 [P, 2, C] (one slot per CTA row-slice, P chosen by the caller) and
+ * a fixed-order fp64 finalize, so forward results are bitwise reproducible.
+ *   s3d_sa_group_fwd_stats   : partials <- sum z1, sum z1^2
+ *   s3d_sa_group_fwd_act     : a1 bf16 [B*S*K, C1] = relu(scale * z1 + shift)                   (layer-2 GEMM operand)
+ *   s3d_sa_group_reduce      : z2 f32 [G*K, C] -> zmax/zmin f32 [G,C], kmax/kmin u8 [G,C] (first k on ties), partials
+ *   s3d_sa_pool_select       : out = relu(scale * zsel + shift), zsel = scale >= 0 ? zmax : zmin, ksel likewise
+ *                              (= max_k relu(bn(z2_k)), :241-242)
+ *   s3d_sa_dz2_expand        : dz2 bf16 [G*K, C] = scale * (dy - m1 - zhat * m2); dy = dout[g,c] on row k == ksel[g,c]
+ *                              where out > 0, else 0 (BatchNorm2d backward of the pooled layer)
+ *   s3d_sa_group_bwd_stats   : partials <- sum dy1, sum dy1 * zhat1; dy1 = da1 where a1 > 0
+ *   s3d_sa_group_bwd_scatter : dz1 = scale * (dy1 - m1 - zhat1 * m2); duf[b, idx] += dz1 (duf zeroed by the caller);
+ *                              dwx_partials f32 [P, 3, C1] <- sum dz1 * (xyz[idx] - cxyz)       (gradient of w1[:, 0:3])
+ *   s3d_bn_rows_stats / s3d_bn_rows_bwd_stats : the same statistics over a plain f32 [R, C] matrix (BatchNorm1d)
+ *   s3d_bn_finalize_fwd      : mean, rstd, scale = gamma * rstd, shift = beta - mean * scale; running statistics
+ *                              updated in place with the unbiased variance (NULL = skip), as nn.BatchNorm*d in train()
+ *   s3d_bn_finalize_bwd      : dgamma (+)= sum dy * zhat, dbeta (+)= sum dy; m1, m2 = those / count (0 when !training)
+ *   s3d_bn_relu_apply        : y = relu(scale * z + shift) -> f32 and/or bf16
+ *   s3d_bn_relu_bwd_apply    : dz bf16 = scale * (dy - m1 - zhat * m2), dy = dout where scale * z + shift > 0
+ *   s3d_three_nn_interp_fwd  : out[b,n,:] = sum_j w_j feats[b, idx[b,n,j], :] (+ addend), w_j = (1/(d_j+1e-8)) / sum
+ *                              (:401-408); idx int64 [B,N,3], dist f32 [B,N,3] from s3d_knn(K=3)
+ *   s3d_three_nn_interp_bwd  : dfeats[b, idx, :] += w_j dout[b,n,:] (dfeats zeroed here)
+ * ------------------------------------------------------------------------------------------------------------- */
+int s3d_sa_group_fwd_stats(const float* uf, const float* xyz, const float* cxyz, const int64_t* idx, const float* w1,
+                           int ldw, int B, int N, int S, int K, int C1, float* partials, int P, void* stream);
+int s3d_sa_group_fwd_act(const float* uf, const float* xyz, const float* cxyz, const int64_t* idx, const float* w1,
+                         int ldw, int B, int N, int S, int K, int C1, const float* scale, const float* shift,
+                         void* a1_bf16, int P, void* stream);
+int s3d_sa_group_bwd_stats(const float* uf, const float* xyz, const float* cxyz, const int64_t* idx, const float* w1,
+                           int ldw, int B, int N, int S, int K, int C1, const float* mean, const float* rstd,
+                           const void* a1_bf16, const void* da1_bf16, float* partials, int P, void* stream);
+int s3d_sa_group_bwd_scatter(const float* uf, const float* xyz, const float* cxyz, const int64_t* idx, const float* w1,
+                             int ldw, int B, int N, int S, int K, int C1, const float* scale, const float* mean,
+                             const float* rstd, const float* m1, const float* m2, const void* a1_bf16,
+                             const void* da1_bf16, float* duf, float* dwx_partials, int P, void* stream);
+int s3d_sa_group_reduce(const float* z2, int64_t G, int K, int C, float* zmax, float* zmin, uint8_t* kmax,
+                        uint8_t* kmin, float* partials, int P, void* stream);
+int s3d_sa_pool_select(const float* zmax, const float* zmin, const uint8_t* kmax, const uint8_t* kmin,
+                       const float* scale, const float* shift, float* out, float* zsel, uint8_t* ksel, int64_t G, int C,
+                       void* stream);
+int s3d_sa_dz2_expand(const float* z2, const float* dout, const float* zsel, const uint8_t* ksel, const float* scale,
+                      const float* shift, const float* mean, const float* rstd, const float* m1, const float* m2,
+                      void* dz2_bf16, int64_t G, int K, int C, int P, void* stream);
+int s3d_bn_rows_stats(const float* z, int64_t R, int C, float* partials, int P, void* stream);
+int s3d_bn_rows_bwd_stats(const float* dout, const float* z, const float* scale, const float* shift, const float* mean,
+                          const float* rstd, int64_t R, int C, float* partials, int P, void* stream);
+int s3d_bn_finalize_fwd(const float* partials, int P, int C, double count, const float* gamma, const float* beta,
+                        float eps, float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
+                        float* scale, float* shift, void* stream);
+int s3d_bn_finalize_bwd(const float* partials, int P, int C, double count, int training, float* m1, float* m2,
+                        float* dgamma, float* dbeta, int accumulate, void* stream);
+int s3d_bn_relu_apply(const float* z, const float* scale, const float* shift, float* y_f32, void* y_bf16, int64_t R,
+                      int C, void* stream);
+int s3d_bn_relu_bwd_apply(const float* dout, const float* z, const float* scale, const float* shift, const float* mean,
+                          const float* rstd, const float* m1, const float* m2, void* dz_bf16, int64_t R, int C,
+                          void* stream);
+int s3d_three_nn_interp_fwd(const float* feats, const int64_t* idx, const float* dist, const float* addend, float* out,
+                            int B, int S, int N, int C, void* stream);
+int s3d_three_nn_interp_bwd(const float* dout, const int64_t* idx, const float* dist, float* dfeats, int B, int S, int N,
+                            int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

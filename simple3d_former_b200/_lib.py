@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 
 import torch
 
@@ -42,6 +42,23 @@ SIGNATURES = {
     "s3d_fps": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "s3d_gather_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "s3d_scatter_add_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "s3d_sa_group_fwd_stats": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    "s3d_sa_group_fwd_act": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P]),
+    "s3d_sa_group_bwd_stats": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P,
+                                       c_int, _P]),
+    "s3d_sa_group_bwd_scatter": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P,
+                                         _P, _P, _P, _P, c_int, _P]),
+    "s3d_sa_group_reduce": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P]),
+    "s3d_sa_pool_select": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "s3d_sa_dz2_expand": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "s3d_bn_rows_stats": (c_int, [_P, c_int64, c_int, _P, c_int, _P]),
+    "s3d_bn_rows_bwd_stats": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, c_int, _P]),
+    "s3d_bn_finalize_fwd": (c_int, [_P, c_int, c_int, c_double, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "s3d_bn_finalize_bwd": (c_int, [_P, c_int, c_int, c_double, c_int, _P, _P, _P, _P, c_int, _P]),
+    "s3d_bn_relu_apply": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "s3d_bn_relu_bwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "s3d_three_nn_interp_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "s3d_three_nn_interp_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
 }
 
 _lib = None
@@ -298,3 +315,173 @@ def scatter_add_rows(grad_out, idx, N):
     gp = torch.empty((B, N, C), device=grad_out.device, dtype=torch.float32)
     call("s3d_scatter_add_rows", ptr(grad_out), ptr(idx), ptr(gp), B, N, M, C, stream())
     return gp
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# set abstraction / feature propagation (csrc/pointnet_fused.cu)
+# ------------------------------------------------------------------------------------------------------------------
+def _slots(work_items, C):
+    """Number of partial-sum slots (CTA row-slices) for a statistics pass over `work_items` warp items of C channels."""
+    nchunks = (C + 127) // 128
+    return int(max(1, min((work_items + 7) // 8, 888 // nchunks)))
+
+
+def _f32(*shape, device):
+    return torch.empty(shape, device=device, dtype=torch.float32)
+
+
+class SaGroup:
+    """Arguments shared by the layer-1 passes of a set-abstraction layer (see include/s3d_b200.h)."""
+
+    def __init__(self, uf, xyz, cxyz, idx, w1):
+        _need_cuda(uf, xyz, cxyz, idx, w1)
+        B, N, _ = xyz.shape
+        S, K = idx.shape[1], idx.shape[2]
+        C1 = uf.shape[-1]
+        assert uf.dtype == torch.float32 and uf.is_contiguous() and uf.numel() == B * N * C1
+        assert xyz.dtype == torch.float32 and xyz.is_contiguous() and cxyz.dtype == torch.float32 and cxyz.is_contiguous()
+        assert cxyz.shape == (B, S, 3) and idx.dtype == torch.long and idx.is_contiguous()
+        assert w1.dtype == torch.float32 and w1.dim() == 2 and w1.stride(1) == 1 and w1.shape[0] == C1
+        self.t = (uf, xyz, cxyz, idx, w1)
+        self.dims = (B, N, S, K, C1)
+        self.P = _slots(B * S, C1)
+        self.head = (ptr(uf), ptr(xyz), ptr(cxyz), ptr(idx), ptr(w1), w1.stride(0), B, N, S, K, C1)
+        self.device = uf.device
+
+
+def sa_group_fwd_stats(g):
+    part = _f32(g.P, 2, g.dims[4], device=g.device)
+    call("s3d_sa_group_fwd_stats", *g.head, ptr(part), g.P, stream())
+    return part
+
+
+def sa_group_fwd_act(g, scale, shift):
+    B, N, S, K, C1 = g.dims
+    a1 = torch.empty((B * S * K, C1), device=g.device, dtype=torch.bfloat16)
+    call("s3d_sa_group_fwd_act", *g.head, ptr(scale), ptr(shift), ptr(a1), g.P, stream())
+    return a1
+
+
+def sa_group_bwd_stats(g, mean, rstd, a1, da1):
+    part = _f32(g.P, 2, g.dims[4], device=g.device)
+    assert a1.is_contiguous() and da1.is_contiguous() and da1.shape == a1.shape and da1.dtype == torch.bfloat16
+    call("s3d_sa_group_bwd_stats", *g.head, ptr(mean), ptr(rstd), ptr(a1), ptr(da1), ptr(part), g.P, stream())
+    return part
+
+
+def sa_group_bwd_scatter(g, scale, mean, rstd, m1, m2, a1, da1):
+    B, N, S, K, C1 = g.dims
+    duf = torch.zeros((B * N, C1), device=g.device, dtype=torch.float32)
+    part = _f32(g.P, 3, C1, device=g.device)
+    call("s3d_sa_group_bwd_scatter", *g.head, ptr(scale), ptr(mean), ptr(rstd), ptr(m1), ptr(m2), ptr(a1), ptr(da1),
+         ptr(duf), ptr(part), g.P, stream())
+    return duf, part
+
+
+def sa_group_reduce(z2, G, K):
+    _need_cuda(z2)
+    assert z2.dtype == torch.float32 and z2.is_contiguous() and z2.shape[0] == G * K
+    C = z2.shape[1]
+    dev = z2.device
+    P = _slots(G, C)
+    zmax, zmin = _f32(G, C, device=dev), _f32(G, C, device=dev)
+    kmax = torch.empty((G, C), device=dev, dtype=torch.uint8)
+    kmin = torch.empty((G, C), device=dev, dtype=torch.uint8)
+    part = _f32(P, 2, C, device=dev)
+    call("s3d_sa_group_reduce", ptr(z2), G, K, C, ptr(zmax), ptr(zmin), ptr(kmax), ptr(kmin), ptr(part), P, stream())
+    return zmax, zmin, kmax, kmin, part
+
+
+def sa_pool_select(zmax, zmin, kmax, kmin, scale, shift):
+    G, C = zmax.shape
+    out, zsel = torch.empty_like(zmax), torch.empty_like(zmax)
+    ksel = torch.empty_like(kmax)
+    call("s3d_sa_pool_select", ptr(zmax), ptr(zmin), ptr(kmax), ptr(kmin), ptr(scale), ptr(shift), ptr(out), ptr(zsel),
+         ptr(ksel), G, C, stream())
+    return out, zsel, ksel
+
+
+def sa_dz2_expand(z2, dout, zsel, ksel, scale, shift, mean, rstd, m1, m2, G, K):
+    C = z2.shape[1]
+    assert dout.dtype == torch.float32 and dout.is_contiguous() and dout.shape == (G, C)
+    dz2 = torch.empty((G * K, C), device=z2.device, dtype=torch.bfloat16)
+    call("s3d_sa_dz2_expand", ptr(z2), ptr(dout), ptr(zsel), ptr(ksel), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+         ptr(m1), ptr(m2), ptr(dz2), G, K, C, _slots(G, C), stream())
+    return dz2
+
+
+def bn_rows_stats(z):
+    _need_cuda(z)
+    assert z.dtype == torch.float32 and z.dim() == 2 and z.is_contiguous()
+    R, C = z.shape
+    P = _slots(R, C)
+    part = _f32(P, 2, C, device=z.device)
+    call("s3d_bn_rows_stats", ptr(z), R, C, ptr(part), P, stream())
+    return part
+
+
+def bn_rows_bwd_stats(dout, z, scale, shift, mean, rstd):
+    _need_cuda(dout, z)
+    assert z.dtype == torch.float32 and z.dim() == 2 and z.is_contiguous()
+    assert dout.dtype == torch.float32 and dout.is_contiguous() and dout.shape == z.shape
+    R, C = z.shape
+    P = _slots(R, C)
+    part = _f32(P, 2, C, device=z.device)
+    call("s3d_bn_rows_bwd_stats", ptr(dout), ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), R, C, ptr(part), P,
+         stream())
+    return part
+
+
+def bn_finalize_fwd(part, count, gamma, beta, eps, momentum, running_mean, running_var):
+    P, _, C = part.shape
+    dev = part.device
+    mean, rstd, scale, shift = (_f32(C, device=dev) for _ in range(4))
+    call("s3d_bn_finalize_fwd", ptr(part), P, C, float(count), ptr(gamma), ptr(beta), float(eps), float(momentum),
+         ptr(running_mean), ptr(running_var), ptr(mean), ptr(rstd), ptr(scale), ptr(shift), stream())
+    return mean, rstd, scale, shift
+
+
+def bn_finalize_bwd(part, count, training):
+    P, _, C = part.shape
+    dev = part.device
+    m1, m2, dgamma, dbeta = (_f32(C, device=dev) for _ in range(4))
+    call("s3d_bn_finalize_bwd", ptr(part), P, C, float(count), int(training), ptr(m1), ptr(m2), ptr(dgamma), ptr(dbeta),
+         0, stream())
+    return m1, m2, dgamma, dbeta
+
+
+def bn_relu_apply(z, scale, shift, want_f32=True, want_bf16=False):
+    R, C = z.shape
+    y32 = torch.empty_like(z) if want_f32 else None
+    y16 = torch.empty(z.shape, device=z.device, dtype=torch.bfloat16) if want_bf16 else None
+    call("s3d_bn_relu_apply", ptr(z), ptr(scale), ptr(shift), ptr(y32), ptr(y16), R, C, stream())
+    return y32, y16
+
+
+def bn_relu_bwd_apply(dout, z, scale, shift, mean, rstd, m1, m2):
+    R, C = z.shape
+    dz16 = torch.empty(z.shape, device=z.device, dtype=torch.bfloat16)
+    call("s3d_bn_relu_bwd_apply", ptr(dout), ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(m1), ptr(m2),
+         ptr(dz16), R, C, stream())
+    return dz16
+
+
+def three_nn_interp_fwd(feats, idx, dist, addend=None):
+    _need_cuda(feats, idx, dist)
+    B, S, C = feats.shape
+    N = idx.shape[1]
+    assert feats.dtype == torch.float32 and feats.is_contiguous() and idx.is_contiguous() and dist.is_contiguous()
+    assert idx.shape == (B, N, 3) and dist.shape == (B, N, 3)
+    if addend is not None:
+        assert addend.dtype == torch.float32 and addend.is_contiguous() and addend.shape == (B, N, C)
+    out = _f32(B, N, C, device=feats.device)
+    call("s3d_three_nn_interp_fwd", ptr(feats), ptr(idx), ptr(dist), ptr(addend), ptr(out), B, S, N, C, stream())
+    return out
+
+
+def three_nn_interp_bwd(dout, idx, dist, S):
+    B, N, C = dout.shape
+    assert dout.dtype == torch.float32 and dout.is_contiguous()
+    dfeats = _f32(B, S, C, device=dout.device)
+    call("s3d_three_nn_interp_bwd", ptr(dout), ptr(idx), ptr(dist), ptr(dfeats), B, S, N, C, stream())
+    return dfeats

@@ -416,3 +416,139 @@ class GatherRowsFn(torch.autograd.Function):
         (flat,) = ctx.saved_tensors
         g = dout.reshape(flat.shape[0], flat.shape[1], -1).contiguous().float()
         return L.scatter_add_rows(g, flat, ctx.n), None
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BatchNorm helpers shared by the point-tokenizer layers
+# ----------------------------------------------------------------------------------------------------------------
+def _bn_eval_affine(gamma, beta, running_mean, running_var, eps):
+    """eval(): BatchNorm is the affine map of its running statistics (a handful of [C]-sized ops)."""
+    rstd = torch.rsqrt(running_var.float() + eps)
+    scale = (gamma.detach() * rstd).contiguous()
+    shift = (beta.detach() - running_mean * scale).contiguous()
+    return running_mean.float().contiguous(), rstd.contiguous(), scale, shift
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Set abstraction: sample_and_group + [Conv2d 1x1 -> BatchNorm2d -> ReLU] x 2 + max over the K neighbours
+# (data/pointnet_util.py:99-138, 220-244) without ever building the grouped tensor; see csrc/pointnet_fused.cu
+# ----------------------------------------------------------------------------------------------------------------
+class SetAbstractionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, xyz, cxyz, idx, w1, b1, g1, be1, rm1, rv1, w2, b2, g2, be2, rm2, rv2, training, eps1, mom1,
+                eps2, mom2):
+        B, N, Cf = f.shape
+        S, K = idx.shape[1], idx.shape[2]
+        C1, C2 = w1.shape[0], w2.shape[0]
+        Cin = w1.numel() // C1
+        assert Cin == Cf + 3 and w2.numel() == C2 * C1
+        R, G = B * S * K, B * S
+        w1_2d = w1.detach().reshape(C1, Cin)
+        w1f16 = shadow(w1).reshape(C1, Cin)[:, 3:].contiguous()  # feature columns; xyz columns stay fp32
+        f16 = L.cast_bf16(f.detach().reshape(B * N, Cf).contiguous().float())
+        uf = L.gemm(f16, w1f16, bias=b1, out_dtype=torch.float32)  # per-point part of layer 1, [B*N, C1]
+        grp = L.SaGroup(uf, xyz.contiguous(), cxyz.contiguous(), idx.contiguous(), w1_2d)
+        if training:
+            mean1, rstd1, sc1, sh1 = L.bn_finalize_fwd(L.sa_group_fwd_stats(grp), R, g1, be1, eps1, mom1, rm1, rv1)
+        else:
+            mean1, rstd1, sc1, sh1 = _bn_eval_affine(g1, be1, rm1, rv1, eps1)
+        a1 = L.sa_group_fwd_act(grp, sc1, sh1)  # bf16 [R, C1]
+        w2_16 = shadow(w2).reshape(C2, C1)
+        z2 = L.gemm(a1, w2_16, bias=b2, out_dtype=torch.float32)  # [R, C2]
+        zmax, zmin, kmax, kmin, part2 = L.sa_group_reduce(z2, G, K)
+        if training:
+            mean2, rstd2, sc2, sh2 = L.bn_finalize_fwd(part2, R, g2, be2, eps2, mom2, rm2, rv2)
+        else:
+            mean2, rstd2, sc2, sh2 = _bn_eval_affine(g2, be2, rm2, rv2, eps2)
+        out, zsel, ksel = L.sa_pool_select(zmax, zmin, kmax, kmin, sc2, sh2)
+        ctx.save_for_backward(uf, grp.t[1], grp.t[2], grp.t[3], f16, w1f16, a1, z2, zsel, ksel, w1, w2, mean1, rstd1,
+                              sc1, mean2, rstd2, sc2, sh2)
+        ctx.meta = (B, N, S, K, Cf, C1, C2, training)
+        ctx.refs = (b1, b2)
+        return out.view(B, S, C2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (uf, xyz, cxyz, idx, f16, w1f16, a1, z2, zsel, ksel, w1, w2, mean1, rstd1, sc1, mean2, rstd2, sc2,
+         sh2) = ctx.saved_tensors
+        B, N, S, K, Cf, C1, C2, training = ctx.meta
+        b1, b2 = ctx.refs
+        R, G = B * S * K, B * S
+        Cin = Cf + 3
+        dout2 = dout.reshape(G, C2).contiguous().float()
+        # layer 2 (pooled): BatchNorm backward statistics only involve the pooled rows
+        m1, m2, dg2, dbe2 = L.bn_finalize_bwd(L.bn_rows_bwd_stats(dout2, zsel, sc2, sh2, mean2, rstd2), R, training)
+        dz2 = L.sa_dz2_expand(z2, dout2, zsel, ksel, sc2, sh2, mean2, rstd2, m1, m2, G, K)  # bf16 [R, C2]
+        dw2 = _wgrad(w2, dz2, a1)
+        db2 = _bgrad(b2, dz2)
+        da1 = L.gemm(dz2, shadow(w2).reshape(C2, C1), b_mn=True)  # bf16 [R, C1]
+        # layer 1
+        grp = L.SaGroup(uf, xyz, cxyz, idx, w1.detach().reshape(C1, Cin))
+        n1, n2, dg1, dbe1 = L.bn_finalize_bwd(L.sa_group_bwd_stats(grp, mean1, rstd1, a1, da1), R, training)
+        duf, dwx_part = L.sa_group_bwd_scatter(grp, sc1, mean1, rstd1, n1, n2, a1, da1)
+        duf16 = L.cast_bf16(duf)
+        df = None
+        if ctx.needs_input_grad[0]:
+            df = L.gemm(duf16, w1f16, b_mn=True, out_dtype=torch.float32).view(B, N, Cf)
+        dw1f = L.gemm(duf16, f16, a_mn=True, b_mn=True, out_dtype=torch.float32)  # [C1, Cf]
+        db1 = L.colsum(duf16) if b1 is not None else None
+        dw1 = torch.cat([dwx_part.sum(0).t(), dw1f], dim=1).view(w1.shape)
+        return (df, None, None, None, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None, None, None,
+                None, None, None)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Linear -> BatchNorm1d -> ReLU on [rows, C] (TransitionUp.fc1 / fc2, models/3DViT/model.py:47-60)
+# ----------------------------------------------------------------------------------------------------------------
+class LinearBnReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, g, be, rm, rv, training, eps, mom):
+        K = x.shape[-1]
+        x16 = L.cast_bf16(x.detach().reshape(-1, K).contiguous().float())
+        z = L.gemm(x16, _w2d(shadow(w)), bias=b, out_dtype=torch.float32)
+        R = z.shape[0]
+        if training:
+            mean, rstd, sc, sh = L.bn_finalize_fwd(L.bn_rows_stats(z), R, g, be, eps, mom, rm, rv)
+        else:
+            mean, rstd, sc, sh = _bn_eval_affine(g, be, rm, rv, eps)
+        y, _ = L.bn_relu_apply(z, sc, sh)
+        ctx.save_for_backward(x16, z, w, mean, rstd, sc, sh)
+        ctx.meta = (x.shape, training)
+        ctx.bias_ref = b
+        return y.view(*x.shape[:-1], z.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, z, w, mean, rstd, sc, sh = ctx.saved_tensors
+        in_shape, training = ctx.meta
+        R = z.shape[0]
+        dy2 = dy.reshape(z.shape).contiguous().float()
+        m1, m2, dg, dbe = L.bn_finalize_bwd(L.bn_rows_bwd_stats(dy2, z, sc, sh, mean, rstd), R, training)
+        dz16 = L.bn_relu_bwd_apply(dy2, z, sc, sh, mean, rstd, m1, m2)
+        dw = _wgrad(w, dz16, x16)
+        db = _bgrad(ctx.bias_ref, dz16)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = L.gemm(dz16, _w2d(shadow(w)), b_mn=True, out_dtype=torch.float32).view(in_shape)
+        return dx, dw, db, dg, dbe, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# 3-NN inverse-distance interpolation (pointnet_util.py:401-408) + the residual add of TransitionUp
+# ----------------------------------------------------------------------------------------------------------------
+class ThreeNNInterpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, idx, dist, addend):
+        feats = feats.contiguous().float()
+        out = L.three_nn_interp_fwd(feats, idx, dist, None if addend is None else addend.contiguous().float())
+        ctx.save_for_backward(idx, dist)
+        ctx.S = feats.shape[1]
+        ctx.has_addend = addend is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        idx, dist = ctx.saved_tensors
+        dout = dout.contiguous().float()
+        dfeats = L.three_nn_interp_bwd(dout, idx, dist, ctx.S) if ctx.needs_input_grad[0] else None
+        return dfeats, None, None, (dout if ctx.has_addend else None)

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as Fn
-from .pointnet_util import PointNetFeaturePropagation, PointNetSetAbstraction
+from .pointnet_util import PointNetFeaturePropagation, PointNetSetAbstraction, knn_point
 from .vision_transformer import FusedLayerNorm, VisionTransformer, _cfg, trunc_normal_
 
 _norm = partial(FusedLayerNorm, eps=1e-6)
@@ -190,11 +190,32 @@ class TransitionUp(nn.Module):
         self.fc2 = nn.Sequential(nn.Linear(dim2, dim_out), _SwapAxes(), nn.BatchNorm1d(dim_out), _SwapAxes(), nn.ReLU())
         self.fp = PointNetFeaturePropagation(-1, [])
 
+    fused = True  # class switch: False forces the PyTorch-op path (kernel-vs-torch parity tests)
+
+    @staticmethod
+    def _fc(seq, x):
+        """Linear -> BatchNorm1d -> ReLU of the reference's Sequential as one fused node (GEMM + two HBM passes)."""
+        lin, bn = seq[0], seq[2]
+        y = Fn.LinearBnReluFn.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                    seq.training, bn.eps, bn.momentum)
+        if seq.training:
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+        return y
+
     def forward(self, xyz1, points1, xyz2, points2):
-        feats1 = self.fc1(points1)
-        feats2 = self.fc2(points2)
-        feats1 = self.fp(xyz2.transpose(1, 2), xyz1.transpose(1, 2), None, feats1.transpose(1, 2)).transpose(1, 2)
-        return feats1 + feats2
+        """xyz1 [B,S,3] / points1 [B,S,dim1]: coarse level; xyz2 [B,N,3] / points2 [B,N,dim2]: fine level."""
+        fusable = self.fused and points1.is_cuda and xyz1.shape[1] > 1 and self.fc1[0].out_features % 4 == 0 and \
+            points1.shape[-1] % 8 == 0 and points2.shape[-1] % 8 == 0
+        if not fusable:
+            feats1 = self.fc1(points1)
+            feats2 = self.fc2(points2)
+            feats1 = self.fp(xyz2.transpose(1, 2), xyz1.transpose(1, 2), None, feats1.transpose(1, 2)).transpose(1, 2)
+            return feats1 + feats2
+        feats1 = self._fc(self.fc1, points1)
+        feats2 = self._fc(self.fc2, points2)
+        idx, dist = knn_point(3, xyz1.detach().contiguous(), xyz2.detach().contiguous(), return_dist=True)
+        return Fn.ThreeNNInterpFn.apply(feats1, idx, dist, feats2)
 
 
 class _DeadPointEmbed(nn.Module):

@@ -3,9 +3,12 @@
 `square_distance + argsort()[:, :, :K]` (:119-120, :233-234) becomes `knn_point` (no [B,S,N] matrix, no full sort),
 `query_ball_point` (:76-96), `farthest_point_sample` (:53-73) and `index_points` (:39-50) are single kernels; integer
 outputs are bit-exact with the reference on tie-free inputs (tie contract: ascending (distance, index)).
-The set-abstraction / feature-propagation modules keep their 1x1 conv + BatchNorm layers as PyTorch ops (SURVEY.md
-section 8(f) rank 1 is the fusion of those) but use the kernels for sampling, grouping and gathering, and drop the
-reference's dead second kNN (:233-235) and its torch.cuda.empty_cache() stalls (:115-127).
+`PointNetSetAbstraction` with a two-layer MLP (the only shape the 3DViT models build) runs as
+`functional.SetAbstractionFn`: the grouped tensor [B,S,K,3+C] is never materialised, layer 1 is evaluated per point on
+the tensor cores and gathered, BatchNorm statistics / ReLU / the max over neighbours are fused passes
+(csrc/pointnet_fused.cu). Other layer counts keep their 1x1 conv + BatchNorm layers as PyTorch ops on top of the
+grouping kernels. The reference's dead second kNN (:233-235) and its torch.cuda.empty_cache() stalls (:115-127) are
+dropped.
 """
 import numpy as np
 import torch
@@ -90,7 +93,35 @@ class PointNetSetAbstraction(nn.Module):
         self.last_pos_embed = nn.Sequential(nn.Linear(3, last), nn.ReLU(), nn.Linear(last, last))
         self.fps_start = None  # optional explicit FPS start indices (parity tests)
 
+    fused = True  # class switch: False forces the PyTorch-op MLP (used by the kernel-vs-torch parity tests)
+
+    def _fusable(self, xyz, points):
+        if not self.fused or self.group_all or points is None or len(self.mlp_convs) != 2 or not xyz.is_cuda:
+            return False
+        c1, c2 = self.mlp_convs[0].out_channels, self.mlp_convs[1].out_channels
+        bns_ok = all(bn.track_running_stats and bn.affine and bn.momentum is not None for bn in self.mlp_bns)
+        return bns_ok and points.shape[-1] % 8 == 0 and c1 % 8 == 0 and c2 % 8 == 0 and self.nsample <= 32
+
+    def _forward_fused(self, xyz, points):
+        xyz = xyz.detach().contiguous().float()
+        fps_idx = farthest_point_sample(xyz, self.npoint, self.fps_start)
+        new_xyz = L.gather_rows(xyz, fps_idx)
+        idx = knn_point(self.nsample, xyz, new_xyz) if self.knn else query_ball_point(self.radius, self.nsample, xyz,
+                                                                                      new_xyz)
+        (c1, c2), (n1, n2) = self.mlp_convs, self.mlp_bns
+        out = Fn.SetAbstractionFn.apply(points, xyz, new_xyz, idx, c1.weight, c1.bias, n1.weight, n1.bias,
+                                        n1.running_mean, n1.running_var, c2.weight, c2.bias, n2.weight, n2.bias,
+                                        n2.running_mean, n2.running_var, self.training, n1.eps, n1.momentum, n2.eps,
+                                        n2.momentum)
+        if self.training:
+            with torch.no_grad():
+                n1.num_batches_tracked += 1
+                n2.num_batches_tracked += 1
+        return new_xyz, out
+
     def forward(self, xyz, points):
+        if self._fusable(xyz, points):
+            return self._forward_fused(xyz, points)
         if self.group_all:
             new_xyz, new_points = sample_and_group_all(xyz, points)
         else:
