@@ -154,6 +154,9 @@ int s3d_scatter_add_rows(const float* grad_out, const int64_t* idx, float* grad_
  *   s3d_bn_finalize_bwd      : dgamma (+)= sum dy * zhat, dbeta (+)= sum dy; m1, m2 = those / count (0 when !training)
  *   s3d_bn_relu_apply        : y = relu(scale * z + shift) -> f32 and/or bf16
  *   s3d_bn_relu_bwd_apply    : dz bf16 = scale * (dy - m1 - zhat * m2), dy = dout where scale * z + shift > 0
+ *   s3d_split_bf16x3         : x f32 [R,K] (row stride ldx) -> bf16 [R,3K] = [hi|lo|hi] (activations) or [hi|hi|lo]
+ *                              (weights), hi = bf16(x), lo = bf16(x - hi): one GEMM over 3K gives fp32-grade products
+ *                              for the small per-point Linear layers in front of a BatchNorm
  *   s3d_three_nn_interp_fwd  : out[b,n,:] = sum_j w_j feats[b, idx[b,n,j], :] (+ addend), w_j = (1/(d_j+1e-8)) / sum
  *                              (:401-408); idx int64 [B,N,3], dist f32 [B,N,3] from s3d_knn(K=3)
  *   s3d_three_nn_interp_bwd  : dfeats[b, idx, :] += w_j dout[b,n,:] (dfeats zeroed here)
@@ -191,6 +194,7 @@ int s3d_bn_relu_apply(const float* z, const float* scale, const float* shift, fl
 int s3d_bn_relu_bwd_apply(const float* dout, const float* z, const float* scale, const float* shift, const float* mean,
                           const float* rstd, const float* m1, const float* m2, void* dz_bf16, int64_t R, int C,
                           void* stream);
+int s3d_split_bf16x3(const float* x, void* out_bf16, int64_t R, int K, int64_t ldx, int weight_layout, void* stream);
 int s3d_three_nn_interp_fwd(const float* feats, const int64_t* idx, const float* dist, const float* addend, float* out,
                             int B, int S, int N, int C, void* stream);
 int s3d_three_nn_interp_bwd(const float* dout, const int64_t* idx, const float* dist, float* dfeats, int B, int S, int N,

@@ -57,6 +57,7 @@ SIGNATURES = {
     "s3d_bn_finalize_bwd": (c_int, [_P, c_int, c_int, c_double, c_int, _P, _P, _P, _P, c_int, _P]),
     "s3d_bn_relu_apply": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "s3d_bn_relu_bwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "s3d_split_bf16x3": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P]),
     "s3d_three_nn_interp_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "s3d_three_nn_interp_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
 }
@@ -485,3 +486,13 @@ def three_nn_interp_bwd(dout, idx, dist, S):
     dfeats = _f32(B, S, C, device=dout.device)
     call("s3d_three_nn_interp_bwd", ptr(dout), ptr(idx), ptr(dist), ptr(dfeats), B, S, N, C, stream())
     return dfeats
+
+
+def split_bf16x3(x, weight_layout=False):
+    """fp32 [R,K] -> bf16 [R,3K] hi/lo split ([hi|lo|hi] for activations, [hi|hi|lo] for weights)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    R, K = x.shape
+    out = torch.empty((R, 3 * K), device=x.device, dtype=torch.bfloat16)
+    call("s3d_split_bf16x3", ptr(x), ptr(out), R, K, x.stride(0), int(weight_layout), stream())
+    return out

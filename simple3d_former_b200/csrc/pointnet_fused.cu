@@ -15,8 +15,8 @@
 // reproducible run to run. Only scatter-adds of gradients use atomics.
 //
 // Work split of the row kernels: a warp owns one group (or row) and a chunk of 128 channels: lane l holds the channel
-// pairs (2l, 2l+1) and (2l+64, 2l+65) of the chunk, so every load / store is a 256-byte (fp32) or 128-byte (bf16)
-// contiguous warp access. All warps of a CTA work on the same chunk, so per-channel accumulators reduce inside the CTA.
+// quad 4l..4l+3 of the chunk, so every load / store / reduction is a 16-byte (fp32) or 8-byte (bf16) vector access
+// and a warp touches 512 (256) contiguous bytes. All warps of a CTA work on the same chunk, so per-channel accumulators reduce inside the CTA.
 #include "kernels.h"
 
 namespace s3d {
@@ -50,11 +50,31 @@ struct SaExtra {
   float* partials;        // modes 0, 2: [P, 2, C1]; mode 3: [P, 3, C1]
 };
 
-__device__ __forceinline__ float2 ld2(const float* p, bool ok) {
-  return ok ? *reinterpret_cast<const float2*>(p) : make_float2(0.f, 0.f);
+__device__ __forceinline__ float4 ld4(const float* p, bool ok) {
+  return ok ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void ld4_bf16(const __nv_bfloat16* p, bool ok, float (&v)[4]) {
+  if (ok) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+  }
+}
+__device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void ldc4(const float* p, int c, bool ok, float (&v)[4]) {
+  const float4 t = ld4(p + c, ok);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 
-// CTA reduction of per-lane channel accumulators acc[set][4] (4 = two channel pairs) and write of one partial slot.
+// CTA reduction of per-lane channel accumulators acc[set][4] (lane l owns channels 4l..4l+3 of the chunk) and write of
+// one partial slot.
 template <int NSETS>
 __device__ __forceinline__ void cta_reduce_write(float (&acc)[NSETS][4], float* red /*[kWarps][NSETS][kChunk]*/,
                                                  float* partial_slot /*[NSETS][C]*/, int C, int chunk_base) {
@@ -62,10 +82,7 @@ __device__ __forceinline__ void cta_reduce_write(float (&acc)[NSETS][4], float* 
 #pragma unroll
   for (int s = 0; s < NSETS; ++s) {
     float* r = red + ((size_t)wib * NSETS + s) * kChunk;
-    r[2 * lane] = acc[s][0];
-    r[2 * lane + 1] = acc[s][1];
-    r[2 * lane + 64] = acc[s][2];
-    r[2 * lane + 65] = acc[s][3];
+    *reinterpret_cast<float4*>(r + 4 * lane) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NSETS * kChunk; i += blockDim.x) {
@@ -84,36 +101,26 @@ __device__ __forceinline__ void cta_reduce_write(float (&acc)[NSETS][4], float* 
 template <int MODE>
 __global__ void __launch_bounds__(kWarps * 32) sa_group_kernel(SaGroup a, SaExtra e) {
   constexpr int NSETS = (MODE == 3) ? 3 : 2;
-  __shared__ float red[(MODE == 1) ? 1 : kWarps * NSETS * kChunk];
+  __shared__ __align__(16) float red[(MODE == 1) ? 4 : kWarps * NSETS * kChunk];
   const int nchunks = (a.C1 + kChunk - 1) / kChunk;
   const int q = blockIdx.x % nchunks;
   const int part = blockIdx.x / nchunks;
   const int nparts = gridDim.x / nchunks;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int cA = q * kChunk + 2 * lane, cB = cA + 64;
-  const bool okA = cA < a.C1, okB = cB < a.C1;
+  const int c0 = q * kChunk + 4 * lane;
+  const bool ok = c0 < a.C1;
 
   float wx[4][3];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = (j < 2 ? cA : cB) + (j & 1);
-    const bool ok = (j < 2 ? okA : okB);
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int t = 0; t < 3; ++t) wx[j][t] = ok ? a.w1[(size_t)c * a.ldw + t] : 0.f;
-  }
+    for (int t = 0; t < 3; ++t) wx[j][t] = ok ? a.w1[(size_t)(c0 + j) * a.ldw + t] : 0.f;
   float sc[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0}, mu[4] = {0, 0, 0, 0}, rs[4] = {0, 0, 0, 0};
   float g1[4] = {0, 0, 0, 0}, g2[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = (j < 2 ? cA : cB) + (j & 1);
-    const bool ok = (j < 2 ? okA : okB);
-    if (ok) {
-      if (MODE == 1 || MODE == 3) sc[j] = e.scale[c];
-      if (MODE == 1) sh[j] = e.shift[c];
-      if (MODE >= 2) { mu[j] = e.mean[c]; rs[j] = e.rstd[c]; }
-      if (MODE == 3) { g1[j] = e.m1[c]; g2[j] = e.m2[c]; }
-    }
-  }
+  if (MODE == 1 || MODE == 3) ldc4(e.scale, c0, ok, sc);
+  if (MODE == 1) ldc4(e.shift, c0, ok, sh);
+  if (MODE >= 2) { ldc4(e.mean, c0, ok, mu); ldc4(e.rstd, c0, ok, rs); }
+  if (MODE == 3) { ldc4(e.m1, c0, ok, g1); ldc4(e.m2, c0, ok, g2); }
   float acc[NSETS][4];
 #pragma unroll
   for (int s = 0; s < NSETS; ++s)
@@ -140,13 +147,12 @@ __global__ void __launch_bounds__(kWarps * 32) sa_group_kernel(SaGroup a, SaExtr
       const float y = __shfl_sync(0xffffffffu, dy, k);
       const float w = __shfl_sync(0xffffffffu, dz, k);
       const size_t prow = (size_t)b * a.N + (size_t)ik;
-      const float* urow = a.uf + prow * a.C1;
-      const float2 uA = ld2(urow + cA, okA), uB = ld2(urow + cB, okB);
+      const float4 u = ld4(a.uf + prow * a.C1 + c0, ok);
       float z[4];
-      z[0] = uA.x + (wx[0][0] * x + wx[0][1] * y + wx[0][2] * w);
-      z[1] = uA.y + (wx[1][0] * x + wx[1][1] * y + wx[1][2] * w);
-      z[2] = uB.x + (wx[2][0] * x + wx[2][1] * y + wx[2][2] * w);
-      z[3] = uB.y + (wx[3][0] * x + wx[3][1] * y + wx[3][2] * w);
+      z[0] = u.x + (wx[0][0] * x + wx[0][1] * y + wx[0][2] * w);
+      z[1] = u.y + (wx[1][0] * x + wx[1][1] * y + wx[1][2] * w);
+      z[2] = u.z + (wx[2][0] * x + wx[2][1] * y + wx[2][2] * w);
+      z[3] = u.w + (wx[3][0] * x + wx[3][1] * y + wx[3][2] * w);
       const size_t row = (size_t)g * a.K + k;
       if (MODE == 0) {
 #pragma unroll
@@ -158,24 +164,16 @@ __global__ void __launch_bounds__(kWarps * 32) sa_group_kernel(SaGroup a, SaExtr
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = fmaxf(fmaf(sc[j], z[j], sh[j]), 0.f);
-        uint32_t* out = reinterpret_cast<uint32_t*>(e.a1_out + row * a.C1);
-        if (okA) out[cA >> 1] = pack_bf16x2(v[0], v[1]);
-        if (okB) out[cB >> 1] = pack_bf16x2(v[2], v[3]);
+        if (ok) st4_bf16(e.a1_out + row * a.C1 + c0, v);
       } else {
-        const uint32_t* ar = reinterpret_cast<const uint32_t*>(e.a1 + row * a.C1);
-        const uint32_t* dr = reinterpret_cast<const uint32_t*>(e.da1 + row * a.C1);
-        const float2 aA = okA ? unpack_bf16x2(ar[cA >> 1]) : make_float2(0.f, 0.f);
-        const float2 aB = okB ? unpack_bf16x2(ar[cB >> 1]) : make_float2(0.f, 0.f);
-        const float2 dA = okA ? unpack_bf16x2(dr[cA >> 1]) : make_float2(0.f, 0.f);
-        const float2 dB = okB ? unpack_bf16x2(dr[cB >> 1]) : make_float2(0.f, 0.f);
-        float d[4];
-        d[0] = aA.x > 0.f ? dA.x : 0.f;
-        d[1] = aA.y > 0.f ? dA.y : 0.f;
-        d[2] = aB.x > 0.f ? dB.x : 0.f;
-        d[3] = aB.y > 0.f ? dB.y : 0.f;
-        float zh[4];
+        float av[4], d[4], zh[4];
+        ld4_bf16(e.a1 + row * a.C1 + c0, ok, av);
+        ld4_bf16(e.da1 + row * a.C1 + c0, ok, d);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) zh[j] = (z[j] - mu[j]) * rs[j];
+        for (int j = 0; j < 4; ++j) {
+          d[j] = av[j] > 0.f ? d[j] : 0.f;
+          zh[j] = (z[j] - mu[j]) * rs[j];
+        }
         if (MODE == 2) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -191,9 +189,7 @@ __global__ void __launch_bounds__(kWarps * 32) sa_group_kernel(SaGroup a, SaExtr
             acc[1][j] += t[j] * y;
             acc[2][j] += t[j] * w;
           }
-          float* drow = e.duf + prow * a.C1;
-          if (okA) atomicAdd(reinterpret_cast<float2*>(drow + cA), make_float2(t[0], t[1]));
-          if (okB) atomicAdd(reinterpret_cast<float2*>(drow + cB), make_float2(t[2], t[3]));
+          if (ok) red_add_f32x4(e.duf + prow * a.C1 + c0, t[0], t[1], t[2], t[3]);
         }
       }
     }
@@ -209,12 +205,12 @@ __global__ void __launch_bounds__(kWarps * 32) sa_group_reduce_kernel(const floa
                                                                      unsigned char* __restrict__ kmax,
                                                                      unsigned char* __restrict__ kmin,
                                                                      float* __restrict__ partials) {
-  __shared__ float red[kWarps * 2 * kChunk];
+  __shared__ __align__(16) float red[kWarps * 2 * kChunk];
   const int nchunks = (C + kChunk - 1) / kChunk;
   const int q = blockIdx.x % nchunks, part = blockIdx.x / nchunks, nparts = gridDim.x / nchunks;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int cA = q * kChunk + 2 * lane, cB = cA + 64;
-  const bool okA = cA < C, okB = cB < C;
+  const int c0 = q * kChunk + 4 * lane;
+  const bool ok = c0 < C;
   float acc[2][4];
 #pragma unroll
   for (int s = 0; s < 2; ++s)
@@ -227,9 +223,8 @@ __global__ void __launch_bounds__(kWarps * 32) sa_group_reduce_kernel(const floa
     for (int j = 0; j < 4; ++j) { mx[j] = -INFINITY; mn[j] = INFINITY; ix[j] = 0; in_[j] = 0; }
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-      const float* r = z2 + ((size_t)g * K + k) * C;
-      const float2 vA = ld2(r + cA, okA), vB = ld2(r + cB, okB);
-      const float v[4] = {vA.x, vA.y, vB.x, vB.y};
+      float v[4];
+      ldc4(z2 + ((size_t)g * K + k) * C, c0, ok, v);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         acc[0][j] += v[j];
@@ -238,18 +233,14 @@ __global__ void __launch_bounds__(kWarps * 32) sa_group_reduce_kernel(const floa
         if (v[j] < mn[j]) { mn[j] = v[j]; in_[j] = k; }
       }
     }
-    const size_t o = (size_t)g * C;
-    if (okA) {
-      *reinterpret_cast<float2*>(zmax + o + cA) = make_float2(mx[0], mx[1]);
-      *reinterpret_cast<float2*>(zmin + o + cA) = make_float2(mn[0], mn[1]);
-      *reinterpret_cast<uchar2*>(kmax + o + cA) = make_uchar2((unsigned char)ix[0], (unsigned char)ix[1]);
-      *reinterpret_cast<uchar2*>(kmin + o + cA) = make_uchar2((unsigned char)in_[0], (unsigned char)in_[1]);
-    }
-    if (okB) {
-      *reinterpret_cast<float2*>(zmax + o + cB) = make_float2(mx[2], mx[3]);
-      *reinterpret_cast<float2*>(zmin + o + cB) = make_float2(mn[2], mn[3]);
-      *reinterpret_cast<uchar2*>(kmax + o + cB) = make_uchar2((unsigned char)ix[2], (unsigned char)ix[3]);
-      *reinterpret_cast<uchar2*>(kmin + o + cB) = make_uchar2((unsigned char)in_[2], (unsigned char)in_[3]);
+    if (ok) {
+      const size_t o = (size_t)g * C + c0;
+      *reinterpret_cast<float4*>(zmax + o) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+      *reinterpret_cast<float4*>(zmin + o) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+      *reinterpret_cast<uchar4*>(kmax + o) = make_uchar4((unsigned char)ix[0], (unsigned char)ix[1],
+                                                         (unsigned char)ix[2], (unsigned char)ix[3]);
+      *reinterpret_cast<uchar4*>(kmin + o) = make_uchar4((unsigned char)in_[0], (unsigned char)in_[1],
+                                                         (unsigned char)in_[2], (unsigned char)in_[3]);
     }
   }
   cta_reduce_write<2>(acc, red, partials + (size_t)part * 2 * C, C, q * kChunk);
@@ -281,57 +272,38 @@ __global__ void __launch_bounds__(kWarps * 32) sa_dz2_expand_kernel(
   const int nchunks = (C + kChunk - 1) / kChunk;
   const int q = blockIdx.x % nchunks, part = blockIdx.x / nchunks, nparts = gridDim.x / nchunks;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int cA = q * kChunk + 2 * lane, cB = cA + 64;
-  const bool okA = cA < C, okB = cB < C;
+  const int c0 = q * kChunk + 4 * lane;
+  const bool ok = c0 < C;
   float sc[4], sh[4], mu[4], rs[4], g1[4], g2[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = (j < 2 ? cA : cB) + (j & 1);
-    const bool ok = (j < 2 ? okA : okB);
-    sc[j] = ok ? scale[c] : 0.f;
-    sh[j] = ok ? shift[c] : 0.f;
-    mu[j] = ok ? mean[c] : 0.f;
-    rs[j] = ok ? rstd[c] : 0.f;
-    g1[j] = ok ? m1[c] : 0.f;
-    g2[j] = ok ? m2[c] : 0.f;
-  }
+  ldc4(scale, c0, ok, sc);
+  ldc4(shift, c0, ok, sh);
+  ldc4(mean, c0, ok, mu);
+  ldc4(rstd, c0, ok, rs);
+  ldc4(m1, c0, ok, g1);
+  ldc4(m2, c0, ok, g2);
   for (long long g = (long long)part * kWarps + wib; g < G; g += (long long)nparts * kWarps) {
-    const size_t o = (size_t)g * C;
-    const float2 dA = ld2(dout + o + cA, okA), dB = ld2(dout + o + cB, okB);
-    const float2 zA = ld2(zsel + o + cA, okA), zB = ld2(zsel + o + cB, okB);
-    const float dsel[4] = {dA.x, dA.y, dB.x, dB.y};
-    const float zs[4] = {zA.x, zA.y, zB.x, zB.y};
+    const size_t o = (size_t)g * C + c0;
+    float dsel[4], zs[4], dy[4];
+    ldc4(dout + (size_t)g * C, c0, ok, dsel);
+    ldc4(zsel + (size_t)g * C, c0, ok, zs);
     int ks[4] = {-1, -1, -1, -1};
-    if (okA) {
-      const uchar2 u = *reinterpret_cast<const uchar2*>(ksel + o + cA);
-      ks[0] = u.x;
-      ks[1] = u.y;
+    if (ok) {
+      const uchar4 u = *reinterpret_cast<const uchar4*>(ksel + o);
+      ks[0] = u.x; ks[1] = u.y; ks[2] = u.z; ks[3] = u.w;
     }
-    if (okB) {
-      const uchar2 u = *reinterpret_cast<const uchar2*>(ksel + o + cB);
-      ks[2] = u.x;
-      ks[3] = u.y;
-    }
-    float dy[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      dy[j] = (fmaf(sc[j], zs[j], sh[j]) > 0.f) ? dsel[j] : 0.f;
-    }
+    for (int j = 0; j < 4; ++j) dy[j] = (fmaf(sc[j], zs[j], sh[j]) > 0.f) ? dsel[j] : 0.f;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
       const size_t row = (size_t)g * K + k;
-      const float* r = z2 + row * C;
-      const float2 vA = ld2(r + cA, okA), vB = ld2(r + cB, okB);
-      const float v[4] = {vA.x, vA.y, vB.x, vB.y};
-      float t[4];
+      float v[4], t[4];
+      ldc4(z2 + row * C, c0, ok, v);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float zh = (v[j] - mu[j]) * rs[j];
         t[j] = sc[j] * ((k == ks[j] ? dy[j] : 0.f) - g1[j] - zh * g2[j]);
       }
-      uint32_t* out = reinterpret_cast<uint32_t*>(dz2 + row * C);
-      if (okA) out[cA >> 1] = pack_bf16x2(t[0], t[1]);
-      if (okB) out[cB >> 1] = pack_bf16x2(t[2], t[3]);
+      if (ok) st4_bf16(dz2 + row * C + c0, t);
     }
   }
 }
@@ -346,19 +318,18 @@ __global__ void __launch_bounds__(kWarps * 32) bn_rows_stats_kernel(const float*
                                                                    const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, long long R, int C,
                                                                    float* __restrict__ partials) {
-  __shared__ float red[kWarps * 2 * kChunk];
+  __shared__ __align__(16) float red[kWarps * 2 * kChunk];
   const int nchunks = (C + kChunk - 1) / kChunk;
   const int q = blockIdx.x % nchunks, part = blockIdx.x / nchunks, nparts = gridDim.x / nchunks;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int cA = q * kChunk + 2 * lane, cB = cA + 64;
-  const bool okA = cA < C, okB = cB < C;
+  const int c0 = q * kChunk + 4 * lane;
+  const bool ok = c0 < C;
   float sc[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0}, mu[4] = {0, 0, 0, 0}, rs[4] = {0, 0, 0, 0};
   if (MODE == 1) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = (j < 2 ? cA : cB) + (j & 1);
-      if (j < 2 ? okA : okB) { sc[j] = scale[c]; sh[j] = shift[c]; mu[j] = mean[c]; rs[j] = rstd[c]; }
-    }
+    ldc4(scale, c0, ok, sc);
+    ldc4(shift, c0, ok, sh);
+    ldc4(mean, c0, ok, mu);
+    ldc4(rstd, c0, ok, rs);
   }
   float acc[2][4];
 #pragma unroll
@@ -367,16 +338,14 @@ __global__ void __launch_bounds__(kWarps * 32) bn_rows_stats_kernel(const float*
     for (int j = 0; j < 4; ++j) acc[s][j] = 0.f;
 #pragma unroll 4
   for (long long r = (long long)part * kWarps + wib; r < R; r += (long long)nparts * kWarps) {
-    const float* zr = z + (size_t)r * C;
-    const float2 vA = ld2(zr + cA, okA), vB = ld2(zr + cB, okB);
-    const float v[4] = {vA.x, vA.y, vB.x, vB.y};
+    float v[4];
+    ldc4(z + (size_t)r * C, c0, ok, v);
     if (MODE == 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc[0][j] += v[j]; acc[1][j] += v[j] * v[j]; }
     } else {
-      const float* dr = dout + (size_t)r * C;
-      const float2 dA = ld2(dr + cA, okA), dB = ld2(dr + cB, okB);
-      const float d[4] = {dA.x, dA.y, dB.x, dB.y};
+      float d[4];
+      ldc4(dout + (size_t)r * C, c0, ok, d);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float dy = (fmaf(sc[j], v[j], sh[j]) > 0.f) ? d[j] : 0.f;
@@ -561,6 +530,26 @@ __global__ void __launch_bounds__(256) three_nn_interp_bwd_kernel(const float* _
   }
 }
 
+// x fp32 [R, K] -> bf16 [R, 3K]: activation layout [hi | lo | hi], weight layout [hi | hi | lo] with hi = bf16(x),
+// lo = bf16(x - hi). A GEMM over the tripled K then yields x_hi w_hi + x_lo w_hi + x_hi w_lo: fp32-grade products
+// (error ~2^-17) from bf16 tensor-core operands, for the small per-point GEMMs that sit in front of a BatchNorm
+// (where a bf16-rounded operand with |mean| >> std would be amplified by the normalisation).
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long R, int K,
+                                    long long ldx, int weight_layout) {
+  const long long n = R * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / K;
+    const int k = (int)(i % K);
+    const float v = x[r * ldx + k];
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + r * 3 * K;
+    o[k] = hi;
+    o[K + k] = weight_layout ? hi : lo;
+    o[2 * K + k] = weight_layout ? lo : hi;
+  }
+}
+
 inline int grid_for_rows(long long work_items, int C, int P) {
   (void)work_items;
   const int nchunks = (C + kChunk - 1) / kChunk;
@@ -569,7 +558,7 @@ inline int grid_for_rows(long long work_items, int C, int P) {
 
 inline int check_group(const SaGroup& a) {
   if (a.B <= 0 || a.N <= 0 || a.S <= 0 || a.K <= 0 || a.C1 <= 0 || a.ldw < 3) return S3D_ERR_BAD_SHAPE;
-  if (a.K > 32 || (a.C1 & 1)) return S3D_ERR_UNSUPPORTED;
+  if (a.K > 32 || (a.C1 & 3)) return S3D_ERR_UNSUPPORTED;
   if (a.uf == nullptr || a.xyz == nullptr || a.cxyz == nullptr || a.idx == nullptr || a.w1 == nullptr)
     return S3D_ERR_NULL;
   return S3D_OK;
@@ -671,7 +660,7 @@ int s3d_sa_group_bwd_scatter(const float* uf, const float* xyz, const float* cxy
 int s3d_sa_group_reduce(const float* z2, int64_t G, int K, int C, float* zmax, float* zmin, uint8_t* kmax,
                         uint8_t* kmin, float* partials, int P, void* stream) {
   if (G <= 0 || K <= 0 || C <= 0 || P <= 0) return S3D_ERR_BAD_SHAPE;
-  if (K > 255 || (C & 1)) return S3D_ERR_UNSUPPORTED;
+  if (K > 255 || (C & 3)) return S3D_ERR_UNSUPPORTED;
   if (z2 == nullptr || zmax == nullptr || zmin == nullptr || kmax == nullptr || kmin == nullptr || partials == nullptr)
     return S3D_ERR_NULL;
   sa_group_reduce_kernel<<<grid_for_rows(G, C, P), kWarps * 32, 0, st(stream)>>>(z2, G, K, C, zmax, zmin, kmax, kmin,
@@ -700,7 +689,7 @@ int s3d_sa_dz2_expand(const float* z2, const float* dout, const float* zsel, con
                       const float* shift, const float* mean, const float* rstd, const float* m1, const float* m2,
                       void* dz2_bf16, int64_t G, int K, int C, int P, void* stream) {
   if (G <= 0 || K <= 0 || C <= 0 || P <= 0) return S3D_ERR_BAD_SHAPE;
-  if (K > 255 || (C & 1)) return S3D_ERR_UNSUPPORTED;
+  if (K > 255 || (C & 3)) return S3D_ERR_UNSUPPORTED;
   if (z2 == nullptr || dout == nullptr || zsel == nullptr || ksel == nullptr || scale == nullptr || shift == nullptr ||
       mean == nullptr || rstd == nullptr || m1 == nullptr || m2 == nullptr || dz2_bf16 == nullptr)
     return S3D_ERR_NULL;
@@ -712,7 +701,7 @@ int s3d_sa_dz2_expand(const float* z2, const float* dout, const float* zsel, con
 
 int s3d_bn_rows_stats(const float* z, int64_t R, int C, float* partials, int P, void* stream) {
   if (R <= 0 || C <= 0 || P <= 0) return S3D_ERR_BAD_SHAPE;
-  if (C & 1) return S3D_ERR_UNSUPPORTED;
+  if (C & 3) return S3D_ERR_UNSUPPORTED;
   if (z == nullptr || partials == nullptr) return S3D_ERR_NULL;
   bn_rows_stats_kernel<0><<<grid_for_rows(R, C, P), kWarps * 32, 0, st(stream)>>>(z, nullptr, nullptr, nullptr, nullptr,
                                                                                    nullptr, R, C, partials);
@@ -723,7 +712,7 @@ int s3d_bn_rows_stats(const float* z, int64_t R, int C, float* partials, int P, 
 int s3d_bn_rows_bwd_stats(const float* dout, const float* z, const float* scale, const float* shift, const float* mean,
                           const float* rstd, int64_t R, int C, float* partials, int P, void* stream) {
   if (R <= 0 || C <= 0 || P <= 0) return S3D_ERR_BAD_SHAPE;
-  if (C & 1) return S3D_ERR_UNSUPPORTED;
+  if (C & 3) return S3D_ERR_UNSUPPORTED;
   if (dout == nullptr || z == nullptr || scale == nullptr || shift == nullptr || mean == nullptr || rstd == nullptr ||
       partials == nullptr)
     return S3D_ERR_NULL;
@@ -785,6 +774,19 @@ int s3d_bn_relu_bwd_apply(const float* dout, const float* z, const float* scale,
   if (blocks > cap) blocks = cap;
   bn_relu_bwd_apply_kernel<<<(int)blocks, 256, 0, st(stream)>>>(dout, z, scale, shift, mean, rstd, m1, m2,
                                                                 reinterpret_cast<__nv_bfloat16*>(dz_bf16), n4, C);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+int s3d_split_bf16x3(const float* x, void* out_bf16, int64_t R, int K, int64_t ldx, int weight_layout, void* stream) {
+  if (R <= 0 || K <= 0 || ldx < K) return S3D_ERR_BAD_SHAPE;
+  if (x == nullptr || out_bf16 == nullptr) return S3D_ERR_NULL;
+  const long long n = (long long)R * K;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  split_bf16x3_kernel<<<(int)blocks, 256, 0, st(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), R, K, ldx,
+                                                           weight_layout);
   S3D_LAUNCH_OK();
   return S3D_OK;
 }

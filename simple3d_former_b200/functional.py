@@ -444,9 +444,11 @@ class SetAbstractionFn(torch.autograd.Function):
         assert Cin == Cf + 3 and w2.numel() == C2 * C1
         R, G = B * S * K, B * S
         w1_2d = w1.detach().reshape(C1, Cin)
-        w1f16 = shadow(w1).reshape(C1, Cin)[:, 3:].contiguous()  # feature columns; xyz columns stay fp32
-        f16 = L.cast_bf16(f.detach().reshape(B * N, Cf).contiguous().float())
-        uf = L.gemm(f16, w1f16, bias=b1, out_dtype=torch.float32)  # per-point part of layer 1, [B*N, C1]
+        # per-point part of layer 1, [B*N, C1]: feature columns on the tensor cores with hi/lo-split bf16 operands
+        # (fp32-grade: a BatchNorm follows, see s3d_split_bf16x3); the xyz columns stay fp32 in the gather passes
+        f3 = L.split_bf16x3(f.detach().reshape(B * N, Cf).contiguous().float())
+        w1f3 = L.split_bf16x3(w1_2d[:, 3:], weight_layout=True)
+        uf = L.gemm(f3, w1f3, bias=b1, out_dtype=torch.float32)
         grp = L.SaGroup(uf, xyz.contiguous(), cxyz.contiguous(), idx.contiguous(), w1_2d)
         if training:
             mean1, rstd1, sc1, sh1 = L.bn_finalize_fwd(L.sa_group_fwd_stats(grp), R, g1, be1, eps1, mom1, rm1, rv1)
@@ -461,7 +463,7 @@ class SetAbstractionFn(torch.autograd.Function):
         else:
             mean2, rstd2, sc2, sh2 = _bn_eval_affine(g2, be2, rm2, rv2, eps2)
         out, zsel, ksel = L.sa_pool_select(zmax, zmin, kmax, kmin, sc2, sh2)
-        ctx.save_for_backward(uf, grp.t[1], grp.t[2], grp.t[3], f16, w1f16, a1, z2, zsel, ksel, w1, w2, mean1, rstd1,
+        ctx.save_for_backward(uf, grp.t[1], grp.t[2], grp.t[3], f3, w1f3, a1, z2, zsel, ksel, w1, w2, mean1, rstd1,
                               sc1, mean2, rstd2, sc2, sh2)
         ctx.meta = (B, N, S, K, Cf, C1, C2, training)
         ctx.refs = (b1, b2)
@@ -469,9 +471,10 @@ class SetAbstractionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        (uf, xyz, cxyz, idx, f16, w1f16, a1, z2, zsel, ksel, w1, w2, mean1, rstd1, sc1, mean2, rstd2, sc2,
+        (uf, xyz, cxyz, idx, f3, w1f3, a1, z2, zsel, ksel, w1, w2, mean1, rstd1, sc1, mean2, rstd2, sc2,
          sh2) = ctx.saved_tensors
         B, N, S, K, Cf, C1, C2, training = ctx.meta
+        f16, w1f16 = f3[:, :Cf], w1f3[:, :Cf]  # the hi parts (row stride 3*Cf)
         b1, b2 = ctx.refs
         R, G = B * S * K, B * S
         Cin = Cf + 3
@@ -504,23 +507,24 @@ class LinearBnReluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, g, be, rm, rv, training, eps, mom):
         K = x.shape[-1]
-        x16 = L.cast_bf16(x.detach().reshape(-1, K).contiguous().float())
-        z = L.gemm(x16, _w2d(shadow(w)), bias=b, out_dtype=torch.float32)
+        x3 = L.split_bf16x3(x.detach().reshape(-1, K).contiguous().float())  # hi/lo split: a BatchNorm follows
+        z = L.gemm(x3, L.split_bf16x3(w.detach(), weight_layout=True), bias=b, out_dtype=torch.float32)
         R = z.shape[0]
         if training:
             mean, rstd, sc, sh = L.bn_finalize_fwd(L.bn_rows_stats(z), R, g, be, eps, mom, rm, rv)
         else:
             mean, rstd, sc, sh = _bn_eval_affine(g, be, rm, rv, eps)
         y, _ = L.bn_relu_apply(z, sc, sh)
-        ctx.save_for_backward(x16, z, w, mean, rstd, sc, sh)
+        ctx.save_for_backward(x3, z, w, mean, rstd, sc, sh)
         ctx.meta = (x.shape, training)
         ctx.bias_ref = b
         return y.view(*x.shape[:-1], z.shape[1])
 
     @staticmethod
     def backward(ctx, dy):
-        x16, z, w, mean, rstd, sc, sh = ctx.saved_tensors
+        x3, z, w, mean, rstd, sc, sh = ctx.saved_tensors
         in_shape, training = ctx.meta
+        x16 = x3[:, :in_shape[-1]]
         R = z.shape[0]
         dy2 = dy.reshape(z.shape).contiguous().float()
         m1, m2, dg, dbe = L.bn_finalize_bwd(L.bn_rows_bwd_stats(dy2, z, sc, sh, mean, rstd), R, training)

@@ -56,7 +56,7 @@ def _sa_reference(sa, xyz, pts, training):
     (c1, c2), (n1, n2) = sa.mlp_convs, sa.mlp_bns
     W1 = c1.weight.flatten(1)
     gx = xyz[bi[:, None, None], idx] - new_xyz[:, :, None]
-    z1 = gx @ W1[:, :3].t() + _r16(pts)[bi[:, None, None], idx] @ _r16(W1[:, 3:]).t() + c1.bias  # [B,S,K,C1]
+    z1 = gx @ W1[:, :3].t() + pts[bi[:, None, None], idx] @ W1[:, 3:].t() + c1.bias  # [B,S,K,C1]; split GEMM = fp32-grade
     a1 = _r16(F.relu(_bn(z1.permute(0, 3, 2, 1), n1, training)))  # [B,C1,K,S]
     z2 = F.conv2d(a1, _r16(c2.weight), c2.bias)
     y2 = F.relu(_bn(z2, n2, training))
@@ -69,7 +69,7 @@ def _tu_reference(tu, xyz1, p1, xyz2, p2, training):
 
     def fc(seq, x):
         lin, bn = seq[0], seq[2]
-        z = _r16(x) @ _r16(lin.weight).t() + lin.bias
+        z = x @ lin.weight.t() + lin.bias  # hi/lo-split GEMM in the product = fp32-grade
         return F.relu(_bn(z.transpose(1, 2), bn, training).transpose(1, 2))
 
     f1, f2 = fc(tu.fc1, p1), fc(tu.fc2, p2)
