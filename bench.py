@@ -242,10 +242,14 @@ class KernelProfile:
         if name == "s3d_attn_bwd":
             B, H, N, dh = a[10], a[11], a[12], a[13]
             return 10.0 * B * H * N * N * dh, 2.0 * 8 * B * H * N * dh
-        if name == "s3d_layernorm_fwd":
-            return 0.0, a[9] * a[10] * 6.0
-        if name == "s3d_layernorm_bwd":
-            return 0.0, a[11] * a[12] * 14.0
+        if name == "s3d_layernorm_fwd":  # read x, [addend]; write [sum], [bf16], [f32]
+            per = 4.0 + (4.0 if a[1] else 0.0) + (4.0 if a[2] else 0.0) + (2.0 if a[5] else 0.0) + (4.0 if a[6] else 0.0)
+            return 0.0, a[9] * a[10] * per
+        if name == "s3d_layernorm_bwd":  # read x, dy (bf16 / f32), [dres]; write dx, [bf16 copy]
+            per = 4.0 + (2.0 if a[1] else 4.0) + (4.0 if a[6] else 0.0) + 4.0 + (2.0 if a[8] else 0.0)
+            return 0.0, a[11] * a[12] * per
+        if name == "s3d_colsum_bf16":
+            return 0.0, a[2] * a[3] * 2.0
         return 0.0, 0.0
 
     @staticmethod

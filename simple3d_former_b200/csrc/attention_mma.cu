@@ -529,29 +529,12 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   load_tile<DH, 16>(sdO, p.dout + ooff, p.o_rs, 0, p.N, lane, 32);
   cp_async_commit();
 
-  // delta_i = sum_d dO[i,d] * O[i,d] straight from global memory (overlaps the cp.async traffic); every lane ends up
-  // with the values of "its" rows (lane/4, lane/4+8) and "its" columns (2*(lane%4)+{0,1} (+8)).
+  // delta_i = sum_d dO[i,d] O[i,d] = sum_j P[i,j] dP[i,j] (O = P V, dP = dO V^T): taken from the P and dP fragments below
+  // instead of re-reading O and dO from global memory row by row (that loop was 15 dependent load + warp-reduce round
+  // trips per warp and dominated the kernel). Lane l owns rows r0 = l/4, r1 = r0+8 and key columns 2*(l%4)+{0,1} (+8).
   const float* glse = p.lse + bh * p.N;
-  float del_r0 = 0.f, del_r1 = 0.f, del_c[4] = {0.f, 0.f, 0.f, 0.f};
   const int r0 = lane >> 2, r1 = r0 + 8;
   const int c0 = 2 * (lane & 3);
-  for (int i = 0; i < p.N; ++i) {
-    float s = 0.f;
-    for (int d = lane * 8; d < DH; d += 256) {
-      const uint4 uo = *reinterpret_cast<const uint4*>(p.o + ooff + (long long)i * p.o_rs + d);
-      const uint4 ug = *reinterpret_cast<const uint4*>(p.dout + ooff + (long long)i * p.o_rs + d);
-      const float2 o0 = unpack_bf16x2(uo.x), o1 = unpack_bf16x2(uo.y), o2 = unpack_bf16x2(uo.z), o3 = unpack_bf16x2(uo.w);
-      const float2 g0 = unpack_bf16x2(ug.x), g1 = unpack_bf16x2(ug.y), g2 = unpack_bf16x2(ug.z), g3 = unpack_bf16x2(ug.w);
-      s += (o0.x * g0.x + o0.y * g0.y) + (o1.x * g1.x + o1.y * g1.y) + (o2.x * g2.x + o2.y * g2.y) + (o3.x * g3.x + o3.y * g3.y);
-    }
-    s = warp_sum(s);
-    if (i == r0) del_r0 = s;
-    if (i == r1) del_r1 = s;
-    if (i == c0) del_c[0] = s;
-    if (i == c0 + 1) del_c[1] = s;
-    if (i == c0 + 8) del_c[2] = s;
-    if (i == c0 + 9) del_c[3] = s;
-  }
   // padded rows / columns: lse = +inf makes P = 0
   const float lse_r0 = r0 < p.N ? glse[r0] * kLog2e : INFINITY, lse_r1 = r1 < p.N ? glse[r1] * kLog2e : INFINITY;
   float lse_c[4];
@@ -584,10 +567,27 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
     const bool v0 = kidx < p.N, v1 = kidx + 1 < p.N;
     const float p00 = v0 ? exp2f(s[nt][0] * sc - lse_r0) : 0.f, p01 = v1 ? exp2f(s[nt][1] * sc - lse_r0) : 0.f;
     const float p10 = v0 ? exp2f(s[nt][2] * sc - lse_r1) : 0.f, p11 = v1 ? exp2f(s[nt][3] * sc - lse_r1) : 0.f;
-    s[nt][0] = p00 * (dp[nt][0] - del_r0);
-    s[nt][1] = p01 * (dp[nt][1] - del_r0);
-    s[nt][2] = p10 * (dp[nt][2] - del_r1);
-    s[nt][3] = p11 * (dp[nt][3] - del_r1);
+    s[nt][0] = p00; s[nt][1] = p01; s[nt][2] = p10; s[nt][3] = p11;
+  }
+  // row sums over the 16 keys: 4 values per lane, then the 4 lanes of a quad
+  float del_r0 = (s[0][0] * dp[0][0] + s[0][1] * dp[0][1]) + (s[1][0] * dp[1][0] + s[1][1] * dp[1][1]);
+  float del_r1 = (s[0][2] * dp[0][2] + s[0][3] * dp[0][3]) + (s[1][2] * dp[1][2] + s[1][3] * dp[1][3]);
+  del_r0 += __shfl_xor_sync(0xffffffffu, del_r0, 1);
+  del_r1 += __shfl_xor_sync(0xffffffffu, del_r1, 1);
+  del_r0 += __shfl_xor_sync(0xffffffffu, del_r0, 2);
+  del_r1 += __shfl_xor_sync(0xffffffffu, del_r1, 2);
+  // the transposed products below need delta per query COLUMN c0, c0+1 (rows r0 of lanes 4*c0, 4*(c0+1)) and c0+8, c0+9
+  float del_c[4];
+  del_c[0] = __shfl_sync(0xffffffffu, del_r0, 4 * c0);
+  del_c[1] = __shfl_sync(0xffffffffu, del_r0, 4 * (c0 + 1));
+  del_c[2] = __shfl_sync(0xffffffffu, del_r1, 4 * c0);
+  del_c[3] = __shfl_sync(0xffffffffu, del_r1, 4 * (c0 + 1));
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    s[nt][0] *= dp[nt][0] - del_r0;
+    s[nt][1] *= dp[nt][1] - del_r0;
+    s[nt][2] *= dp[nt][2] - del_r1;
+    s[nt][3] *= dp[nt][3] - del_r1;
   }
   {  // ---- dQ = dS K
     const uint32_t a0 = pack_bf16x2(s[0][0], s[0][1]), a1 = pack_bf16x2(s[0][2], s[0][3]);
