@@ -416,7 +416,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                                  "unit": "TFLOP/s" if rate(v)[0] else "GB/s"}
                              for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
                 "top_shapes": {k: {"ms_per_step": round(v["ms"] / 2, 3), "achieved": round(rate(v)[1], 1),
-                                   "unit": "TFLOP/s" if rate(v)[0] else "GB/s"} for k, v in shapes_sorted[:8]}}
+                                   "unit": "TFLOP/s" if rate(v)[0] else "GB/s"} for k, v in shapes_sorted[:24]}}
     samples = B * world * args.steps
     value = samples * cfg["per_sample"] / (dev_ms * 1e-3)
     e2e_value = samples * cfg["per_sample"] / (e2e_ms * 1e-3)

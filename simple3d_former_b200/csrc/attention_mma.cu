@@ -58,6 +58,13 @@ __device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g
   }
 }
 
+// transpose of an 8x8 matrix of 16-bit elements spread over the warp (lane l holds row l/4, columns 2*(l%4)+{0,1})
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
 template <bool INDEP>
 __device__ __forceinline__ void group_sync() {
   if (INDEP) __syncwarp(); else __syncthreads();
@@ -516,18 +523,32 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   extern __shared__ __align__(128) uint8_t smem_attn[];
   constexpr int kTile = 16 * DH * 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long bh = (long long)blockIdx.x * NWARPS + warp;
-  if (bh >= (long long)p.B * p.H) return;  // warp-uniform; only __syncwarp below
+  // persistent: warp w walks (batch, head) pairs w, w + W, ... with two smem stages, so the cp.async traffic of the
+  // next pair is in flight while the current one is multiplied (the kernel is HBM-bound: 54 KB moved per pair)
+  const long long BH = (long long)p.B * p.H;
+  const long long gw = (long long)blockIdx.x * NWARPS + warp;
+  const long long gstride = (long long)gridDim.x * NWARPS;
+  const uint32_t wbase = smem_u32(smem_attn) + warp * 8 * kTile;
+  auto prefetch = [&](long long t, int st) {
+    const int tb = (int)(t / p.H), th = (int)(t % p.H);
+    const long long tq = (long long)tb * p.qkv_bs + (long long)th * p.qkv_hs;
+    const long long to = (long long)tb * p.o_bs + (long long)th * p.o_hs;
+    const uint32_t sb = wbase + st * 4 * kTile;
+    load_tile<DH, 16>(sb, p.q + tq, p.qkv_rs, 0, p.N, lane, 32);
+    load_tile<DH, 16>(sb + kTile, p.k + tq, p.qkv_rs, 0, p.N, lane, 32);
+    load_tile<DH, 16>(sb + 2 * kTile, p.v + tq, p.qkv_rs, 0, p.N, lane, 32);
+    load_tile<DH, 16>(sb + 3 * kTile, p.dout + to, p.o_rs, 0, p.N, lane, 32);
+  };
+  if (gw < BH) prefetch(gw, 0);
+  cp_async_commit();
+  int it = 0;
+  for (long long bh = gw; bh < BH; bh += gstride, ++it) {
+  if (bh + gstride < BH) prefetch(bh + gstride, (it + 1) & 1);
+  cp_async_commit();
   const int b = (int)(bh / p.H), h = (int)(bh % p.H);
-  const uint32_t sbase = smem_u32(smem_attn) + warp * 4 * kTile;
+  const uint32_t sbase = wbase + (it & 1) * 4 * kTile;
   const uint32_t sQ = sbase, sK = sbase + kTile, sV = sbase + 2 * kTile, sdO = sbase + 3 * kTile;
   const long long qoff = (long long)b * p.qkv_bs + (long long)h * p.qkv_hs;
-  const long long ooff = (long long)b * p.o_bs + (long long)h * p.o_hs;
-  load_tile<DH, 16>(sQ, p.q + qoff, p.qkv_rs, 0, p.N, lane, 32);
-  load_tile<DH, 16>(sK, p.k + qoff, p.qkv_rs, 0, p.N, lane, 32);
-  load_tile<DH, 16>(sV, p.v + qoff, p.qkv_rs, 0, p.N, lane, 32);
-  load_tile<DH, 16>(sdO, p.dout + ooff, p.o_rs, 0, p.N, lane, 32);
-  cp_async_commit();
 
   // delta_i = sum_d dO[i,d] O[i,d] = sum_j P[i,j] dP[i,j] (O = P V, dP = dO V^T): taken from the P and dP fragments below
   // instead of re-reading O and dO from global memory row by row (that loop was 15 dependent load + warp-reduce round
@@ -537,13 +558,8 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   const int c0 = 2 * (lane & 3);
   // padded rows / columns: lse = +inf makes P = 0
   const float lse_r0 = r0 < p.N ? glse[r0] * kLog2e : INFINITY, lse_r1 = r1 < p.N ? glse[r1] * kLog2e : INFINITY;
-  float lse_c[4];
-  lse_c[0] = c0 < p.N ? glse[c0] * kLog2e : INFINITY;
-  lse_c[1] = c0 + 1 < p.N ? glse[c0 + 1] * kLog2e : INFINITY;
-  lse_c[2] = c0 + 8 < p.N ? glse[c0 + 8] * kLog2e : INFINITY;
-  lse_c[3] = c0 + 9 < p.N ? glse[c0 + 9] * kLog2e : INFINITY;
   const float sc = p.scale * kLog2e;
-  cp_async_wait<0>();
+  cp_async_wait<1>();
   __syncwarp();
 
   // ---- S = Q K^T, dP = dO V^T (rows = queries)
@@ -576,12 +592,9 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   del_r1 += __shfl_xor_sync(0xffffffffu, del_r1, 1);
   del_r0 += __shfl_xor_sync(0xffffffffu, del_r0, 2);
   del_r1 += __shfl_xor_sync(0xffffffffu, del_r1, 2);
-  // the transposed products below need delta per query COLUMN c0, c0+1 (rows r0 of lanes 4*c0, 4*(c0+1)) and c0+8, c0+9
-  float del_c[4];
-  del_c[0] = __shfl_sync(0xffffffffu, del_r0, 4 * c0);
-  del_c[1] = __shfl_sync(0xffffffffu, del_r0, 4 * (c0 + 1));
-  del_c[2] = __shfl_sync(0xffffffffu, del_r1, 4 * c0);
-  del_c[3] = __shfl_sync(0xffffffffu, del_r1, 4 * (c0 + 1));
+  // P as the A operand (rows = queries) of an m16n8k16 MMA; its transpose is taken below with movmatrix
+  const uint32_t pq0 = pack_bf16x2(s[0][0], s[0][1]), pq1 = pack_bf16x2(s[0][2], s[0][3]);
+  const uint32_t pq2 = pack_bf16x2(s[1][0], s[1][1]), pq3 = pack_bf16x2(s[1][2], s[1][3]);
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
     s[nt][0] *= dp[nt][0] - del_r0;
@@ -589,9 +602,9 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
     s[nt][2] *= dp[nt][2] - del_r1;
     s[nt][3] *= dp[nt][3] - del_r1;
   }
+  const uint32_t a0 = pack_bf16x2(s[0][0], s[0][1]), a1 = pack_bf16x2(s[0][2], s[0][3]);
+  const uint32_t a2 = pack_bf16x2(s[1][0], s[1][1]), a3 = pack_bf16x2(s[1][2], s[1][3]);
   {  // ---- dQ = dS K
-    const uint32_t a0 = pack_bf16x2(s[0][0], s[0][1]), a1 = pack_bf16x2(s[0][2], s[0][3]);
-    const uint32_t a2 = pack_bf16x2(s[1][0], s[1][1]), a3 = pack_bf16x2(s[1][2], s[1][3]);
     __nv_bfloat16* gdq = p.dq + qoff;
 #pragma unroll
     for (int dt2 = 0; dt2 < DH / 16; ++dt2) {
@@ -611,37 +624,14 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
       }
     }
   }
-  // ---- transposed products (rows = keys): S^T = K Q^T, dP^T = V dO^T
-  float st[2][4] = {}, dpt[2][4] = {};
-#pragma unroll
-  for (int ks = 0; ks < DH / 16; ++ks) {
-    uint32_t a0, a1, a2, a3, g0, g1, g2, g3, b0, b1, b2, b3;
-    ldsm_x4(tile_addr<DH>(sK, lane & 15, ks * 2 + (lane >> 4)), a0, a1, a2, a3);
-    ldsm_x4(tile_addr<DH>(sV, lane & 15, ks * 2 + (lane >> 4)), g0, g1, g2, g3);
-    const int qrow = (lane & 7) + ((lane >> 4) << 3), qch = ks * 2 + ((lane >> 3) & 1);
-    ldsm_x4(tile_addr<DH>(sQ, qrow, qch), b0, b1, b2, b3);
-    mma16816(st[0], a0, a1, a2, a3, b0, b1);
-    mma16816(st[1], a0, a1, a2, a3, b2, b3);
-    ldsm_x4(tile_addr<DH>(sdO, qrow, qch), b0, b1, b2, b3);
-    mma16816(dpt[0], g0, g1, g2, g3, b0, b1);
-    mma16816(dpt[1], g0, g1, g2, g3, b2, b3);
-  }
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    const float l0 = lse_c[2 * nt], l1 = lse_c[2 * nt + 1], d0 = del_c[2 * nt], d1 = del_c[2 * nt + 1];
-    const float p00 = exp2f(st[nt][0] * sc - l0), p01 = exp2f(st[nt][1] * sc - l1);
-    const float p10 = exp2f(st[nt][2] * sc - l0), p11 = exp2f(st[nt][3] * sc - l1);
-    st[nt][0] = p00; st[nt][1] = p01; st[nt][2] = p10; st[nt][3] = p11;
-    dpt[nt][0] = p00 * (dpt[nt][0] - d0);
-    dpt[nt][1] = p01 * (dpt[nt][1] - d1);
-    dpt[nt][2] = p10 * (dpt[nt][2] - d0);
-    dpt[nt][3] = p11 * (dpt[nt][3] - d1);
-  }
+  // ---- P^T and dS^T as A operands (rows = keys): a 16x16 fragment is four 8x8 blocks [[X00, X01], [X10, X11]] held
+  // as (a0, a2 / a1, a3); its transpose is [[X00^T, X10^T], [X01^T, X11^T]], each block transposed across the warp by
+  // movmatrix. This replaces recomputing K Q^T and V dO^T (64 of the kernel's 224 MMAs, 48 ldmatrix, 16 exp2).
   {  // ---- dV = P^T dO, dK = dS^T Q
-    const uint32_t pa0 = pack_bf16x2(st[0][0], st[0][1]), pa1 = pack_bf16x2(st[0][2], st[0][3]);
-    const uint32_t pa2 = pack_bf16x2(st[1][0], st[1][1]), pa3 = pack_bf16x2(st[1][2], st[1][3]);
-    const uint32_t sa0 = pack_bf16x2(dpt[0][0], dpt[0][1]), sa1 = pack_bf16x2(dpt[0][2], dpt[0][3]);
-    const uint32_t sa2 = pack_bf16x2(dpt[1][0], dpt[1][1]), sa3 = pack_bf16x2(dpt[1][2], dpt[1][3]);
+    const uint32_t pa0 = movmatrix_trans(pq0), pa1 = movmatrix_trans(pq2), pa2 = movmatrix_trans(pq1),
+                   pa3 = movmatrix_trans(pq3);
+    const uint32_t sa0 = movmatrix_trans(a0), sa1 = movmatrix_trans(a2), sa2 = movmatrix_trans(a1),
+                   sa3 = movmatrix_trans(a3);
     __nv_bfloat16* gdk = p.dk + qoff;
     __nv_bfloat16* gdv = p.dv + qoff;
     const int qrow = (lane & 7) + (((lane >> 3) & 1) << 3);
@@ -669,6 +659,8 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
         *reinterpret_cast<uint32_t*>(gdk + (long long)r1 * p.qkv_rs + col + 8) = pack_bf16x2(k1[2] * p.scale, k1[3] * p.scale);
       }
     }
+  }
+  __syncwarp();  // all lanes are done with this stage before it is refilled two pairs later
   }
 }
 
@@ -723,12 +715,14 @@ template <int DH>
 static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
   const long long BH = (long long)p.B * p.H;
   if (p.N <= 16) {  // fused delta + dQ + dK + dV, one warp per (batch, head)
-    constexpr int NW = (DH == 64) ? 4 : 2;
-    constexpr int smem = NW * 4 * 16 * DH * 2;
+    constexpr int NW = (DH == 64) ? 8 : (DH == 192 ? 4 : 3);
+    constexpr int smem = NW * 2 * 4 * 16 * DH * 2;  // two stages of {Q, K, V, dO} per warp
     auto kern = attn_bwd_small_kernel<DH, NW>;
     int rc = set_smem(kern, smem);
     if (rc) return rc;
-    kern<<<(unsigned)((BH + NW - 1) / NW), NW * 32, smem, stream>>>(p);
+    long long ctas = (BH + NW - 1) / NW;
+    if (ctas > num_sms()) ctas = num_sms();
+    kern<<<(unsigned)ctas, NW * 32, smem, stream>>>(p);
     S3D_LAUNCH_OK();
     return S3D_OK;
   }

@@ -113,6 +113,10 @@ __device__ __forceinline__ void epi_act(const GemmParams& p, int row, bool row_o
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
 __device__ __forceinline__ void epi_residual(const GemmParams& p, long long boff_r, int row, bool row_ok, int n,
                                              float (&f)[32]) {
   if (p.residual == nullptr || !row_ok || n >= p.N) return;
@@ -321,10 +325,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       int m0, n0, kb0, kb1, split;
       decode(item, m0, n0, kb0, kb1, split);
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
+      if (splits == 1 && row_ok) {
+        // The epilogue reads its residual / aux operands straight from global memory, one 32-column chunk at a time,
+        // and each read used to expose a full DRAM round trip (short-K GEMMs were epilogue-latency bound: the fp32
+        // residual proj GEMM ran at 565 TFLOP/s, the dGELU GEMM at 790). Pull this thread's lines of the tile into L2
+        // now, while the tensor cores are still producing the accumulator.
+        const int nb0 = n0 + half * kColsPerHalf;
+        if (p.residual != nullptr) {
+          const float* r = p.residual + boff_r + (long long)row * p.ldr + nb0;
+#pragma unroll
+          for (int c = 0; c < kColsPerHalf; c += 32)
+            if (nb0 + c < p.N) prefetch_l2(r + c);
+        }
+        if (p.aux_in != nullptr) {
+          const __nv_bfloat16* a = p.aux_in + (long long)row * p.ld_aux_in + nb0;
+#pragma unroll
+          for (int c = 0; c < kColsPerHalf; c += 64)
+            if (nb0 + c < p.N) prefetch_l2(a + c);
+        }
+      }
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
       if constexpr (BN >= 128) {
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
         if (splits == 1) {
@@ -749,6 +772,12 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   }
   if (bn != 64 && bn != 128 && bn != 256) return S3D_ERR_UNSUPPORTED;
   const long long tiles = (long long)num_m * ((p.N + bn - 1) / bn) * nb;
+  // cluster size along M (B-tile multicast): needs >= 2 m-tiles and whole 64-wide chunks of B per CTA
+  int cl = g.force_cluster > 0 ? g.force_cluster : (env_cluster > 0 ? env_cluster : 2);
+  if (cl > bn / 64) cl = bn / 64;
+  if (num_m < 2 || cl < 1) cl = 1;
+  if (cl == 4 && (bn != 256 || num_m < 4)) cl = 2;
+  if (cl == 3 || cl > 4) cl = 2;
   // split-K: plain fp32 output (optionally accumulating onto itself), too few tiles to fill the machine, long K
   const bool split_ok = p.out_fp32 && p.epilogue == EPI_NONE && p.aux_out == nullptr &&
                         (p.residual == nullptr || p.residual == p.D) && nb == 1;
@@ -756,10 +785,28 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   if (g.force_splits > 0) splits = split_ok ? g.force_splits : 1;
   else if (split_ok && g.a_mn && g.b_mn && tiles * 2 <= sms && num_kb >= 8) {
     // automatic split-K only for weight-gradient GEMMs (both operands MN-major, K = tokens): red.add makes the fp32
-    // summation order non-deterministic, which forward / activation-gradient GEMMs must not be
-    splits = (int)((2LL * sms + tiles - 1) / tiles);
-    if (splits > num_kb / 4) splits = num_kb / 4;
-    if (splits < 1) splits = 1;
+    // summation order non-deterministic, which forward / activation-gradient GEMMs must not be.
+    // The persistent kernel walks work items in rounds of `slots` clusters: pick the smallest split factor whose last
+    // round is (nearly) full -- e.g. 27 cluster tiles on 74 slots: 5 splits = 135 items = 2 rounds at 91 %, 6 splits =
+    // 3 rounds at 73 %, 8 splits = 216 items = 3 rounds at 97 %.
+    const long long ctiles = (long long)((num_m + cl - 1) / cl) * ((p.N + bn - 1) / bn);
+    const long long slots = sms / cl > 0 ? sms / cl : 1;
+    int smax = (int)((4 * slots + ctiles - 1) / ctiles);
+    if (smax > num_kb / 4) smax = num_kb / 4;
+    if (smax < 1) smax = 1;
+    double best = 0.0;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const long long items = ctiles * sp;
+      const long long rounds = (items + slots - 1) / slots;
+      const double eff = (double)items / (double)(rounds * slots);
+      if (eff > best) best = eff;
+    }
+    for (int sp = 1; sp <= smax; ++sp) {
+      const long long items = ctiles * sp;
+      const long long rounds = (items + slots - 1) / slots;
+      const double eff = (double)items / (double)(rounds * slots);
+      if (eff >= 0.97 * best) { splits = sp; break; }
+    }
   }
   if (splits > num_kb) splits = num_kb;
   p.splits = splits;
@@ -771,12 +818,6 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
     }
     p.residual = nullptr;  // accumulate-in-place is what the reduction does anyway
   }
-  // cluster size along M (B-tile multicast): needs >= 2 m-tiles and whole 64-wide chunks of B per CTA
-  int cl = g.force_cluster > 0 ? g.force_cluster : (env_cluster > 0 ? env_cluster : 2);
-  if (cl > bn / 64) cl = bn / 64;
-  if (num_m < 2 || cl < 1) cl = 1;
-  if (cl == 4 && (bn != 256 || num_m < 4)) cl = 2;
-  if (cl == 3 || cl > 4) cl = 2;
   switch (bn) {
     case 256:
       if (cl == 4) return dispatch_major<256, 4>(g, stream);

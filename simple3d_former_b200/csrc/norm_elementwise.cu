@@ -82,6 +82,150 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
 }
 
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward, bulk-async pipelined variant (large T, 16-byte aligned rows): each warp streams its rows through a
+// ring of shared-memory slots with cp.async.bulk + mbarrier (see the backward variant below for the rationale).
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnFwdWarps = 16;
+
+template <int VEC_ITERS, int STAGES>
+__global__ void __launch_bounds__(kLnFwdWarps * 32, 1)
+    layernorm_fwd_pipe_kernel(const float* __restrict__ x, const float* __restrict__ addend, float* __restrict__ sum_out,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
+                              float* __restrict__ mean_out, float* __restrict__ rstd_out, int T, int D, float eps) {
+  extern __shared__ __align__(128) uint8_t lnf_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  const uint32_t x_bytes = (uint32_t)D * 4u;
+  const uint32_t row_bytes = addend != nullptr ? 2u * x_bytes : x_bytes;
+  uint8_t* ring = lnf_smem + (size_t)wib * STAGES * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lnf_smem + (size_t)kLnFwdWarps * STAGES * row_bytes) + wib * STAGES;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+  }
+  fence_barrier_init();
+  __syncthreads();
+  const long long warp = (long long)blockIdx.x * kLnFwdWarps + wib;
+  const long long nwarps = (long long)gridDim.x * kLnFwdWarps;
+  auto issue = [&](long long row, int s) {  // lane 0 only
+    uint8_t* dst = ring + (size_t)s * row_bytes;
+    mbar_expect_tx(&bars[s], row_bytes);
+    bulk_g2s(dst, x + (size_t)row * D, x_bytes, &bars[s]);
+    if (addend != nullptr) bulk_g2s(dst + x_bytes, addend + (size_t)row * D, x_bytes, &bars[s]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      const long long row = warp + (long long)s * nwarps;
+      if (row < T) issue(row, s);
+    }
+  }
+  float4 gm[VEC_ITERS], bt[VEC_ITERS];
+#pragma unroll
+  for (int i = 0; i < VEC_ITERS; ++i) {
+    const int c = lane + 32 * i;
+    gm[i] = c < nvec ? reinterpret_cast<const float4*>(gamma)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[i] = c < nvec ? reinterpret_cast<const float4*>(beta)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int it = 0;
+  for (long long row = warp; row < T; row += nwarps, ++it) {
+    const int s = it % STAGES;
+    const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+    const uint8_t* buf = ring + (size_t)s * row_bytes;
+    mbar_wait(&bars[s], parity);
+    float4 v[VEC_ITERS];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        v[i] = reinterpret_cast<const float4*>(buf)[c];
+        if (addend != nullptr) {
+          const float4 a = reinterpret_cast<const float4*>(buf + x_bytes)[c];
+          v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+          if (sum_out != nullptr) reinterpret_cast<float4*>(sum_out + (size_t)row * D)[c] = v[i];
+        }
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      } else {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // slot s is in registers now: refill it for the row STAGES ahead before doing the arithmetic
+    __syncwarp();
+    const long long next = row + (long long)STAGES * nwarps;
+    if (lane == 0 && next < T) issue(next, s);
+    sum = warp_sum(sum);
+    const float mean = sum / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / (float)D + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * gm[i].x + bt[i].x;
+        o.y = (v[i].y - mean) * rstd * gm[i].y + bt[i].y;
+        o.z = (v[i].z - mean) * rstd * gm[i].z + bt[i].z;
+        o.w = (v[i].w - mean) * rstd * gm[i].w + bt[i].w;
+        if (y_bf16 != nullptr) {
+          uint2 u;
+          u.x = pack_bf16x2(o.x, o.y);
+          u.y = pack_bf16x2(o.z, o.w);
+          reinterpret_cast<uint2*>(y_bf16 + (size_t)row * D)[c] = u;
+        }
+        if (y_f32 != nullptr) reinterpret_cast<float4*>(y_f32 + (size_t)row * D)[c] = o;
+      }
+    }
+  }
+}
+
+template <int I>
+static int launch_ln_fwd_pipe(const float* x, const float* addend, float* sum_out, const float* gamma, const float* beta,
+                              __nv_bfloat16* yb, float* y_f32, float* mean, float* rstd, int T, int D, float eps,
+                              cudaStream_t stream) {
+  const size_t row_bytes = (size_t)D * 4 * (addend != nullptr ? 2 : 1);
+  const int stages = addend != nullptr ? 2 : 3;
+  const size_t shmem = (size_t)kLnFwdWarps * stages * (row_bytes + sizeof(uint64_t));
+  if (shmem > 227 * 1024) return S3D_ERR_UNSUPPORTED;
+  long long blocks = ((long long)T + kLnFwdWarps - 1) / kLnFwdWarps;
+  if (blocks > num_sms()) blocks = num_sms();
+  if (stages == 3) {
+    auto kern = layernorm_fwd_pipe_kernel<I, 3>;
+    S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    kern<<<(int)blocks, kLnFwdWarps * 32, shmem, stream>>>(x, addend, sum_out, gamma, beta, yb, y_f32, mean, rstd, T, D,
+                                                           eps);
+  } else {
+    auto kern = layernorm_fwd_pipe_kernel<I, 2>;
+    S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    kern<<<(int)blocks, kLnFwdWarps * 32, shmem, stream>>>(x, addend, sum_out, gamma, beta, yb, y_f32, mean, rstd, T, D,
+                                                           eps);
+  }
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
 int layernorm_fwd(const float* x, const float* addend, float* sum_out, const float* gamma, const float* beta,
                   void* y_bf16, float* y_f32, float* mean, float* rstd, int T, int D, float eps, cudaStream_t stream) {
   if (T <= 0 || D <= 0 || D % 4 != 0 || D > 1024) return S3D_ERR_BAD_SHAPE;
@@ -92,6 +236,25 @@ int layernorm_fwd(const float* x, const float* addend, float* sum_out, const flo
   if (blocks > cap) blocks = cap;
   const int iters = (D / 4 + 31) / 32;
   auto yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  static const bool no_pipe = getenv("S3D_LN_FWD_NO_PIPE") != nullptr;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(addend)) & 15) == 0;
+  if (!no_pipe && aligned && (long long)T >= (long long)num_sms() * kLnFwdWarps * 4) {
+    int rc = S3D_ERR_UNSUPPORTED;
+#define S3D_LN_FWD_PIPE(I) \
+  rc = launch_ln_fwd_pipe<I>(x, addend, sum_out, gamma, beta, yb, y_f32, mean, rstd, T, D, eps, stream)
+    switch (iters) {
+      case 1: S3D_LN_FWD_PIPE(1); break;
+      case 2: S3D_LN_FWD_PIPE(2); break;
+      case 3: S3D_LN_FWD_PIPE(3); break;
+      case 4: S3D_LN_FWD_PIPE(4); break;
+      case 5: S3D_LN_FWD_PIPE(5); break;
+      case 6: S3D_LN_FWD_PIPE(6); break;
+      case 7: S3D_LN_FWD_PIPE(7); break;
+      default: S3D_LN_FWD_PIPE(8); break;
+    }
+#undef S3D_LN_FWD_PIPE
+    if (rc != S3D_ERR_UNSUPPORTED) return rc;
+  }
 #define S3D_LN_FWD(I)                                                                                              \
   layernorm_fwd_kernel<I><<<(int)blocks, warps_per_block * 32, 0, stream>>>(x, addend, sum_out, gamma, beta, yb, \
                                                                             y_f32, mean, rstd, T, D, eps)
@@ -226,13 +389,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 12;
 constexpr int kLnStages = 2;
-
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 template <int VEC_ITERS, bool DY_BF16>
 __global__ void __launch_bounds__(kLnWarps * 32, 1)
