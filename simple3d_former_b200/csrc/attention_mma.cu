@@ -31,6 +31,15 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// D = A * B with a zero accumulator (C is the zero register: no accumulator initialisation moves)
+__device__ __forceinline__ void mma16816_z(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                           uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%10, %10, %10, %10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -529,15 +538,46 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   const long long gw = (long long)blockIdx.x * NWARPS + warp;
   const long long gstride = (long long)gridDim.x * NWARPS;
   const uint32_t wbase = smem_u32(smem_attn) + warp * 8 * kTile;
+  // one tile = 16 rows x DH bf16; lane l copies 16-byte chunk l (+32, ...) of every VALID row: the source pointer
+  // advances by one row stride per row, the swizzled smem offsets (chunk ^ (row & 7)) are 8 per-lane constants.
+  // Rows >= N are never written by cp.async; they are zeroed once here (P = 0 must not meet NaN garbage).
+  constexpr int CH = DH / 8;
+  uint32_t xs[(CH + 31) / 32][8];
+#pragma unroll
+  for (int c = 0; c < (CH + 31) / 32; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xs[c][k] = (uint32_t)(((c * 32 + lane) ^ k) << 4);
+  for (int i = lane; i < 8 * 16 * CH; i += 32) {
+    const int t = i / (16 * CH), r = (i / CH) % 16, ch = i % CH;
+    if (r >= p.N) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tile_addr<DH>(wbase + t * kTile, r, ch)), "r"(0));
+    }
+  }
+  __syncwarp();
+  auto load16 = [&](uint32_t sb, const __nv_bfloat16* g, long long rs) {
+#pragma unroll
+    for (int c = 0; c < (CH + 31) / 32; ++c) {
+      if (CH % 32 == 0 || c * 32 + lane < CH) {
+        const __nv_bfloat16* src = g + (c * 32 + lane) * 8;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          if (r < p.N) {  // warp-uniform
+            cp_async16(sb + r * (DH * 2) + xs[c][r & 7], src, 16);
+            src += rs;
+          }
+        }
+      }
+    }
+  };
   auto prefetch = [&](long long t, int st) {
     const int tb = (int)(t / p.H), th = (int)(t % p.H);
     const long long tq = (long long)tb * p.qkv_bs + (long long)th * p.qkv_hs;
     const long long to = (long long)tb * p.o_bs + (long long)th * p.o_hs;
     const uint32_t sb = wbase + st * 4 * kTile;
-    load_tile<DH, 16>(sb, p.q + tq, p.qkv_rs, 0, p.N, lane, 32);
-    load_tile<DH, 16>(sb + kTile, p.k + tq, p.qkv_rs, 0, p.N, lane, 32);
-    load_tile<DH, 16>(sb + 2 * kTile, p.v + tq, p.qkv_rs, 0, p.N, lane, 32);
-    load_tile<DH, 16>(sb + 3 * kTile, p.dout + to, p.o_rs, 0, p.N, lane, 32);
+    load16(sb, p.q + tq, p.qkv_rs);
+    load16(sb + kTile, p.k + tq, p.qkv_rs);
+    load16(sb + 2 * kTile, p.v + tq, p.qkv_rs);
+    load16(sb + 3 * kTile, p.dout + to, p.o_rs);
   };
   if (gw < BH) prefetch(gw, 0);
   cp_async_commit();
@@ -595,32 +635,35 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   // P as the A operand (rows = queries) of an m16n8k16 MMA; its transpose is taken below with movmatrix
   const uint32_t pq0 = pack_bf16x2(s[0][0], s[0][1]), pq1 = pack_bf16x2(s[0][2], s[0][3]);
   const uint32_t pq2 = pack_bf16x2(s[1][0], s[1][1]), pq3 = pack_bf16x2(s[1][2], s[1][3]);
+  // dS = P * (dP - delta), pre-multiplied by the softmax scale that both dQ = scale * dS K and dK = scale * dS^T Q carry
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
-    s[nt][0] *= dp[nt][0] - del_r0;
-    s[nt][1] *= dp[nt][1] - del_r0;
-    s[nt][2] *= dp[nt][2] - del_r1;
-    s[nt][3] *= dp[nt][3] - del_r1;
+    s[nt][0] *= (dp[nt][0] - del_r0) * p.scale;
+    s[nt][1] *= (dp[nt][1] - del_r0) * p.scale;
+    s[nt][2] *= (dp[nt][2] - del_r1) * p.scale;
+    s[nt][3] *= (dp[nt][3] - del_r1) * p.scale;
   }
+  const bool ok0 = r0 < p.N, ok1 = r1 < p.N;
+  const long long roff0 = qoff + (long long)r0 * p.qkv_rs + c0, roff1 = roff0 + 8 * p.qkv_rs;
   const uint32_t a0 = pack_bf16x2(s[0][0], s[0][1]), a1 = pack_bf16x2(s[0][2], s[0][3]);
   const uint32_t a2 = pack_bf16x2(s[1][0], s[1][1]), a3 = pack_bf16x2(s[1][2], s[1][3]);
   {  // ---- dQ = dS K
-    __nv_bfloat16* gdq = p.dq + qoff;
+    uint32_t* q0 = reinterpret_cast<uint32_t*>(p.dq + roff0);
+    uint32_t* q1 = reinterpret_cast<uint32_t*>(p.dq + roff1);
 #pragma unroll
     for (int dt2 = 0; dt2 < DH / 16; ++dt2) {
-      float acc0[4] = {}, acc1[4] = {};
+      float acc0[4], acc1[4];
       uint32_t b0, b1, b2, b3;
       ldsm_x4_t(tile_addr<DH>(sK, (lane & 7) + (((lane >> 3) & 1) << 3), dt2 * 2 + (lane >> 4)), b0, b1, b2, b3);
-      mma16816(acc0, a0, a1, a2, a3, b0, b1);
-      mma16816(acc1, a0, a1, a2, a3, b2, b3);
-      const int col = dt2 * 16 + c0;
-      if (r0 < p.N) {
-        *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * p.qkv_rs + col) = pack_bf16x2(acc0[0] * p.scale, acc0[1] * p.scale);
-        *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * p.qkv_rs + col + 8) = pack_bf16x2(acc1[0] * p.scale, acc1[1] * p.scale);
+      mma16816_z(acc0, a0, a1, a2, a3, b0, b1);
+      mma16816_z(acc1, a0, a1, a2, a3, b2, b3);
+      if (ok0) {
+        q0[dt2 * 8] = pack_bf16x2(acc0[0], acc0[1]);
+        q0[dt2 * 8 + 4] = pack_bf16x2(acc1[0], acc1[1]);
       }
-      if (r1 < p.N) {
-        *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * p.qkv_rs + col) = pack_bf16x2(acc0[2] * p.scale, acc0[3] * p.scale);
-        *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * p.qkv_rs + col + 8) = pack_bf16x2(acc1[2] * p.scale, acc1[3] * p.scale);
+      if (ok1) {
+        q1[dt2 * 8] = pack_bf16x2(acc0[2], acc0[3]);
+        q1[dt2 * 8 + 4] = pack_bf16x2(acc1[2], acc1[3]);
       }
     }
   }
@@ -632,31 +675,32 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
                    pa3 = movmatrix_trans(pq3);
     const uint32_t sa0 = movmatrix_trans(a0), sa1 = movmatrix_trans(a2), sa2 = movmatrix_trans(a1),
                    sa3 = movmatrix_trans(a3);
-    __nv_bfloat16* gdk = p.dk + qoff;
-    __nv_bfloat16* gdv = p.dv + qoff;
+    uint32_t* k0p = reinterpret_cast<uint32_t*>(p.dk + roff0);
+    uint32_t* k1p = reinterpret_cast<uint32_t*>(p.dk + roff1);
+    uint32_t* v0p = reinterpret_cast<uint32_t*>(p.dv + roff0);
+    uint32_t* v1p = reinterpret_cast<uint32_t*>(p.dv + roff1);
     const int qrow = (lane & 7) + (((lane >> 3) & 1) << 3);
 #pragma unroll
     for (int dt2 = 0; dt2 < DH / 16; ++dt2) {
-      float v0[4] = {}, v1[4] = {}, k0[4] = {}, k1[4] = {};
+      float v0[4], v1[4], k0[4], k1[4];
       uint32_t b0, b1, b2, b3;
       ldsm_x4_t(tile_addr<DH>(sdO, qrow, dt2 * 2 + (lane >> 4)), b0, b1, b2, b3);
-      mma16816(v0, pa0, pa1, pa2, pa3, b0, b1);
-      mma16816(v1, pa0, pa1, pa2, pa3, b2, b3);
+      mma16816_z(v0, pa0, pa1, pa2, pa3, b0, b1);
+      mma16816_z(v1, pa0, pa1, pa2, pa3, b2, b3);
       ldsm_x4_t(tile_addr<DH>(sQ, qrow, dt2 * 2 + (lane >> 4)), b0, b1, b2, b3);
-      mma16816(k0, sa0, sa1, sa2, sa3, b0, b1);
-      mma16816(k1, sa0, sa1, sa2, sa3, b2, b3);
-      const int col = dt2 * 16 + c0;
-      if (r0 < p.N) {
-        *reinterpret_cast<uint32_t*>(gdv + (long long)r0 * p.qkv_rs + col) = pack_bf16x2(v0[0], v0[1]);
-        *reinterpret_cast<uint32_t*>(gdv + (long long)r0 * p.qkv_rs + col + 8) = pack_bf16x2(v1[0], v1[1]);
-        *reinterpret_cast<uint32_t*>(gdk + (long long)r0 * p.qkv_rs + col) = pack_bf16x2(k0[0] * p.scale, k0[1] * p.scale);
-        *reinterpret_cast<uint32_t*>(gdk + (long long)r0 * p.qkv_rs + col + 8) = pack_bf16x2(k1[0] * p.scale, k1[1] * p.scale);
+      mma16816_z(k0, sa0, sa1, sa2, sa3, b0, b1);
+      mma16816_z(k1, sa0, sa1, sa2, sa3, b2, b3);
+      if (ok0) {
+        v0p[dt2 * 8] = pack_bf16x2(v0[0], v0[1]);
+        v0p[dt2 * 8 + 4] = pack_bf16x2(v1[0], v1[1]);
+        k0p[dt2 * 8] = pack_bf16x2(k0[0], k0[1]);
+        k0p[dt2 * 8 + 4] = pack_bf16x2(k1[0], k1[1]);
       }
-      if (r1 < p.N) {
-        *reinterpret_cast<uint32_t*>(gdv + (long long)r1 * p.qkv_rs + col) = pack_bf16x2(v0[2], v0[3]);
-        *reinterpret_cast<uint32_t*>(gdv + (long long)r1 * p.qkv_rs + col + 8) = pack_bf16x2(v1[2], v1[3]);
-        *reinterpret_cast<uint32_t*>(gdk + (long long)r1 * p.qkv_rs + col) = pack_bf16x2(k0[2] * p.scale, k0[3] * p.scale);
-        *reinterpret_cast<uint32_t*>(gdk + (long long)r1 * p.qkv_rs + col + 8) = pack_bf16x2(k1[2] * p.scale, k1[3] * p.scale);
+      if (ok1) {
+        v1p[dt2 * 8] = pack_bf16x2(v0[2], v0[3]);
+        v1p[dt2 * 8 + 4] = pack_bf16x2(v1[2], v1[3]);
+        k1p[dt2 * 8] = pack_bf16x2(k0[2], k0[3]);
+        k1p[dt2 * 8 + 4] = pack_bf16x2(k1[2], k1[3]);
       }
     }
   }
