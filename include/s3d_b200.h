@@ -200,6 +200,21 @@ int s3d_three_nn_interp_fwd(const float* feats, const int64_t* idx, const float*
 int s3d_three_nn_interp_bwd(const float* dout, const int64_t* idx, const float* dist, float* dfeats, int B, int S, int N,
                             int C, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * binvox payload -> dense occupancy grid (reference utils/binvox_rw.py:117-151 read_as_3d_array, as called by
+ * data/modelnet40.py:35-45 / data/shapenet_v2.py:34-44). `payload` holds the (value, count) byte pairs of B models
+ * back to back (everything after the "data\n" header line); offsets int64 [B+1] are byte offsets of each model's
+ * pairs; run_offsets int64 [B+1] the same in runs (= offsets / 2 when the models are packed pair-aligned).
+ *   s3d_binvox_scan   : run_end[r] = inclusive prefix sum of the counts of model b (uint32, workspace of total-runs
+ *                       entries), totals[b] = number of voxels the stream encodes (the caller checks it equals V^3)
+ *   s3d_binvox_expand : out [B,1,V,V,V] (out_dtype 0 = f32, 1 = u8, 2 = i32), voxel != 0 -> 1; the stream is x-z-y
+ *                       ordered, fix_coords = 1 writes x-y-z like read_as_3d_array(fix_coords=True) (:143-146)
+ * ------------------------------------------------------------------------------------------------------------- */
+int s3d_binvox_scan(const uint8_t* payload, const int64_t* offsets, uint32_t* run_end, const int64_t* run_offsets,
+                    int64_t* totals, int B, void* stream);
+int s3d_binvox_expand(const uint8_t* payload, const int64_t* offsets, const uint32_t* run_end,
+                      const int64_t* run_offsets, void* out, int out_dtype, int B, int V, int fix_coords, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

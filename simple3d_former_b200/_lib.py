@@ -58,6 +58,8 @@ SIGNATURES = {
     "s3d_bn_relu_apply": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "s3d_bn_relu_bwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "s3d_split_bf16x3": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P]),
+    "s3d_binvox_scan": (c_int, [_P, _P, _P, _P, _P, c_int, _P]),
+    "s3d_binvox_expand": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "s3d_three_nn_interp_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "s3d_three_nn_interp_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
 }
@@ -496,3 +498,20 @@ def split_bf16x3(x, weight_layout=False):
     out = torch.empty((R, 3 * K), device=x.device, dtype=torch.bfloat16)
     call("s3d_split_bf16x3", ptr(x), ptr(out), R, K, x.stride(0), int(weight_layout), stream())
     return out
+
+
+def binvox_expand(payload, offsets, V, out_dtype=torch.uint8, fix_coords=True):
+    """payload uint8 [bytes] (value, count) pairs of B models back to back, offsets int64 [B+1] (even byte offsets).
+    Returns (grid [B,1,V,V,V] of out_dtype, totals int64 [B] = voxels encoded per model)."""
+    _need_cuda(payload, offsets)
+    assert payload.dtype == torch.uint8 and payload.is_contiguous() and offsets.dtype == torch.long
+    B = offsets.numel() - 1
+    dev = payload.device
+    run_offsets = offsets // 2
+    run_end = torch.empty(max(payload.numel() // 2, 1), device=dev, dtype=torch.int32)
+    totals = torch.empty(B, device=dev, dtype=torch.long)
+    call("s3d_binvox_scan", ptr(payload), ptr(offsets), ptr(run_end), ptr(run_offsets), ptr(totals), B, stream())
+    out = torch.empty((B, 1, V, V, V), device=dev, dtype=out_dtype)
+    call("s3d_binvox_expand", ptr(payload), ptr(offsets), ptr(run_end), ptr(run_offsets), ptr(out),
+         _VOXEL_DTYPES[out_dtype], B, V, int(fix_coords), stream())
+    return out, totals
