@@ -251,7 +251,8 @@ class KernelProfile:
         """Algorithmic (flops, bytes) of one launch."""
         if name == "s3d_gemm_bf16":
             M, N, K, batch = a[3], a[4], a[5], a[21]
-            return 2.0 * M * N * K * batch, 2.0 * batch * (M * K + N * K + M * N)
+            out_b = (4.0 if a[11] else 2.0) + (4.0 if a[14] else 0.0) + (2.0 if a[17] else 0.0) + (2.0 if a[19] else 0.0)
+            return 2.0 * M * N * K * batch, batch * (2.0 * (M * K + N * K) + out_b * M * N)
         if name == "s3d_attn_fwd":
             B, H, N, dh = a[5], a[6], a[7], a[8]
             return 4.0 * B * H * N * N * dh, 2.0 * 4 * B * H * N * dh

@@ -69,10 +69,14 @@ def load_voxel_batch(sources, device="cuda", dtype=torch.uint8, fix_coords=True,
     V = metas[0][0][0]
     if any(m[0][0] != V for m in metas):
         raise ValueError("all models of a batch must have the same grid size")
-    offs = [0]
+    # every model's pairs start on a 16-byte boundary (vector loads in the scan); the padding is (value 0, count 0)
+    # pairs, i.e. empty runs
+    chunks, offs = [], [0]
     for m in metas:
-        offs.append(offs[-1] + len(m[3]))
-    host = torch.frombuffer(bytearray(b"".join(m[3] for m in metas)), dtype=torch.uint8).pin_memory()
+        pad = (-len(m[3])) % 16
+        chunks.append(m[3] + b"\0" * pad)
+        offs.append(offs[-1] + len(m[3]) + pad)
+    host = torch.frombuffer(bytearray(b"".join(chunks)), dtype=torch.uint8).pin_memory()
     payload = host.to(dev, non_blocking=True)
     offsets = torch.tensor(offs, dtype=torch.long).to(dev)
     grid, totals = L.binvox_expand(payload, offsets, V, out_dtype=dtype, fix_coords=fix_coords)

@@ -15,6 +15,10 @@ namespace {
 
 constexpr int kScanThreads = 1024;
 
+// 16 runs (32 payload bytes) per thread and iteration: serial prefix inside the thread, warp + block scan of the thread
+// totals, one carry per iteration -> 16384 runs per iteration of the 1024-thread CTA that owns a model.
+constexpr int kRunsPerThread = 16;
+
 __global__ void __launch_bounds__(kScanThreads) binvox_scan_kernel(const uint8_t* __restrict__ payload,
                                                                    const long long* __restrict__ offsets,
                                                                    unsigned* __restrict__ run_end,
@@ -27,11 +31,32 @@ __global__ void __launch_bounds__(kScanThreads) binvox_scan_kernel(const uint8_t
   const long long nruns = (offsets[b + 1] - offsets[b]) / 2;
   unsigned* out = run_end + run_offsets[b];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(pairs) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (long long base = 0; base < nruns; base += kScanThreads) {
-    const long long r = base + threadIdx.x;
-    unsigned v = r < nruns ? (unsigned)pairs[2 * r + 1] : 0u;
+  for (long long base = 0; base < nruns; base += (long long)kScanThreads * kRunsPerThread) {
+    const long long r0 = base + (long long)threadIdx.x * kRunsPerThread;
+    unsigned pre[kRunsPerThread];
+    unsigned run = 0;
+    if (vec_ok && r0 + kRunsPerThread <= nruns) {
+      const uint4 u0 = *reinterpret_cast<const uint4*>(pairs + 2 * r0);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(pairs + 2 * r0 + 16);
+      const unsigned w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // each 32-bit word holds two (value, count) pairs: counts are bytes 1 and 3
+        run += (w[j] >> 8) & 0xffu;
+        pre[2 * j] = run;
+        run += (w[j] >> 24) & 0xffu;
+        pre[2 * j + 1] = run;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kRunsPerThread; ++j) {
+        if (r0 + j < nruns) run += (unsigned)pairs[2 * (r0 + j) + 1];
+        pre[j] = run;
+      }
+    }
+    unsigned v = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
@@ -49,11 +74,19 @@ __global__ void __launch_bounds__(kScanThreads) binvox_scan_kernel(const uint8_t
       warp_sums[lane] = w;
     }
     __syncthreads();
-    const unsigned carry = carry_s;
-    const unsigned incl = v + (warp > 0 ? warp_sums[warp - 1] : 0u) + carry;
-    if (r < nruns) out[r] = incl;
+    const unsigned excl = (v - run) + (warp > 0 ? warp_sums[warp - 1] : 0u) + carry_s;
+    if (vec_ok && r0 + kRunsPerThread <= nruns) {
+#pragma unroll
+      for (int j = 0; j < kRunsPerThread; j += 4)
+        *reinterpret_cast<uint4*>(out + r0 + j) =
+            make_uint4(excl + pre[j], excl + pre[j + 1], excl + pre[j + 2], excl + pre[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kRunsPerThread; ++j)
+        if (r0 + j < nruns) out[r0 + j] = excl + pre[j];
+    }
     __syncthreads();
-    if (threadIdx.x == kScanThreads - 1) carry_s = incl;
+    if (threadIdx.x == kScanThreads - 1) carry_s = excl + run;
     __syncthreads();
   }
   if (threadIdx.x == 0) totals[b] = (long long)carry_s;
@@ -73,10 +106,24 @@ __global__ void __launch_bounds__(256) binvox_expand_kernel(const uint8_t* __res
   const unsigned slab = (unsigned)V * (unsigned)V;
   const unsigned lo = (unsigned)x * slab, hi = lo + slab;
   for (int i = threadIdx.x; i < (int)slab; i += blockDim.x) plane[i] = 0;  // voxels past a short stream read as empty
-  // first run whose end is > lo
+  // first run whose end is > lo: two parallel narrowing rounds (every thread probes one sample of the current range, the
+  // CTA keeps the last sample that is still <= lo) and a short serial tail: 3 dependent load latencies instead of ~19
+  __shared__ int range_lo;
   int first = 0;
   {
-    int l = 0, h = nruns;
+    int l = 0, h = nruns;  // invariant: ends[l - 1] <= lo (or l == 0), answer in [l, h]
+    for (int round = 0; round < 2 && h - l > 8; ++round) {
+      const int step = (h - l + (int)blockDim.x - 1) / (int)blockDim.x;
+      if (threadIdx.x == 0) range_lo = l;
+      __syncthreads();
+      const int probe = l + (int)threadIdx.x * step;  // ends[probe - 1] <= lo  =>  answer >= probe
+      if (probe > l && probe <= h && ends[probe - 1] <= lo) atomicMax(&range_lo, probe);
+      __syncthreads();
+      const int nl = range_lo;
+      h = min(h, nl + step);
+      l = nl;
+      __syncthreads();
+    }
     while (l < h) {
       const int m = (l + h) >> 1;
       if (ends[m] > lo) h = m; else l = m + 1;

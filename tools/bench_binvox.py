@@ -21,6 +21,7 @@ rng = np.random.default_rng(9)
 files = [BO.write(rng.random((V, V, V)) < 0.1) for _ in range(4)]
 files = [files[i % 4] for i in range(B)]
 payloads = [f[f.index(b"data\n") + 5:] for f in files]
+payloads = [p + b"\0" * ((-len(p)) % 16) for p in payloads]  # 16-byte aligned models (empty padding runs)
 offs = np.concatenate(([0], np.cumsum([len(p) for p in payloads])))
 dev = torch.device("cuda:0")
 host = torch.frombuffer(bytearray(b"".join(payloads)), dtype=torch.uint8).pin_memory()
@@ -40,7 +41,7 @@ for _ in range(10):
     torch.cuda.synchronize()
     ms.append(s.elapsed_time(e))
 t = sorted(ms)[len(ms) // 2]
-alg = payload.numel() + B * V ** 3 + payload.numel() // 2 * 4 * 2  # payload + grid + run_end written and re-read
+alg = payload.numel() + B * V ** 3  # algorithmic: RLE payload read once + uint8 grid written once
 t0 = time.perf_counter()
 for f in files[:4]:
     BO.read_as_3d_array(f)

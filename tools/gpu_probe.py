@@ -219,7 +219,9 @@ def g_ln():
     import torch.nn.functional as F
     from simple3d_former_b200 import _lib as L
     torch.manual_seed(4)
-    for (T, D) in [(1664, 384), (1000, 768), (333, 192), (50, 1024)]:
+    # the last four shapes are large enough for the bulk-async pipelined variants (T >= 148 * warps * 4 rows); D = 1024 with
+    # an fp32 dy does not fit their shared-memory ring and must fall back to the register-resident kernel
+    for (T, D) in [(1664, 384), (1000, 768), (333, 192), (50, 1024), (20000, 768), (12001, 192), (9500, 384), (9600, 1024)]:
         x = torch.randn(T, D, device="cuda") * 2 + 0.5
         g = torch.randn(D, device="cuda")
         b = torch.randn(D, device="cuda")
@@ -240,13 +242,20 @@ def g_ln():
         report(f"ln bwd dbeta T{T} D{D}", rel_err(db, br.grad), 1e-4)
         dx, _, dg, db = L.layernorm_bwd(dy.bfloat16(), x, g, mean, rstd)
         report(f"ln bwd (bf16 dy) dx T{T} D{D}", rel_err(dx, xr.grad), 1e-2)
-    x = torch.randn(100, 768, device="cuda")
-    a = torch.randn(100, 768, device="cuda")
-    g = torch.ones(768, device="cuda")
-    b = torch.zeros(768, device="cuda")
-    _, y32, s, _, _ = L.layernorm_fwd(x, g, b, 1e-5, addend=a, want_sum=True, want_f32=True)
-    report("ln fwd fused add", rel_err(y32, F.layer_norm(x + a, (768,), g, b, 1e-5)), 1e-5)
-    report("ln fwd fused add sum", rel_err(s, x + a), 1e-6)
+    for T in (100, 11000):
+        x = torch.randn(T, 768, device="cuda")
+        a = torch.randn(T, 768, device="cuda")
+        g = torch.ones(768, device="cuda")
+        b = torch.zeros(768, device="cuda")
+        _, y32, s, _, _ = L.layernorm_fwd(x, g, b, 1e-5, addend=a, want_sum=True, want_f32=True)
+        report(f"ln fwd fused add T{T}", rel_err(y32, F.layer_norm(x + a, (768,), g, b, 1e-5)), 1e-5)
+        report(f"ln fwd fused add sum T{T}", rel_err(s, x + a), 1e-6)
+    for (T, C) in [(300, 768), (5000, 3072), (777, 100), (20000, 2304)]:  # 16-byte and 4-byte column-sum kernels
+        m = torch.randn(T, C, device="cuda").bfloat16()
+        report(f"colsum T{T} C{C}", rel_err(L.colsum(m), m.float().sum(0)), 1e-4)
+        acc = torch.ones(C, device="cuda")
+        L.colsum(m, out=acc, accumulate=True)
+        report(f"colsum accumulate T{T} C{C}", rel_err(acc, m.float().sum(0) + 1), 1e-4)
 
 
 def _attn_ref(q, k, v, scale):
