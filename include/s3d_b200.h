@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define S3D_ABI_VERSION 1
+#define S3D_ABI_VERSION 2
 
 enum {
   S3D_OK = 0,
@@ -78,14 +78,21 @@ int s3d_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const floa
  * group_embed layer). q/k/v/out addressed by element strides (batch, head, row) so both [B,N,3,H,dh] and the
  * sequence-first [S,Nb,3E] layouts are read in place. head_dim in {64,192,256}. lse [B,H,N] f32 is written by fwd and
  * read by bwd; delta [B,H,N] f32 is scratch for bwd. dq/dk/dv use the q/k/v strides, dout uses the out strides.
+ * Attention-probability dropout (nn.MultiheadAttention(dropout=p) inside nn.TransformerEncoderLayer, reference
+ * vit_3d_2d_pretrain.py:381, active in train()): dropout_seed = DEVICE pointer to a uint32 seed (NULL or dropout_p == 0
+ * = off), dropout_site = stream id; out = ((P o mask) / (1 - p)) V with the softmax normaliser taken over the full row;
+ * the mask is a counter-based hash of (seed, site, (b*H + h)*N + query, key) that bwd regenerates (tcgen05 kernels:
+ * head_dim 64 / 192 only).
  * ------------------------------------------------------------------------------------------------------------- */
 int s3d_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int head_dim,
                  int64_t qkv_batch_stride, int64_t qkv_head_stride, int64_t qkv_row_stride, int64_t o_batch_stride,
-                 int64_t o_head_stride, int64_t o_row_stride, float scale, void* stream);
+                 int64_t o_head_stride, int64_t o_row_stride, float scale, const uint32_t* dropout_seed,
+                 uint32_t dropout_site, float dropout_p, void* stream);
 int s3d_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                  float* delta, void* dq, void* dk, void* dv, int B, int H, int N, int head_dim,
                  int64_t qkv_batch_stride, int64_t qkv_head_stride, int64_t qkv_row_stride, int64_t o_batch_stride,
-                 int64_t o_head_stride, int64_t o_row_stride, float scale, void* stream);
+                 int64_t o_head_stride, int64_t o_row_stride, float scale, const uint32_t* dropout_seed,
+                 uint32_t dropout_site, float dropout_p, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Elementwise / data-movement helpers of the path
@@ -121,6 +128,14 @@ int s3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  *   s3d_gather_rows  : index_points (:39-50): out[b,m,:] = points[b, idx[b,m], :], points f32 [B,N,C], idx int64 [B,M].
  *   s3d_scatter_add_rows: its backward (grad_points zeroed, then accumulated).
  * ------------------------------------------------------------------------------------------------------------- */
+/* Element-wise dropout of the group_embed layer (dropout1 / dropout / dropout2 of nn.TransformerEncoderLayer), same
+ * counter-based mask keyed by (device seed, site, row, column); rows x cols row-major, cols % 4 == 0:
+ *   s3d_dropout_add_f32 : out = residual + mask o x / (1 - p)   (residual may be NULL)
+ *   s3d_dropout_bf16    : out = mask o x / (1 - p)              (bf16, in place allowed) */
+int s3d_dropout_add_f32(const float* x, const float* residual, float* out, int64_t rows, int cols,
+                        const uint32_t* seed, uint32_t site, float p, void* stream);
+int s3d_dropout_bf16(const void* x, void* out, int64_t rows, int cols, const uint32_t* seed, uint32_t site, float p,
+                     void* stream);
 int s3d_knn(const float* xyz, const float* query, int64_t* idx, float* dist, int B, int N, int S, int K, void* stream);
 int s3d_ball_query(const float* xyz, const float* query, int64_t* idx, int B, int N, int S, float radius_sq,
                    int nsample, void* stream);

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_void_p
 
 import torch
 
@@ -27,9 +27,11 @@ SIGNATURES = {
     "s3d_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "s3d_layernorm_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "s3d_attn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64,
-                             c_int64, c_int64, c_float, _P]),
+                             c_int64, c_int64, c_float, _P, c_uint32, c_float, _P]),
     "s3d_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64,
-                             c_int64, c_int64, c_int64, c_int64, c_float, _P]),
+                             c_int64, c_int64, c_int64, c_int64, c_float, _P, c_uint32, c_float, _P]),
+    "s3d_dropout_add_f32": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_uint32, c_float, _P]),
+    "s3d_dropout_bf16": (c_int, [_P, _P, c_int64, c_int, _P, c_uint32, c_float, _P]),
     "s3d_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
     "s3d_transpose_to_bf16": (c_int, [_P, c_int, _P, c_int, c_int, c_int64, c_int64, _P]),
     "s3d_colsum_bf16": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, _P]),
@@ -90,7 +92,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
-        if _lib.s3d_abi_version() != 1:
+        if _lib.s3d_abi_version() != 2:
             raise RuntimeError("libs3d_b200.so ABI version mismatch")
     return _lib
 
@@ -202,15 +204,37 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dres=None, want_bf16=False, dgamm
     return dx, dx16, dgamma, dbeta
 
 
-def attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale):
+def attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale, drop_seed=None, drop_site=0, drop_p=0.0):
+    """drop_seed: int32 CUDA tensor [1] (device-resident seed) enabling attention-probability dropout with rate drop_p."""
     call("s3d_attn_fwd", ptr(q) if hasattr(q, "data_ptr") else q, ptr(k) if hasattr(k, "data_ptr") else k,
          ptr(v) if hasattr(v, "data_ptr") else v, ptr(out), ptr(lse), B, H, N, dh, qs[0], qs[1], qs[2], os_[0], os_[1],
-         os_[2], float(scale), stream())
+         os_[2], float(scale), ptr(drop_seed), int(drop_site), float(drop_p), stream())
 
 
-def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, B, H, N, dh, qs, os_, scale):
+def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, B, H, N, dh, qs, os_, scale, drop_seed=None, drop_site=0,
+             drop_p=0.0):
     call("s3d_attn_bwd", q, k, v, ptr(out), ptr(dout), ptr(lse), ptr(delta), dq, dk, dv, B, H, N, dh, qs[0], qs[1],
-         qs[2], os_[0], os_[1], os_[2], float(scale), stream())
+         qs[2], os_[0], os_[1], os_[2], float(scale), ptr(drop_seed), int(drop_site), float(drop_p), stream())
+
+
+def dropout_add(x, residual, seed, site, p):
+    """out = residual + mask * x / (1 - p) on fp32 [rows, cols] (counter-based mask keyed by the device seed)."""
+    _need_cuda(x, seed)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == x.shape
+    out = torch.empty_like(x)
+    call("s3d_dropout_add_f32", ptr(x), ptr(residual), ptr(out), x.shape[0], x.shape[1], ptr(seed), int(site), float(p),
+         stream())
+    return out
+
+
+def dropout_bf16(x, seed, site, p, inplace=False):
+    _need_cuda(x, seed)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 2
+    out = x if inplace else torch.empty_like(x)
+    call("s3d_dropout_bf16", ptr(x), ptr(out), x.shape[0], x.shape[1], ptr(seed), int(site), float(p), stream())
+    return out
 
 
 def cast_bf16(x, out=None):

@@ -98,22 +98,37 @@ static s3d::AttnParams make_attn(const void* q, const void* k, const void* v, in
   return p;
 }
 
+static int set_dropout(s3d::AttnParams& p, const uint32_t* seed, uint32_t site, float prob) {
+  if (seed == nullptr || prob <= 0.f) return 0;
+  if (prob >= 1.f) return s3d::S3D_ERR_BAD_SHAPE;
+  const float t = prob * 65536.0f + 0.5f;
+  p.drop_seed = seed;
+  p.drop_site = site;
+  p.drop_thresh16 = t >= 65535.f ? 65535u : (uint32_t)t;
+  p.drop_scale = 1.0f / (1.0f - (float)p.drop_thresh16 / 65536.0f);
+  return 0;
+}
+
 int s3d_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int head_dim,
                  int64_t qkv_batch_stride, int64_t qkv_head_stride, int64_t qkv_row_stride, int64_t o_batch_stride,
-                 int64_t o_head_stride, int64_t o_row_stride, float scale, void* stream) {
+                 int64_t o_head_stride, int64_t o_row_stride, float scale, const uint32_t* dropout_seed,
+                 uint32_t dropout_site, float dropout_p, void* stream) {
   s3d::AttnParams p = make_attn(q, k, v, B, H, N, qkv_batch_stride, qkv_head_stride, qkv_row_stride, o_batch_stride,
                                 o_head_stride, o_row_stride, scale);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
+  if (int rc = set_dropout(p, dropout_seed, dropout_site, dropout_p)) return rc;
   return s3d::attn_fwd(p, head_dim, as_stream(stream));
 }
 
 int s3d_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                  float* delta, void* dq, void* dk, void* dv, int B, int H, int N, int head_dim,
                  int64_t qkv_batch_stride, int64_t qkv_head_stride, int64_t qkv_row_stride, int64_t o_batch_stride,
-                 int64_t o_head_stride, int64_t o_row_stride, float scale, void* stream) {
+                 int64_t o_head_stride, int64_t o_row_stride, float scale, const uint32_t* dropout_seed,
+                 uint32_t dropout_site, float dropout_p, void* stream) {
   s3d::AttnParams p = make_attn(q, k, v, B, H, N, qkv_batch_stride, qkv_head_stride, qkv_row_stride, o_batch_stride,
                                 o_head_stride, o_row_stride, scale);
+  if (int rc = set_dropout(p, dropout_seed, dropout_site, dropout_p)) return rc;
   p.o = reinterpret_cast<const __nv_bfloat16*>(out);
   p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
   p.lse = const_cast<float*>(lse);
@@ -162,6 +177,14 @@ int s3d_ball_query(const float* xyz, const float* query, int64_t* idx, int B, in
 int s3d_fps(const float* xyz, const int64_t* start, int64_t* idx, int B, int N, int npoint, void* stream) {
   return s3d::fps(xyz, reinterpret_cast<const long long*>(start), reinterpret_cast<long long*>(idx), B, N, npoint,
                   as_stream(stream));
+}
+int s3d_dropout_add_f32(const float* x, const float* residual, float* out, int64_t rows, int cols,
+                        const uint32_t* seed, uint32_t site, float p, void* stream) {
+  return s3d::dropout_add_f32(x, residual, out, rows, cols, seed, site, p, as_stream(stream));
+}
+int s3d_dropout_bf16(const void* x, void* out, int64_t rows, int cols, const uint32_t* seed, uint32_t site, float p,
+                     void* stream) {
+  return s3d::dropout_bf16(x, out, rows, cols, seed, site, p, as_stream(stream));
 }
 int s3d_gather_rows(const float* points, const int64_t* idx, float* out, int B, int N, int M, int C, void* stream) {
   return s3d::gather_rows(points, reinterpret_cast<const long long*>(idx), out, B, N, M, C, as_stream(stream));

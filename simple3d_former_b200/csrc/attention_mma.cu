@@ -846,6 +846,10 @@ int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream) {
   if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.out == nullptr) return S3D_ERR_NULL;
   // long sequences run on the tcgen05 / TMEM flash kernel; everything else on the warp-level mma.sync kernels
   static const bool tc_enabled = []() { const char* v = getenv("S3D_ATTN_TC"); return v == nullptr || v[0] != '0'; }();
+  if (p.drop_seed != nullptr) {  // attention-probability dropout lives in the tcgen05 kernels only
+    if (DH != 192 && DH != 64) return S3D_ERR_UNSUPPORTED;
+    return attn_fwd_tc(p, DH, stream);
+  }
   if (tc_enabled && (DH == 192 || DH == 64) && p.N >= 512) {
     const int rc_tc = attn_fwd_tc(p, DH, stream);
     if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;
@@ -864,6 +868,10 @@ int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream) {
       p.dk == nullptr || p.dv == nullptr || p.lse == nullptr || p.delta == nullptr)
     return S3D_ERR_NULL;
   static const bool tc_enabled = []() { const char* v = getenv("S3D_ATTN_TC"); return v == nullptr || v[0] != '0'; }();
+  if (p.drop_seed != nullptr) {
+    if (DH != 192 && DH != 64) return S3D_ERR_UNSUPPORTED;
+    return attn_bwd_tc(p, DH, stream);
+  }
   if (tc_enabled && (DH == 192 || DH == 64) && p.N >= 512) {
     const int rc_tc = attn_bwd_tc(p, DH, stream);
     if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;

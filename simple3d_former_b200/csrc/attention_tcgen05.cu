@@ -39,6 +39,9 @@ struct FaParams {
   int col_q, col_k, col_v;  // column of head 0 for q / k / v
   long long o_bs, o_hs, o_rs;
   float scale;
+  const uint32_t* drop_seed;  // attention-probability dropout: device seed (nullptr = off)
+  uint32_t drop_site, drop_thresh16;
+  float drop_scale;           // 1 / (1 - p)
 };
 
 template <int DH>
@@ -184,6 +187,12 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     uint8_t* prow = sP + t * Cfg::kPBytes + r * 128;
     const float c = p.scale * kFaLog2e;
     float m_ref = -INFINITY, l = 0.f;
+    // dropout on the attention probabilities (MultiheadAttention(dropout=p) inside nn.TransformerEncoderLayer): P V uses
+    // P o mask, the softmax normaliser the full row sum; mask element = (row (b*H + h)*N + query, column key)
+    const bool drop = p.drop_seed != nullptr;
+    const uint32_t drop_row = drop ? (drop_site_seed(*p.drop_seed, p.drop_site) ^
+                                      (((uint32_t)(b * p.H + h) * (uint32_t)p.N + (uint32_t)(q0 + t * kFaBM + r)) * kDropRowMul))
+                                   : 0u;
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
@@ -238,6 +247,15 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
           e[i] = (i & 1) ? poly_exp2(xs) : fast_exp2(xs);  // half on MUFU, half on the FMA pipe
           sum4[i & 3] += e[i];
         }
+        if (drop) {
+          const uint32_t cp0 = (uint32_t)(key0 + ch * 8) >> 1;
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const uint32_t hsh = drop_mix(drop_row ^ ((cp0 + (i >> 1)) * kDropColMul));
+            if ((hsh & 0xffffu) < p.drop_thresh16) e[i] = 0.f;
+            if ((hsh >> 16) < p.drop_thresh16) e[i + 1] = 0.f;
+          }
+        }
         uint4 u;
         u.x = pack_bf16x2(e[0], e[1]);
         u.y = pack_bf16x2(e[2], e[3]);
@@ -255,7 +273,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     mbar_wait(&o_full[t], 0);
     tc_fence_after();
     const int row = q0 + t * kFaBM + r;
-    const float inv = 1.0f / l;
+    const float inv = (drop ? p.drop_scale : 1.0f) / l;
     __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)row * p.o_rs;
 #pragma unroll 1
     for (int cc = 0; cc < DH; cc += 32) {
@@ -328,6 +346,10 @@ static int fa_fwd_launch(const AttnParams& a, cudaStream_t stream) {
   p.o_hs = a.o_hs;
   p.o_rs = a.o_rs;
   p.scale = a.scale;
+  p.drop_seed = a.drop_seed;
+  p.drop_site = a.drop_site;
+  p.drop_thresh16 = a.drop_thresh16;
+  p.drop_scale = a.drop_scale;
   if ((a.o_rs % 8) || (a.o_hs % 8) || (a.o_bs % 8) || (reinterpret_cast<uintptr_t>(a.out) & 15)) return S3D_ERR_ALIGNMENT;
   auto kern = fa_fwd_tc_kernel<DH>;
   static bool attr_set = false;
@@ -362,6 +384,9 @@ struct FaBwdParams {
   long long o_row_bs, o_col_bs;  // dout 2-D view
   long long qkv_bs, qkv_hs, qkv_rs;
   float scale;
+  const uint32_t* drop_seed;  // attention-probability dropout (same mask as the forward kernel)
+  uint32_t drop_site, drop_thresh16;
+  float drop_scale;
 };
 
 constexpr int kFaBwdThreads = 320;
@@ -525,6 +550,10 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
     const float lse2 = row < p.N ? p.lse[bh * p.N + row] * kFaLog2e : INFINITY;
     const float del = row < p.N ? p.delta[bh * p.N + row] : 0.f;
     const float c = p.scale * kFaLog2e;
+    const bool drop = p.drop_seed != nullptr;  // dP = mask o (dO V^T) / (1 - p): regenerate the forward mask
+    const uint32_t drop_row = drop ? (drop_site_seed(*p.drop_seed, p.drop_site) ^
+                                      (((uint32_t)bh * (uint32_t)p.N + (uint32_t)row) * kDropRowMul))
+                                   : 0u;
     for (int j = 0; j < nkv; ++j) {
       const int u = j & 1;
       mbar_wait(&sp_full[u], (j >> 1) & 1);
@@ -540,7 +569,12 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
       for (int i = 0; i < 32; ++i) {
         const float x0 = fmaf(__uint_as_float(a0[i]), c, -lse2);
         const float p0 = (key0 + i < p.N) ? ((i & 1) ? poly_exp2(x0) : fast_exp2(x0)) : 0.f;  // MUFU / FMA pipes alternate
-        e[i] = p0 * (__uint_as_float(d0[i]) - del);
+        float dpv = __uint_as_float(d0[i]);
+        if (drop) {
+          const uint32_t hsh = drop_mix(drop_row ^ (((uint32_t)(key0 + i) >> 1) * kDropColMul));  // CSE'd per pair
+          dpv = (((i & 1) ? (hsh >> 16) : (hsh & 0xffffu)) >= p.drop_thresh16) ? dpv * p.drop_scale : 0.f;
+        }
+        e[i] = p0 * (dpv - del);
       }
       store_half_row_bf16_sw128(sdS + u * Cfg::kSBytes + r * 128, r, half, e);
       fence_proxy_async_smem();
@@ -725,6 +759,9 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const long long bh = (long long)b * p.H + h;
     const float c = p.scale * kFaLog2e;
+    const bool drop = p.drop_seed != nullptr;  // this thread owns key column krow of the mask; queries vary along i
+    const uint32_t drop_col = drop ? (drop_site_seed(*p.drop_seed, p.drop_site) ^ (((uint32_t)krow >> 1) * kDropColMul)) : 0u;
+    const bool drop_hi = (krow & 1) != 0;
     for (int j = 0; j < nq; ++j) {
       const int u = j & 1;
       if (tid < 128) {  // stage lse / delta of this query block (padded queries: lse = +inf -> P = 0)
@@ -751,7 +788,29 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
         const float x0 = fmaf(__uint_as_float(a0[i]), c, -lrow[i]);
         const float p0 = (i & 1) ? poly_exp2(x0) : fast_exp2(x0);  // MUFU / FMA pipes alternate
         pt[i] = p0;
-        ds[i] = p0 * (__uint_as_float(d0[i]) - drow[i]);
+        ds[i] = __uint_as_float(d0[i]);
+      }
+      if (drop) {
+        // Lanes 2m and 2m+1 own keys of the same column pair, i.e. they need the SAME 32-bit hash for a given query and
+        // take different halves of it: each computes the hash for every other query and gets the rest from its partner.
+        const uint32_t q_base = (uint32_t)bh * (uint32_t)p.N + (uint32_t)(j * 64 + half * 32);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const uint32_t mine = drop_mix(drop_col ^ ((q_base + (uint32_t)(i + (lane & 1))) * kDropRowMul));
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          const uint32_t h0 = (lane & 1) ? other : mine, h1 = (lane & 1) ? mine : other;  // queries i, i + 1
+          const bool k0 = (drop_hi ? (h0 >> 16) : (h0 & 0xffffu)) >= p.drop_thresh16;
+          const bool k1 = (drop_hi ? (h1 >> 16) : (h1 & 0xffffu)) >= p.drop_thresh16;
+          // dV = (P o mask / (1 - p))^T dO;  dP = mask o (dO V^T) / (1 - p)
+          const float pa = pt[i], pb = pt[i + 1];
+          pt[i] = k0 ? pa * p.drop_scale : 0.f;
+          pt[i + 1] = k1 ? pb * p.drop_scale : 0.f;
+          ds[i] = pa * ((k0 ? ds[i] * p.drop_scale : 0.f) - drow[i]);
+          ds[i + 1] = pb * ((k1 ? ds[i + 1] * p.drop_scale : 0.f) - drow[i + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ds[i] = pt[i] * (ds[i] - drow[i]);
       }
       if (j > 0) mbar_wait(pds_free, (j - 1) & 1);  // dV / dK MMAs of block j-1 no longer read the smem tiles
       store_half_row_bf16_sw128(sPT + r * 128, r, half, pt);
@@ -865,6 +924,10 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
   p.qkv_hs = a.qkv_hs;
   p.qkv_rs = a.qkv_rs;
   p.scale = a.scale;
+  p.drop_seed = a.drop_seed;
+  p.drop_site = a.drop_site;
+  p.drop_thresh16 = a.drop_thresh16;
+  p.drop_scale = a.drop_scale;
   {
     const long long rows = (long long)a.B * a.H * a.N;
     fa_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a.o, a.dout, a.delta, a.B, a.H, a.N, DH, a.o_bs, a.o_hs, a.o_rs);

@@ -93,19 +93,41 @@ __global__ void __launch_bounds__(kScanThreads) binvox_scan_kernel(const uint8_t
 }
 
 template <typename TOut>
+__device__ __forceinline__ void store4(TOut* dst, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3);
+template <>
+__device__ __forceinline__ void store4<uint8_t>(uint8_t* dst, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+  *reinterpret_cast<uint32_t*>(dst) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+template <>
+__device__ __forceinline__ void store4<int>(int* dst, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+  *reinterpret_cast<int4*>(dst) = make_int4((int)b0, (int)b1, (int)b2, (int)b3);
+}
+template <>
+__device__ __forceinline__ void store4<float>(float* dst, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+  *reinterpret_cast<float4*>(dst) = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
+}
+
+// plane row stride: odd, so that a warp reading one byte per row (the z <-> y transpose) touches 32 different banks
+__host__ __device__ __forceinline__ int plane_stride(int V) { return V | 1; }
+
+template <typename TOut>
 __global__ void __launch_bounds__(256) binvox_expand_kernel(const uint8_t* __restrict__ payload,
                                                             const long long* __restrict__ offsets,
                                                             const unsigned* __restrict__ run_end,
                                                             const long long* __restrict__ run_offsets,
                                                             TOut* __restrict__ out, int V, int fix_coords) {
-  extern __shared__ uint8_t plane[];  // [V][V] in stream order (z-major, y fastest)
+  extern __shared__ __align__(16) uint8_t plane[];  // [V][PS] in stream order (row = z, column = y), PS = V | 1
   const int b = blockIdx.y, x = blockIdx.x;
+  const int PS = plane_stride(V);
   const uint8_t* pairs = payload + offsets[b];
   const unsigned* ends = run_end + run_offsets[b];
   const int nruns = (int)((offsets[b + 1] - offsets[b]) / 2);
   const unsigned slab = (unsigned)V * (unsigned)V;
   const unsigned lo = (unsigned)x * slab, hi = lo + slab;
-  for (int i = threadIdx.x; i < (int)slab; i += blockDim.x) plane[i] = 0;  // voxels past a short stream read as empty
+  {  // voxels past a short stream read as empty
+    const int n16 = (V * PS + 15) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) reinterpret_cast<uint4*>(plane)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   // first run whose end is > lo: two parallel narrowing rounds (every thread probes one sample of the current range, the
   // CTA keeps the last sample that is still <= lo) and a short serial tail: 3 dependent load latencies instead of ~19
   __shared__ int range_lo;
@@ -133,21 +155,40 @@ __global__ void __launch_bounds__(256) binvox_expand_kernel(const uint8_t* __res
   __syncthreads();
   for (int r = first + threadIdx.x; r < nruns; r += blockDim.x) {
     const unsigned e = ends[r];
-    const unsigned cnt = pairs[2 * r + 1];
-    const unsigned s = e - cnt;
+    const uint2 pr = make_uint2(pairs[2 * r], pairs[2 * r + 1]);
+    const unsigned s = e - pr.y;
     if (s >= hi) break;  // runs are ordered: everything this thread would see later is past the slab too
-    if (pairs[2 * r] != 0) {
-      const unsigned a = s > lo ? s : lo, z = e < hi ? e : hi;
-      for (unsigned i = a; i < z; ++i) plane[i - lo] = 1;
+    if (pr.x != 0) {
+      const unsigned a = (s > lo ? s : lo) - lo, z = (e < hi ? e : hi) - lo;
+      unsigned row = a / (unsigned)V, col = a - row * (unsigned)V;
+      for (unsigned i = a; i < z; ++i) {
+        plane[row * PS + col] = 1;
+        if (++col == (unsigned)V) { col = 0; ++row; }
+      }
     }
   }
   __syncthreads();
   // write out: out[b][x][j][k]; fix_coords: (j, k) = (y, z) <- plane[z][y]; otherwise the stream order (z, y) is kept
   TOut* o = out + ((size_t)b * V + x) * slab;
-  for (int i = threadIdx.x; i < (int)slab; i += blockDim.x) {
-    const int j = i / V, k = i % V;
-    const uint8_t v = fix_coords ? plane[k * V + j] : plane[i];
-    o[i] = (TOut)v;
+  if ((V & 3) == 0) {
+    const int vq = V >> 2;
+    for (int g = threadIdx.x; g < (int)(slab >> 2); g += blockDim.x) {
+      const int j = g / vq, k = (g - j * vq) << 2;
+      uint32_t v0, v1, v2, v3;
+      if (fix_coords) {
+        const uint8_t* src = plane + k * PS + j;
+        v0 = src[0]; v1 = src[PS]; v2 = src[2 * PS]; v3 = src[3 * PS];
+      } else {
+        const uint8_t* src = plane + j * PS + k;
+        v0 = src[0]; v1 = src[1]; v2 = src[2]; v3 = src[3];
+      }
+      store4<TOut>(o + (size_t)g * 4, v0, v1, v2, v3);
+    }
+  } else {
+    for (int i = threadIdx.x; i < (int)slab; i += blockDim.x) {
+      const int j = i / V, k = i - j * V;
+      o[i] = (TOut)(fix_coords ? plane[k * PS + j] : plane[j * PS + k]);
+    }
   }
 }
 
@@ -176,7 +217,7 @@ int s3d_binvox_expand(const uint8_t* payload, const int64_t* offsets, const uint
   if (V > 384 || B > 65535) return S3D_ERR_UNSUPPORTED;  // V x V byte plane in shared memory
   if (payload == nullptr || offsets == nullptr || run_end == nullptr || run_offsets == nullptr || out == nullptr)
     return S3D_ERR_NULL;
-  const size_t smem = (size_t)V * V;
+  const size_t smem = (((size_t)V * plane_stride(V) + 15) / 16) * 16;
   const dim3 grid(V, B);
   auto st = reinterpret_cast<cudaStream_t>(stream);
   auto off = reinterpret_cast<const long long*>(offsets);

@@ -324,6 +324,30 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(p, u, 0.5f);
 }
 
+// Counter-based dropout mask (nn.Dropout / attention-probability dropout of the group_embed layer, reference
+// vit_3d_2d_pretrain.py:381: nn.TransformerEncoderLayer's default p = 0.1, active in train()). Element (row, col) of a
+// site gets 16 pseudo-random bits; one 32-bit hash serves the column pair (col & ~1, col | 1). keep <=> bits >= thresh,
+// thresh = round(p * 65536). Stateless: backward regenerates the forward mask from (seed, row, col).
+constexpr uint32_t kDropRowMul = 0x9E3779B1u, kDropColMul = 0x85EBCA77u, kDropSiteMul = 0x632BE5ABu;
+__host__ __device__ __forceinline__ uint32_t drop_mix(uint32_t x) {
+  x *= 0x2C1B3C6Du;
+  x ^= x >> 15;
+  x *= 0x297A2D39u;
+  x ^= x >> 15;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_site_seed(uint32_t seed, uint32_t site) {
+  return drop_mix(seed ^ (site * kDropSiteMul) ^ 0xA511E9B3u);
+}
+// hash of the pair; caller picks the half: low 16 bits for even columns, high 16 bits for odd ones
+__host__ __device__ __forceinline__ uint32_t drop_pair(uint32_t site_seed, uint32_t row, uint32_t col_pair) {
+  return drop_mix(site_seed ^ (row * kDropRowMul) ^ (col_pair * kDropColMul));
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t site_seed, uint32_t row, uint32_t col, uint32_t thresh16) {
+  const uint32_t h = drop_pair(site_seed, row, col >> 1);
+  return ((col & 1u) ? (h >> 16) : (h & 0xffffu)) >= thresh16;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

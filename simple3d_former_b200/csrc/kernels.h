@@ -50,6 +50,10 @@ int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t strea
 int transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int C, long long ld_in, long long ld_out,
                       cudaStream_t stream);
 int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accumulate, cudaStream_t stream);
+int dropout_add_f32(const float* x, const float* res, float* out, long long rows, int cols, const uint32_t* seed,
+                    unsigned site, float p, cudaStream_t stream);
+int dropout_bf16(const void* x, void* out, long long rows, int cols, const uint32_t* seed, unsigned site, float p,
+                 cudaStream_t stream);
 int voxel_patch_gather(const void* x, int in_dtype, void* P, int B, int V, int cell, int patch, int Kpad, int zsum,
                        cudaStream_t stream);
 int sgd_momentum_step(float* p, const float* g, float* buf, void* shadow_bf16, long long n, float lr, float momentum,
@@ -70,6 +74,11 @@ struct AttnParams {
   long long o_bs, o_hs, o_rs;
   int B, H, N;
   float scale;
+  // attention-probability dropout (tcgen05 kernels only): device seed (nullptr = off), site id, threshold, 1 / (1 - p)
+  const uint32_t* drop_seed;
+  uint32_t drop_site;
+  uint32_t drop_thresh16;
+  float drop_scale;
 };
 int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream);
 int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream);

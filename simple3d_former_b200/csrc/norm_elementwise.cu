@@ -785,6 +785,83 @@ int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accu
 }
 
 // ------------------------------------------------------------------------------------------------
+// Element-wise dropout of the group_embed layer (nn.TransformerEncoderLayer dropout1 / dropout / dropout2):
+//   dropout_add : out = residual + keep(row, col) * x / (1 - p)      (fp32 residual stream)
+//   dropout_bf16: out = keep(row, col) * x / (1 - p)                 (bf16 GEMM operand; in place allowed)
+// The mask is the counter-based hash of common.cuh keyed by a device-resident seed (CUDA-graph replays see a new seed).
+// ------------------------------------------------------------------------------------------------
+__global__ void dropout_add_f32_kernel(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ out,
+                                       long long n4, int cols, const uint32_t* __restrict__ seed, uint32_t site,
+                                       uint32_t thresh16, float scale) {
+  const uint32_t ss = drop_site_seed(*seed, site);
+  const int c4 = cols >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t row = (uint32_t)(i / c4), col = (uint32_t)(i % c4) * 4u;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 o = res != nullptr ? reinterpret_cast<const float4*>(res)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t h0 = drop_pair(ss, row, col >> 1), h1 = drop_pair(ss, row, (col >> 1) + 1);
+    if ((h0 & 0xffffu) >= thresh16) o.x += v.x * scale;
+    if ((h0 >> 16) >= thresh16) o.y += v.y * scale;
+    if ((h1 & 0xffffu) >= thresh16) o.z += v.z * scale;
+    if ((h1 >> 16) >= thresh16) o.w += v.w * scale;
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+__global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n4,
+                                    int cols, const uint32_t* __restrict__ seed, uint32_t site, uint32_t thresh16,
+                                    float scale) {
+  const uint32_t ss = drop_site_seed(*seed, site);
+  const int c4 = cols >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t row = (uint32_t)(i / c4), col = (uint32_t)(i % c4) * 4u;
+    const uint2 u = reinterpret_cast<const uint2*>(x)[i];
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    const uint32_t h0 = drop_pair(ss, row, col >> 1), h1 = drop_pair(ss, row, (col >> 1) + 1);
+    uint2 w;
+    w.x = pack_bf16x2((h0 & 0xffffu) >= thresh16 ? a.x * scale : 0.f, (h0 >> 16) >= thresh16 ? a.y * scale : 0.f);
+    w.y = pack_bf16x2((h1 & 0xffffu) >= thresh16 ? b.x * scale : 0.f, (h1 >> 16) >= thresh16 ? b.y * scale : 0.f);
+    reinterpret_cast<uint2*>(out)[i] = w;
+  }
+}
+
+static inline uint32_t drop_thresh16(float p) {
+  const float t = p * 65536.0f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);
+}
+
+int dropout_add_f32(const float* x, const float* res, float* out, long long rows, int cols, const uint32_t* seed,
+                    unsigned site, float p, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0 || cols % 4 != 0 || p < 0.f || p >= 1.f) return S3D_ERR_BAD_SHAPE;
+  if (x == nullptr || out == nullptr || seed == nullptr) return S3D_ERR_NULL;
+  const uint32_t th = drop_thresh16(p);
+  const long long n4 = rows * cols / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dropout_add_f32_kernel<<<(int)blocks, 256, 0, stream>>>(x, res, out, n4, cols, seed, site, th,
+                                                          1.0f / (1.0f - (float)th / 65536.0f));
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+int dropout_bf16(const void* x, void* out, long long rows, int cols, const uint32_t* seed, unsigned site, float p,
+                 cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0 || cols % 4 != 0 || p < 0.f || p >= 1.f) return S3D_ERR_BAD_SHAPE;
+  if (x == nullptr || out == nullptr || seed == nullptr) return S3D_ERR_NULL;
+  const uint32_t th = drop_thresh16(p);
+  const long long n4 = rows * cols / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dropout_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                       reinterpret_cast<__nv_bfloat16*>(out), n4, cols, seed, site, th,
+                                                       1.0f / (1.0f - (float)th / 65536.0f));
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Voxel patch gather: x [B,1,V,V,V] fp32 -> P bf16 [B*p*p*(zsum?1:p), Kpad], K = c^3 (zero padded to Kpad).
 // Row order is (b, px, py, pz), column order (dx, dy, dz) = Conv3d weight [D,1,c,c,c] flattened, so the patchify
 // conv (embed_layer_3d_modality.py:22-24) is P @ W^T. With zsum=1 the pz patches of a column are summed first

@@ -341,12 +341,22 @@ def _padded_conv_weight(weight, K, kpad):
 # group_embed: nn.TransformerEncoderLayer (post-norm, ReLU, sequence-first) with a flash attention core
 # ----------------------------------------------------------------------------------------------------------------
 class GroupEmbedFn(torch.autograd.Function):
+    """nn.TransformerEncoderLayer (post-norm, ReLU, sequence-first) as one autograd node.
+
+    Dropout (p = 0.1 by default in the reference, vit_3d_2d_pretrain.py:381) is active when `drop_p > 0` and a device
+    seed is given (the module does that in train()): site 1 = attention probabilities (inside the flash kernels),
+    site 2 = dropout1 on the attention block output, site 3 = dropout inside the FFN (after ReLU), site 4 = dropout2 on
+    the FFN output. Masks are counter-based hashes of (seed, site, row, column), regenerated in backward."""
+
     @staticmethod
-    def forward(ctx, x, in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1w, n1b, n2w, n2b, nhead, eps):
+    def forward(ctx, x, in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1w, n1b, n2w, n2b, nhead, eps, drop_p=0.0,
+                drop_seed=None):
         S, Nb, E = x.shape
         T = S * Nb
         dh = E // nhead
         scale = dh ** -0.5
+        drop = drop_seed is not None and drop_p > 0.0
+        seed = drop_seed.clone() if drop else None  # backward must see the value this forward used
         x2 = x.contiguous().view(T, E)
         x16 = L.cast_bf16(x2)
         qkv = L.gemm(x16, shadow(in_w), bias=in_b)  # [S*Nb, 3E], sequence-first
@@ -355,47 +365,64 @@ class GroupEmbedFn(torch.autograd.Function):
         qs = (3 * E, dh, Nb * 3 * E)
         os_ = (E, dh, Nb * E)
         base = qkv.data_ptr()
-        L.attn_fwd(base, base + 2 * E, base + 4 * E, o16, lse, Nb, nhead, S, dh, qs, os_, scale)
-        sa = L.gemm(o16, shadow(out_w), bias=out_b, residual=x2, out_dtype=torch.float32)  # x + attn(x)
+        L.attn_fwd(base, base + 2 * E, base + 4 * E, o16, lse, Nb, nhead, S, dh, qs, os_, scale, drop_seed=seed,
+                   drop_site=1, drop_p=drop_p if drop else 0.0)
+        if drop:
+            attn_out = L.gemm(o16, shadow(out_w), bias=out_b, out_dtype=torch.float32)
+            sa = L.dropout_add(attn_out, x2, seed, 2, drop_p)  # x + dropout1(attn(x))
+        else:
+            sa = L.gemm(o16, shadow(out_w), bias=out_b, residual=x2, out_dtype=torch.float32)  # x + attn(x)
         y1_16, y1, _, mean1, rstd1 = L.layernorm_fwd(sa, n1w, n1b, eps, want_f32=True)
         h16 = L.gemm(y1_16, shadow(l1_w), bias=l1_b, epilogue=L.EPI_RELU)
-        f = L.gemm(h16, shadow(l2_w), bias=l2_b, residual=y1, out_dtype=torch.float32)
+        if drop:
+            L.dropout_bf16(h16, seed, 3, drop_p, inplace=True)
+            ffn = L.gemm(h16, shadow(l2_w), bias=l2_b, out_dtype=torch.float32)
+            f = L.dropout_add(ffn, y1, seed, 4, drop_p)
+        else:
+            f = L.gemm(h16, shadow(l2_w), bias=l2_b, residual=y1, out_dtype=torch.float32)
         _, y2, _, mean2, rstd2 = L.layernorm_fwd(f, n2w, n2b, eps, want_bf16=False, want_f32=True)
         ctx.save_for_backward(x16, qkv, o16, lse, sa, mean1, rstd1, y1_16, h16, f, mean2, rstd2, in_w, out_w, l1_w, l2_w,
-                              n1w, n2w)
-        ctx.meta = (S, Nb, E, nhead, dh, scale, qs, os_)
+                              n1w, n2w, seed)
+        ctx.meta = (S, Nb, E, nhead, dh, scale, qs, os_, drop_p if drop else 0.0)
         ctx.refs = (in_b, out_b, l1_b, l2_b, n1b, n2b)
         return y2.view(S, Nb, E)
 
     @staticmethod
     def backward(ctx, dy):
         (x16, qkv, o16, lse, sa, mean1, rstd1, y1_16, h16, f, mean2, rstd2, in_w, out_w, l1_w, l2_w, n1w,
-         n2w) = ctx.saved_tensors
-        S, Nb, E, nhead, dh, scale, qs, os_ = ctx.meta
+         n2w, seed) = ctx.saved_tensors
+        S, Nb, E, nhead, dh, scale, qs, os_, drop_p = ctx.meta
+        drop = drop_p > 0.0
+        keep_scale = 1.0
+        if drop:
+            keep_scale = 1.0 / (1.0 - int(drop_p * 65536.0 + 0.5) / 65536.0)
         T = S * Nb
         dy2 = dy.reshape(T, E).contiguous()
         in_b, out_b, l1_b, l2_b, n1b, n2b = ctx.refs
         df, df16, dn2w, dn2b = _ln_bwd(dy2, f, n2w, n2b, mean2, rstd2, want_bf16=True)
-        dl2_w = _wgrad(l2_w, df16, h16)
-        dl2_b = _bgrad(l2_b, df16)
-        dh16 = L.gemm(df16, shadow(l2_w), b_mn=True, epilogue=L.EPI_DRELU, aux_in=h16)
+        dffn16 = L.dropout_bf16(df16, seed, 4, drop_p) if drop else df16  # gradient of the (pre-dropout2) FFN output
+        dl2_w = _wgrad(l2_w, dffn16, h16)
+        dl2_b = _bgrad(l2_b, dffn16)
+        # h16 holds the dropped, rescaled ReLU output: its zeros mask both the ReLU and the dropout; kept entries carry 1/(1-p)
+        dh16 = L.gemm(dffn16, shadow(l2_w), b_mn=True, epilogue=L.EPI_DRELU, aux_in=h16, alpha=keep_scale)
         dl1_w = _wgrad(l1_w, dh16, y1_16)
         dl1_b = _bgrad(l1_b, dh16)
         dy1 = L.gemm(dh16, shadow(l1_w), b_mn=True, residual=df, out_dtype=torch.float32)  # + residual branch of y1
         dsa, dsa16, dn1w, dn1b = _ln_bwd(dy1, sa, n1w, n1b, mean1, rstd1, want_bf16=True)
-        dout_w = _wgrad(out_w, dsa16, o16)
-        dout_b = _bgrad(out_b, dsa16)
-        do16 = L.gemm(dsa16, shadow(out_w), b_mn=True)
+        dattn16 = L.dropout_bf16(dsa16, seed, 2, drop_p) if drop else dsa16
+        dout_w = _wgrad(out_w, dattn16, o16)
+        dout_b = _bgrad(out_b, dattn16)
+        do16 = L.gemm(dattn16, shadow(out_w), b_mn=True)
         dqkv = torch.empty_like(qkv)
         delta = torch.empty_like(lse)
         base, dbase = qkv.data_ptr(), dqkv.data_ptr()
         L.attn_bwd(base, base + 2 * E, base + 4 * E, o16, do16, lse, delta, dbase, dbase + 2 * E, dbase + 4 * E, Nb, nhead,
-                   S, dh, qs, os_, scale)
+                   S, dh, qs, os_, scale, drop_seed=seed if drop else None, drop_site=1, drop_p=drop_p)
         din_w = _wgrad(in_w, dqkv, x16)
         din_b = _bgrad(in_b, dqkv)
         dx = L.gemm(dqkv, shadow(in_w), b_mn=True, residual=dsa, out_dtype=torch.float32)
         return (dx.view(S, Nb, E), din_w, din_b, dout_w, dout_b, dl1_w, dl1_b, dl2_w, dl2_b, dn1w, dn1b, dn2w, dn2b, None,
-                None)
+                None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -53,8 +53,10 @@ class _SelfAttnParams(nn.Module):
 class GroupEmbedLayer(nn.Module):
     """nn.TransformerEncoderLayer(d_model, nhead, dim_feedforward) as used for `group_embed`
     (vit_3d_2d_pretrain.py:381): post-norm, ReLU, sequence-first [S, Nb, E] -- attention runs over S = B*px*py.
-    State-dict keys match torch's layer. Dropout: the reference's p=0.1 is active only in train(); parity is defined in
-    eval mode and this layer always evaluates the deterministic (p=0) arithmetic."""
+    State-dict keys match torch's layer. Dropout (p = 0.1 as in the reference) is active in train() at the four sites of
+    torch's layer (attention probabilities, dropout1, FFN dropout, dropout2) with counter-based masks keyed by a
+    device-resident seed that advances every training forward (so CUDA-graph replays draw fresh masks); eval() and
+    p = 0 run the deterministic arithmetic that parity is defined on."""
 
     def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, layer_norm_eps=1e-5):
         super().__init__()
@@ -65,13 +67,20 @@ class GroupEmbedLayer(nn.Module):
         self.norm2 = nn.LayerNorm(d_model, eps=layer_norm_eps)
         self.dropout_p = dropout
         self.nhead = nhead
+        # dropout seed lives on the device (not in the state dict): bumped in place before every training forward
+        # (a fixed start value: drawing it from torch's generator would shift the reference's weight-init stream)
+        self.register_buffer("_drop_seed", torch.full((1,), 20210914, dtype=torch.int32), persistent=False)
 
     def forward(self, src):
         a = self.self_attn
+        drop = self.training and self.dropout_p > 0.0
+        if drop:
+            with torch.no_grad():
+                self._drop_seed += 1
         return Fn.GroupEmbedFn.apply(src, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias,
                                      self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
                                      self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias, self.nhead,
-                                     self.norm1.eps)
+                                     self.norm1.eps, self.dropout_p if drop else 0.0, self._drop_seed if drop else None)
 
 
 def _load_pretrained(model, url, distilled=False):
