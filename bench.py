@@ -37,10 +37,10 @@ CONFIGS = {
                  n_classes=55, unit="voxels/s", per_sample=128 ** 3, cpu_B=2),
     # configs[3]: 3DViT point classification, 1024 points, kNN K=16, batch 128/GPU
     "cfg4": dict(kind="point", model="PointTransformerCls(deit_tiny)", backbone="deit_tiny_patch16_224", seg=False, N=1024,
-                 input_dim=6, n_classes=40, B=128, unit="points/s", per_sample=1024, cpu_B=8),
+                 input_dim=6, n_classes=40, B=128, unit="points/s", per_sample=1024, cpu_B=8, opt=("sgd", 0.01)),
     # configs[4]: ShapeNetPart part segmentation, 2048 points x 50 parts, batch 32/GPU
     "cfg5": dict(kind="point", model="PointTransformerSeg(deit_tiny)", backbone="deit_tiny_patch16_224", seg=True, N=2048,
-                 input_dim=22, n_classes=50, B=32, unit="points/s", per_sample=2048, cpu_B=4),
+                 input_dim=22, n_classes=50, B=32, unit="points/s", per_sample=2048, cpu_B=4, opt=("sgd", 0.05)),
 }
 
 
@@ -166,7 +166,11 @@ def cpu_reference_step_fn(cfg, B):
         frozen = tuple(k for k in sd if "running_" in k)
     params = {k: v.requires_grad_(True) for k, v in sd.items() if k not in frozen}
     sd = {**sd, **params}
-    opt = torch.optim.Adam(list(params.values()), lr=1e-3)
+    kind, lr = cfg.get("opt", ("adam", 1e-3))  # voxel: Adam (train_cls_voxel.py:195); point: SGD momentum 0.9
+    if kind == "sgd":                          # (train_cls.py:91, train_partseg.py:95 with config/*.yaml optimizer: SGD)
+        opt = torch.optim.SGD(list(params.values()), lr=lr, momentum=0.9)
+    else:
+        opt = torch.optim.Adam(list(params.values()), lr=lr)
     x, y = synthetic_batch(cfg, B, seed=9)
     lf = loss_fn_for(cfg)
     starts = None
@@ -304,7 +308,8 @@ def run_ours(args, cfg, rank, world, local_rank):
     torch.cuda.set_device(device)
     L.lib()  # fail loudly if the CUDA extension is missing
     model, exclude = build_model(cfg, device)
-    trainer = DataParallelTrainer(model, lr=1e-3, exclude=exclude)
+    opt_kind, opt_lr = cfg.get("opt", ("adam", 1e-3))
+    trainer = DataParallelTrainer(model, lr=opt_lr, exclude=exclude, optimizer=opt_kind, momentum=0.9)
     lf = loss_fn_for(cfg)
     B = cfg["B"]
     xh, yh = synthetic_batch(cfg, B, seed=9 + rank)
@@ -487,7 +492,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {cfg['model']}, batch {B}/GPU, fwd+bwd+Adam, bf16 operands / fp32 accumulate",
+        "config": {"workload": f"{args.config}: {cfg['model']}, batch {B}/GPU, fwd+bwd+{'SGD' if cfg.get('opt', ('adam',))[0] == 'sgd' else 'Adam'}, bf16 operands / fp32 accumulate",
                    "global_batch": B * world, "parallelism": f"dp{world}", "launch": graph_note,
                    "l2": "256 MB flush between timed steps; per-step working set (weights + Adam state + activations) >> 126 MB L2",
                    "input": "uint8 occupancy grid (1 B/voxel)" if cfg["kind"] == "voxel" else "fp32 points",
@@ -503,7 +508,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         v, ms, n = run_cpu(cfg, cfg["cpu_B"], steps=50, warmup=1, budget_s=15.0)
         out["cpu_baseline"] = {"value": v, "unit": cfg["unit"], "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"oracle port (torch CPU fp32), batch {cfg['cpu_B']} fwd+bwd+Adam, {n} steps, {ms:.0f} ms/step"}
+                               "sample": f"oracle port (torch CPU fp32), batch {cfg['cpu_B']} fwd+bwd+optimizer, {n} steps, {ms:.0f} ms/step"}
     return out
 
 
@@ -533,7 +538,7 @@ def main():
             "impl": "reference", "metric": "voxels/sec fwd+bwd" if cfg["kind"] == "voxel" else "points/sec fwd+bwd",
             "value": v, "unit": cfg["unit"], "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {cfg['model']}, CPU fp32, bounded sample batch {B}, fwd+bwd+Adam"},
+            "config": {"workload": f"{args.config}: {cfg['model']}, CPU fp32, bounded sample batch {B}, fwd+bwd+optimizer"},
             "cpu_baseline": {"value": v, "unit": cfg["unit"], "cores": cores, "kind": "port",
                              "sample": f"oracle port of the reference modules (torch CPU fp32, {cores} threads), batch {B} per step"},
             "e2e": {"value": v, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
