@@ -42,6 +42,7 @@ def _worker(rank, world, port, q):
                                transformer_backbone="deit_base_patch16_224", pretrained=False, pos_embedding="group_embed")
         m.load_state_dict(sd, strict=False)
         m.freeze_image_branch()
+        m.group_embed.dropout_p = 0.0  # this test compares gradients across separate forwards: no stochastic masks
         return m.to(dev).train()
 
     x, y = O.synthetic_voxels(3, 36, seed=100 + rank, n_classes=55)  # a different batch on every rank
