@@ -87,6 +87,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // ================================================================================================
 template <int DH, int NWARPS, int BKV, bool INDEP>
 __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams p) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem_attn[];
   constexpr int BQ = INDEP ? 16 : 16 * NWARPS;
   constexpr int kQBytes = BQ * DH * 2;
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams 
 // Backward, part 0: delta[b,h,i] = sum_d dO[i,d] * O[i,d]   (one warp per row)
 // ================================================================================================
 __global__ void __launch_bounds__(256) attn_delta_kernel(const AttnParams p, int DH) {
+  pdl_prologue();
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = (long long)p.B * p.H * p.N;
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const AttnParams p, int
 // ================================================================================================
 template <int DH, int NWARPS, int BKV, bool INDEP>
 __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_dq_kernel(const AttnParams p) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem_attn[];
   constexpr int BQ = INDEP ? 16 : 16 * NWARPS;
   constexpr int kQBytes = BQ * DH * 2;
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_dq_kernel(const AttnPara
 // ================================================================================================
 template <int DH, int NWARPS, int BQ, int SPLIT, bool INDEP>
 __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_dkv_kernel(const AttnParams p) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem_attn[];
   constexpr int BKVT = INDEP ? 16 : 16 * NWARPS;
   constexpr int DHS = DH / SPLIT;
@@ -529,6 +533,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_dkv_kernel(const AttnPar
 // ================================================================================================
 template <int DH, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnParams p) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem_attn[];
   constexpr int kTile = 16 * DH * 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -733,7 +738,7 @@ static int attn_fwd_dh(const AttnParams& p, cudaStream_t stream) {
     auto kern = attn_fwd_kernel<DH, NW, BKV, true>;
     int rc = set_smem(kern, smem);
     if (rc) return rc;
-    kern<<<(unsigned)((BH + NW - 1) / NW), NW * 32, smem, stream>>>(p);
+    S3D_CUDA_OK(launch_pdl(kern, dim3((unsigned)((BH + NW - 1) / NW)), dim3(NW * 32), (size_t)(smem), stream, p));
   } else if (p.N <= 32) {
     constexpr int NW = 2, BKV = 32;
     constexpr int smem = 32 * DH * 2 + 4 * BKV * DH * 2;
@@ -741,7 +746,7 @@ static int attn_fwd_dh(const AttnParams& p, cudaStream_t stream) {
     int rc = set_smem(kern, smem);
     if (rc) return rc;
     if (p.B > 65535) return S3D_ERR_BAD_SHAPE;
-    kern<<<dim3(1, p.H, p.B), NW * 32, smem, stream>>>(p);
+    S3D_CUDA_OK(launch_pdl(kern, dim3(dim3(1, p.H, p.B)), dim3(NW * 32), (size_t)(smem), stream, p));
   } else {
     constexpr int NW = 4, BKV = (DH == 64) ? 64 : 32;
     constexpr int smem = 64 * DH * 2 + 4 * BKV * DH * 2;
@@ -749,7 +754,7 @@ static int attn_fwd_dh(const AttnParams& p, cudaStream_t stream) {
     int rc = set_smem(kern, smem);
     if (rc) return rc;
     if (p.B > 65535) return S3D_ERR_BAD_SHAPE;
-    kern<<<dim3((p.N + 63) / 64, p.H, p.B), NW * 32, smem, stream>>>(p);
+    S3D_CUDA_OK(launch_pdl(kern, dim3(dim3((p.N + 63) / 64, p.H, p.B)), dim3(NW * 32), (size_t)(smem), stream, p));
   }
   S3D_LAUNCH_OK();
   return S3D_OK;
@@ -766,13 +771,13 @@ static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
     if (rc) return rc;
     long long ctas = (BH + NW - 1) / NW;
     if (ctas > num_sms()) ctas = num_sms();
-    kern<<<(unsigned)ctas, NW * 32, smem, stream>>>(p);
+    S3D_CUDA_OK(launch_pdl(kern, dim3((unsigned)ctas), dim3(NW * 32), (size_t)(smem), stream, p));
     S3D_LAUNCH_OK();
     return S3D_OK;
   }
   {
     const long long rows = BH * p.N;
-    attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(p, DH);
+    S3D_CUDA_OK(launch_pdl(attn_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), stream, p, DH));
     S3D_LAUNCH_OK();
   }
   constexpr int SPLIT = (DH == 64) ? 1 : 2;
@@ -783,7 +788,7 @@ static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
       auto kern = attn_bwd_dq_kernel<DH, NW, BKV, true>;
       int rc = set_smem(kern, smem);
       if (rc) return rc;
-      kern<<<(unsigned)((BH + NW - 1) / NW), NW * 32, smem, stream>>>(p);
+      S3D_CUDA_OK(launch_pdl(kern, dim3((unsigned)((BH + NW - 1) / NW)), dim3(NW * 32), (size_t)(smem), stream, p));
       S3D_LAUNCH_OK();
     }
     {
@@ -792,7 +797,7 @@ static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
       auto kern = attn_bwd_dkv_kernel<DH, NW, BQ, SPLIT, true>;
       int rc = set_smem(kern, smem);
       if (rc) return rc;
-      kern<<<(unsigned)((BH * SPLIT + NW - 1) / NW), NW * 32, smem, stream>>>(p);
+      S3D_CUDA_OK(launch_pdl(kern, dim3((unsigned)((BH * SPLIT + NW - 1) / NW)), dim3(NW * 32), (size_t)(smem), stream, p));
       S3D_LAUNCH_OK();
     }
   } else if (p.N <= 32) {
@@ -803,7 +808,7 @@ static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
       auto kern = attn_bwd_dq_kernel<DH, NW, BKV, false>;
       int rc = set_smem(kern, smem);
       if (rc) return rc;
-      kern<<<dim3(1, p.H, p.B), NW * 32, smem, stream>>>(p);
+      S3D_CUDA_OK(launch_pdl(kern, dim3(dim3(1, p.H, p.B)), dim3(NW * 32), (size_t)(smem), stream, p));
       S3D_LAUNCH_OK();
     }
     {
@@ -812,7 +817,7 @@ static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
       auto kern = attn_bwd_dkv_kernel<DH, NW, BQ, SPLIT, false>;
       int rc = set_smem(kern, smem);
       if (rc) return rc;
-      kern<<<dim3(SPLIT, p.H, p.B), NW * 32, smem, stream>>>(p);
+      S3D_CUDA_OK(launch_pdl(kern, dim3(dim3(SPLIT, p.H, p.B)), dim3(NW * 32), (size_t)(smem), stream, p));
       S3D_LAUNCH_OK();
     }
   } else {
@@ -824,7 +829,7 @@ static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
       auto kern = attn_bwd_dq_kernel<DH, NW, BKV, false>;
       int rc = set_smem(kern, smem);
       if (rc) return rc;
-      kern<<<dim3((p.N + 63) / 64, p.H, p.B), NW * 32, smem, stream>>>(p);
+      S3D_CUDA_OK(launch_pdl(kern, dim3(dim3((p.N + 63) / 64, p.H, p.B)), dim3(NW * 32), (size_t)(smem), stream, p));
       S3D_LAUNCH_OK();
     }
     {
@@ -833,7 +838,7 @@ static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
       auto kern = attn_bwd_dkv_kernel<DH, NW, BQ, SPLIT, false>;
       int rc = set_smem(kern, smem);
       if (rc) return rc;
-      kern<<<dim3(((p.N + 63) / 64) * SPLIT, p.H, p.B), NW * 32, smem, stream>>>(p);
+      S3D_CUDA_OK(launch_pdl(kern, dim3(dim3(((p.N + 63) / 64) * SPLIT, p.H, p.B)), dim3(NW * 32), (size_t)(smem), stream, p));
       S3D_LAUNCH_OK();
     }
   }

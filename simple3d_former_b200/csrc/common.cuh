@@ -33,6 +33,39 @@ enum : int {
     if (_e != cudaSuccess) return (int)_e;  \
   } while (0)
 
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). The small configurations are launch-latency bound (cfg2: ~280 kernels of
+// 5-10 us per step), so consecutive kernels of ours are launched with programmaticStreamSerialization: the next grid
+// is scheduled, and runs its prologue (barrier init, TMEM allocation, descriptor prefetch), while the previous grid
+// drains. Contract: every kernel launched through launch_pdl() calls pdl_prologue() (or pdl_trigger() + pdl_wait())
+// BEFORE its first global-memory access; griddepcontrol.wait returns once all prerequisite grids have completed and
+// their writes are visible, so data dependencies (RAW / WAR / WAW, transitively) are exactly those of a plain stream.
+// S3D_PDL=0 in the environment launches everything without the attribute (the instructions are then no-ops).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_trigger();
+  pdl_wait();
+}
+bool pdl_enabled();  // gemm_tcgen05.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }

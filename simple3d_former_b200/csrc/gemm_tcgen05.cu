@@ -156,6 +156,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                  const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN>;
+  pdl_trigger();  // the next grid may be scheduled (and run its on-chip prologue) while this one works
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes;  // 8 epilogue warps x 4 KB (TMA-store staging)
@@ -205,6 +206,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above touched only on-chip state and kernel parameters and may overlap the previous grid's tail;
+  // from here on global memory is read / written
+  pdl_wait();
 
   // work item -> (m tile of this CTA, n tile, k-block range)
   auto decode = [&](int item, int& m0, int& n0, int& kb0, int& kb1, int& split) {
@@ -648,6 +652,11 @@ static int make_tmap_out(CUtensorMap* map, const void* base, int is_f32, uint64_
   return r == CUDA_SUCCESS ? S3D_OK : S3D_ERR_DRIVER;
 }
 
+bool pdl_enabled() {
+  static const bool on = []() { const char* v = getenv("S3D_PDL"); return v == nullptr || v[0] != '0'; }();
+  return on;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -710,13 +719,15 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   cfg.blockDim = dim3(kNumThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see common.cuh: PDL
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   S3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, taux, p));
   return S3D_OK;
 }

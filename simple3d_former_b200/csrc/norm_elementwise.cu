@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                            __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                            int T, int D, float eps) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kLnFwdWarps * 32, 1)
                               const float* __restrict__ gamma, const float* __restrict__ beta,
                               __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
                               float* __restrict__ mean_out, float* __restrict__ rstd_out, int T, int D, float eps) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t lnf_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nvec = D >> 2;
@@ -214,13 +216,13 @@ static int launch_ln_fwd_pipe(const float* x, const float* addend, float* sum_ou
   if (stages == 3) {
     auto kern = layernorm_fwd_pipe_kernel<I, 3>;
     S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    kern<<<(int)blocks, kLnFwdWarps * 32, shmem, stream>>>(x, addend, sum_out, gamma, beta, yb, y_f32, mean, rstd, T, D,
-                                                           eps);
+    S3D_CUDA_OK(launch_pdl(kern, dim3((int)blocks), dim3(kLnFwdWarps * 32), (size_t)(shmem), stream, x, addend, sum_out, gamma, beta, yb, y_f32, mean, rstd, T, D,
+                                                           eps));
   } else {
     auto kern = layernorm_fwd_pipe_kernel<I, 2>;
     S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    kern<<<(int)blocks, kLnFwdWarps * 32, shmem, stream>>>(x, addend, sum_out, gamma, beta, yb, y_f32, mean, rstd, T, D,
-                                                           eps);
+    S3D_CUDA_OK(launch_pdl(kern, dim3((int)blocks), dim3(kLnFwdWarps * 32), (size_t)(shmem), stream, x, addend, sum_out, gamma, beta, yb, y_f32, mean, rstd, T, D,
+                                                           eps));
   }
   S3D_LAUNCH_OK();
   return S3D_OK;
@@ -256,8 +258,8 @@ int layernorm_fwd(const float* x, const float* addend, float* sum_out, const flo
     if (rc != S3D_ERR_UNSUPPORTED) return rc;
   }
 #define S3D_LN_FWD(I)                                                                                              \
-  layernorm_fwd_kernel<I><<<(int)blocks, warps_per_block * 32, 0, stream>>>(x, addend, sum_out, gamma, beta, yb, \
-                                                                            y_f32, mean, rstd, T, D, eps)
+  S3D_CUDA_OK(launch_pdl(layernorm_fwd_kernel<I>, dim3((int)blocks), dim3(warps_per_block * 32), (size_t)(0), stream, x, addend, sum_out, gamma, beta, yb, \
+                                                                            y_f32, mean, rstd, T, D, eps))
   switch (iters) {
     case 1: S3D_LN_FWD(1); break;
     case 2: S3D_LN_FWD(2); break;
@@ -287,6 +289,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                                                            __nv_bfloat16* __restrict__ dx_bf16,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int T,
                                                            int D) {
+  pdl_prologue();
   extern __shared__ float red[];  // [2][D]
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -396,6 +399,7 @@ __global__ void __launch_bounds__(kLnWarps * 32, 1)
                               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                               const float* __restrict__ dres, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int D) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -537,7 +541,7 @@ static int launch_ln_bwd_pipe(const void* dy, const float* x, const float* gamma
   S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
   long long blocks = ((long long)T + kLnWarps - 1) / kLnWarps;
   if (blocks > num_sms()) blocks = num_sms();
-  kern<<<(int)blocks, kLnWarps * 32, shmem, stream>>>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, T, D);
+  S3D_CUDA_OK(launch_pdl(kern, dim3((int)blocks), dim3(kLnWarps * 32), (size_t)(shmem), stream, dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, T, D));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -580,13 +584,13 @@ int layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* g
 #define S3D_LN_BWD(I)                                                                                                 \
   do {                                                                                                                \
     if (dy_is_bf16)                                                                                                   \
-      layernorm_bwd_kernel<I, true><<<(int)blocks, warps_per_block * 32, shmem, stream>>>(dy, x, gamma, mean, rstd,  \
+      S3D_CUDA_OK(launch_pdl(layernorm_bwd_kernel<I, true>, dim3((int)blocks), dim3(warps_per_block * 32), (size_t)(shmem), stream, dy, x, gamma, mean, rstd,  \
                                                                                           dres, dx, dxb, dgamma,      \
-                                                                                          dbeta, T, D);               \
+                                                                                          dbeta, T, D));               \
     else                                                                                                              \
-      layernorm_bwd_kernel<I, false><<<(int)blocks, warps_per_block * 32, shmem, stream>>>(dy, x, gamma, mean, rstd, \
+      S3D_CUDA_OK(launch_pdl(layernorm_bwd_kernel<I, false>, dim3((int)blocks), dim3(warps_per_block * 32), (size_t)(shmem), stream, dy, x, gamma, mean, rstd, \
                                                                                            dres, dx, dxb, dgamma,     \
-                                                                                           dbeta, T, D);              \
+                                                                                           dbeta, T, D));              \
   } while (0)
   switch (iters) {
     case 1: S3D_LN_BWD(1); break;
@@ -607,6 +611,7 @@ int layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* g
 // fp32 -> bf16 cast (weight shadow copies / activations), with optional transposed copy [C,R] of a [R,C] matrix.
 // ------------------------------------------------------------------------------------------------
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n4) {
+  pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(in)[i];
     uint2 u;
@@ -617,6 +622,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 }
 __global__ void cast_bf16_tail_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t start,
                                       size_t n) {
+  pdl_prologue();
   const size_t i = start + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = __float2bfloat16(in[i]);
 }
@@ -631,13 +637,13 @@ int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t strea
     size_t blocks = (n4 + 255) / 256;
     const size_t cap = (size_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    cast_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, o, n4);
+    S3D_CUDA_OK(launch_pdl(cast_bf16_kernel, dim3((int)blocks), dim3(256), (size_t)(0), stream, in, o, n4));
     S3D_LAUNCH_OK();
   }
   const size_t done = n4 * 4;
   if (done < (size_t)n) {
     const size_t rem = (size_t)n - done;
-    cast_bf16_tail_kernel<<<(int)((rem + 255) / 256), 256, 0, stream>>>(in, o, done, (size_t)n);
+    S3D_CUDA_OK(launch_pdl(cast_bf16_tail_kernel, dim3((int)((rem + 255) / 256)), dim3(256), (size_t)(0), stream, in, o, done, (size_t)n));
     S3D_LAUNCH_OK();
   }
   return S3D_OK;
@@ -647,6 +653,7 @@ int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t strea
 template <typename TIn>
 __global__ void transpose_to_bf16_kernel(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C,
                                          long long ld_in, long long ld_out) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -667,13 +674,13 @@ int transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int C, l
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
   if (grid.y > 65535) return S3D_ERR_BAD_SHAPE;
   if (in_is_bf16)
-    transpose_to_bf16_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+    S3D_CUDA_OK(launch_pdl(transpose_to_bf16_kernel<__nv_bfloat16>, dim3(grid), dim3(block), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(in),
                                                                         reinterpret_cast<__nv_bfloat16*>(out), R, C,
-                                                                        ld_in, ld_out);
+                                                                        ld_in, ld_out));
   else
-    transpose_to_bf16_kernel<float><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(in),
+    S3D_CUDA_OK(launch_pdl(transpose_to_bf16_kernel<float>, dim3(grid), dim3(block), (size_t)(0), stream, reinterpret_cast<const float*>(in),
                                                                 reinterpret_cast<__nv_bfloat16*>(out), R, C, ld_in,
-                                                                ld_out);
+                                                                ld_out));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -684,6 +691,7 @@ int transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int C, l
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
                                                          int T, int C, long long ld, int rows_per_block) {
+  pdl_prologue();
   // blockDim = (32 column-pairs, 8 row lanes)
   __shared__ float red[8][64];
   const int c = blockIdx.x * 64 + threadIdx.x * 2;
@@ -717,6 +725,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // warps of the CTA take rows r, r+8, ... four at a time (4 independent 16-byte loads per thread in flight).
 __global__ void __launch_bounds__(256) colsum_bf16_v8_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
                                                             int T, int C, long long ld, int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + lane * 8;
@@ -767,8 +776,8 @@ int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accu
     if (row_blocks < 1) row_blocks = 1;
     const int rows_per_block = (T + row_blocks - 1) / row_blocks;
     dim3 grid(col_blocks, row_blocks);
-    colsum_bf16_v8_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, T, C, ld,
-                                                    rows_per_block);
+    S3D_CUDA_OK(launch_pdl(colsum_bf16_v8_kernel, dim3(grid), dim3(256), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(in), out, T, C, ld,
+                                                    rows_per_block));
     S3D_LAUNCH_OK();
     return S3D_OK;
   }
@@ -778,8 +787,8 @@ int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accu
   if (row_blocks < 1) row_blocks = 1;
   const int rows_per_block = (T + row_blocks - 1) / row_blocks;
   dim3 grid(col_blocks, row_blocks), block(32, 8);
-  colsum_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, T, C, ld,
-                                                 rows_per_block);
+  S3D_CUDA_OK(launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(block), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(in), out, T, C, ld,
+                                                 rows_per_block));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -793,6 +802,7 @@ int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accu
 __global__ void dropout_add_f32_kernel(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ out,
                                        long long n4, int cols, const uint32_t* __restrict__ seed, uint32_t site,
                                        uint32_t thresh16, float scale) {
+  pdl_prologue();
   const uint32_t ss = drop_site_seed(*seed, site);
   const int c4 = cols >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -811,6 +821,7 @@ __global__ void dropout_add_f32_kernel(const float* __restrict__ x, const float*
 __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n4,
                                     int cols, const uint32_t* __restrict__ seed, uint32_t site, uint32_t thresh16,
                                     float scale) {
+  pdl_prologue();
   const uint32_t ss = drop_site_seed(*seed, site);
   const int c4 = cols >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -839,8 +850,8 @@ int dropout_add_f32(const float* x, const float* res, float* out, long long rows
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  dropout_add_f32_kernel<<<(int)blocks, 256, 0, stream>>>(x, res, out, n4, cols, seed, site, th,
-                                                          1.0f / (1.0f - (float)th / 65536.0f));
+  S3D_CUDA_OK(launch_pdl(dropout_add_f32_kernel, dim3((int)blocks), dim3(256), (size_t)(0), stream, x, res, out, n4, cols, seed, site, th,
+                                                          1.0f / (1.0f - (float)th / 65536.0f)));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -854,9 +865,9 @@ int dropout_bf16(const void* x, void* out, long long rows, int cols, const uint3
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  dropout_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  S3D_CUDA_OK(launch_pdl(dropout_bf16_kernel, dim3((int)blocks), dim3(256), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(x),
                                                        reinterpret_cast<__nv_bfloat16*>(out), n4, cols, seed, site, th,
-                                                       1.0f / (1.0f - (float)th / 65536.0f));
+                                                       1.0f / (1.0f - (float)th / 65536.0f)));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -872,6 +883,7 @@ template <typename TIn>
 __global__ void __launch_bounds__(256) voxel_patch_gather_kernel(const TIn* __restrict__ x,
                                                                 __nv_bfloat16* __restrict__ P, int B, int V, int c,
                                                                 int p, int Kpad, int zsum) {
+  pdl_prologue();
   const int K = c * c * c;
   const int pz_out = zsum ? 1 : p;
   const long long rows = (long long)B * p * p * pz_out;
@@ -925,11 +937,11 @@ int voxel_patch_gather(const void* x, int in_dtype, void* P, int B, int V, int c
   if (blocks > cap) blocks = cap;
   auto out = reinterpret_cast<__nv_bfloat16*>(P);
   if (in_dtype == 0)
-    voxel_patch_gather_kernel<float><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(x), out, B, V, cell, patch, Kpad, zsum);
+    S3D_CUDA_OK(launch_pdl(voxel_patch_gather_kernel<float>, dim3((int)blocks), dim3(256), (size_t)(0), stream, reinterpret_cast<const float*>(x), out, B, V, cell, patch, Kpad, zsum));
   else if (in_dtype == 1)
-    voxel_patch_gather_kernel<uint8_t><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(x), out, B, V, cell, patch, Kpad, zsum);
+    S3D_CUDA_OK(launch_pdl(voxel_patch_gather_kernel<uint8_t>, dim3((int)blocks), dim3(256), (size_t)(0), stream, reinterpret_cast<const uint8_t*>(x), out, B, V, cell, patch, Kpad, zsum));
   else
-    voxel_patch_gather_kernel<int><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const int*>(x), out, B, V, cell, patch, Kpad, zsum);
+    S3D_CUDA_OK(launch_pdl(voxel_patch_gather_kernel<int>, dim3((int)blocks), dim3(256), (size_t)(0), stream, reinterpret_cast<const int*>(x), out, B, V, cell, patch, Kpad, zsum));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -945,6 +957,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                   float beta2, float eps, float weight_decay, float bias_corr1,
                                                   float bias_corr2_sqrt, float grad_scale,
                                                   const int* __restrict__ step_dev) {
+  pdl_prologue();
   if (step_dev != nullptr) {  // CUDA-graph replays: the step counter lives on the device
     const float st = (float)(*step_dev);
     bias_corr1 = 1.f - powf(beta1, st);
@@ -975,8 +988,8 @@ int adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, l
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  adam_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), (size_t)n,
-                                               lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale, step_dev);
+  S3D_CUDA_OK(launch_pdl(adam_kernel, dim3((int)blocks), dim3(256), (size_t)(0), stream, p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), (size_t)n,
+                                               lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale, step_dev));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -989,6 +1002,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
                                                  float* __restrict__ buf, __nv_bfloat16* __restrict__ shadow, size_t n,
                                                  float lr, float momentum, float weight_decay, float grad_scale,
                                                  int first_step, const int* __restrict__ step_dev) {
+  pdl_prologue();
   if (step_dev != nullptr) first_step = (*step_dev <= 1);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float pi = p[i];
@@ -1009,8 +1023,8 @@ int sgd_momentum_step(float* p, const float* g, float* buf, void* shadow_bf16, l
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  sgd_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, buf, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), (size_t)n, lr, momentum,
-                                              weight_decay, grad_scale, step == 1, step_dev);
+  S3D_CUDA_OK(launch_pdl(sgd_kernel, dim3((int)blocks), dim3(256), (size_t)(0), stream, p, g, buf, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), (size_t)n, lr, momentum,
+                                              weight_decay, grad_scale, step == 1, step_dev));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }

@@ -100,6 +100,7 @@ __device__ __forceinline__ void cta_reduce_write(float (&acc)[NSETS][4], float* 
 // MODE 3: dz1 = scale * (dy1 - m1 - zhat1 * m2); duf[idx] += dz1; sum dz1 * (centred xyz)  (dW1x)
 template <int MODE>
 __global__ void __launch_bounds__(kWarps * 32) sa_group_kernel(SaGroup a, SaExtra e) {
+  pdl_prologue();
   constexpr int NSETS = (MODE == 3) ? 3 : 2;
   __shared__ __align__(16) float red[(MODE == 1) ? 4 : kWarps * NSETS * kChunk];
   const int nchunks = (a.C1 + kChunk - 1) / kChunk;
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(kWarps * 32) sa_group_reduce_kernel(const floa
                                                                      unsigned char* __restrict__ kmax,
                                                                      unsigned char* __restrict__ kmin,
                                                                      float* __restrict__ partials) {
+  pdl_prologue();
   __shared__ __align__(16) float red[kWarps * 2 * kChunk];
   const int nchunks = (C + kChunk - 1) / kChunk;
   const int q = blockIdx.x % nchunks, part = blockIdx.x / nchunks, nparts = gridDim.x / nchunks;
@@ -252,6 +254,7 @@ __global__ void sa_pool_select_kernel(const float* __restrict__ zmax, const floa
                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                       float* __restrict__ out, float* __restrict__ zsel,
                                       unsigned char* __restrict__ ksel, long long n, int C) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const float s = scale[c];
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(kWarps * 32) sa_dz2_expand_kernel(
     const unsigned char* __restrict__ ksel, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ m1,
     const float* __restrict__ m2, __nv_bfloat16* __restrict__ dz2, long long G, int K, int C) {
+  pdl_prologue();
   const int nchunks = (C + kChunk - 1) / kChunk;
   const int q = blockIdx.x % nchunks, part = blockIdx.x / nchunks, nparts = gridDim.x / nchunks;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -318,6 +322,7 @@ __global__ void __launch_bounds__(kWarps * 32) bn_rows_stats_kernel(const float*
                                                                    const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, long long R, int C,
                                                                    float* __restrict__ partials) {
+  pdl_prologue();
   __shared__ __align__(16) float red[kWarps * 2 * kChunk];
   const int nchunks = (C + kChunk - 1) / kChunk;
   const int q = blockIdx.x % nchunks, part = blockIdx.x / nchunks, nparts = gridDim.x / nchunks;
@@ -381,6 +386,7 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partials, int P
                                        float momentum, float* __restrict__ running_mean,
                                        float* __restrict__ running_var, float* __restrict__ mean,
                                        float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_prologue();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;  // warp-uniform
   double s, ss;
@@ -408,6 +414,7 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partials, int P
 __global__ void bn_finalize_bwd_kernel(const float* __restrict__ partials, int P, int C, double count, int training,
                                        float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int accumulate) {
+  pdl_prologue();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;  // warp-uniform
   double s, ss;
@@ -423,6 +430,7 @@ __global__ void bn_finalize_bwd_kernel(const float* __restrict__ partials, int P
 __global__ void bn_relu_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale,
                                      const float* __restrict__ shift, float* __restrict__ y32,
                                      __nv_bfloat16* __restrict__ y16, long long n4, int C) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4) % C);
     const float4 v = reinterpret_cast<const float4*>(z)[i];
@@ -449,6 +457,7 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ dout, const f
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ m1, const float* __restrict__ m2,
                                          __nv_bfloat16* __restrict__ dz16, long long n4, int C) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4) % C);
     const float4 v = reinterpret_cast<const float4*>(z)[i];
@@ -490,6 +499,7 @@ __global__ void __launch_bounds__(256) three_nn_interp_fwd_kernel(const float* _
                                                                  const float* __restrict__ addend,
                                                                  float* __restrict__ out, long long rows, int N, int S,
                                                                  int C) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -514,6 +524,7 @@ __global__ void __launch_bounds__(256) three_nn_interp_bwd_kernel(const float* _
                                                                  const float* __restrict__ dist,
                                                                  float* __restrict__ dfeats, long long rows, int N,
                                                                  int S, int C) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -536,6 +547,7 @@ __global__ void __launch_bounds__(256) three_nn_interp_bwd_kernel(const float* _
 // (where a bf16-rounded operand with |mean| >> std would be amplified by the normalisation).
 __global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long R, int K,
                                     long long ldx, int weight_layout) {
+  pdl_prologue();
   const long long n = R * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / K;
@@ -574,22 +586,22 @@ int sa_group_launch(int mode, const SaGroup& a, const SaExtra& e, int P, cudaStr
   switch (mode) {
     case 0:
       if (e.partials == nullptr) return S3D_ERR_NULL;
-      sa_group_kernel<0><<<grid, kWarps * 32, 0, stream>>>(a, e);
+      S3D_CUDA_OK(launch_pdl(sa_group_kernel<0>, dim3(grid), dim3(kWarps * 32), (size_t)(0), stream, a, e));
       break;
     case 1:
       if (e.scale == nullptr || e.shift == nullptr || e.a1_out == nullptr) return S3D_ERR_NULL;
-      sa_group_kernel<1><<<grid, kWarps * 32, 0, stream>>>(a, e);
+      S3D_CUDA_OK(launch_pdl(sa_group_kernel<1>, dim3(grid), dim3(kWarps * 32), (size_t)(0), stream, a, e));
       break;
     case 2:
       if (e.mean == nullptr || e.rstd == nullptr || e.a1 == nullptr || e.da1 == nullptr || e.partials == nullptr)
         return S3D_ERR_NULL;
-      sa_group_kernel<2><<<grid, kWarps * 32, 0, stream>>>(a, e);
+      S3D_CUDA_OK(launch_pdl(sa_group_kernel<2>, dim3(grid), dim3(kWarps * 32), (size_t)(0), stream, a, e));
       break;
     case 3:
       if (e.scale == nullptr || e.mean == nullptr || e.rstd == nullptr || e.m1 == nullptr || e.m2 == nullptr ||
           e.a1 == nullptr || e.da1 == nullptr || e.duf == nullptr || e.partials == nullptr)
         return S3D_ERR_NULL;
-      sa_group_kernel<3><<<grid, kWarps * 32, 0, stream>>>(a, e);
+      S3D_CUDA_OK(launch_pdl(sa_group_kernel<3>, dim3(grid), dim3(kWarps * 32), (size_t)(0), stream, a, e));
       break;
     default: return S3D_ERR_UNSUPPORTED;
   }
@@ -663,8 +675,8 @@ int s3d_sa_group_reduce(const float* z2, int64_t G, int K, int C, float* zmax, f
   if (K > 255 || (C & 3)) return S3D_ERR_UNSUPPORTED;
   if (z2 == nullptr || zmax == nullptr || zmin == nullptr || kmax == nullptr || kmin == nullptr || partials == nullptr)
     return S3D_ERR_NULL;
-  sa_group_reduce_kernel<<<grid_for_rows(G, C, P), kWarps * 32, 0, st(stream)>>>(z2, G, K, C, zmax, zmin, kmax, kmin,
-                                                                                  partials);
+  S3D_CUDA_OK(launch_pdl(sa_group_reduce_kernel, dim3(grid_for_rows(G, C, P)), dim3(kWarps * 32), (size_t)(0), st(stream), z2, G, K, C, zmax, zmin, kmax, kmin,
+                                                                                  partials));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -680,7 +692,7 @@ int s3d_sa_pool_select(const float* zmax, const float* zmin, const uint8_t* kmax
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  sa_pool_select_kernel<<<(int)blocks, 256, 0, st(stream)>>>(zmax, zmin, kmax, kmin, scale, shift, out, zsel, ksel, n, C);
+  S3D_CUDA_OK(launch_pdl(sa_pool_select_kernel, dim3((int)blocks), dim3(256), (size_t)(0), st(stream), zmax, zmin, kmax, kmin, scale, shift, out, zsel, ksel, n, C));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -693,8 +705,8 @@ int s3d_sa_dz2_expand(const float* z2, const float* dout, const float* zsel, con
   if (z2 == nullptr || dout == nullptr || zsel == nullptr || ksel == nullptr || scale == nullptr || shift == nullptr ||
       mean == nullptr || rstd == nullptr || m1 == nullptr || m2 == nullptr || dz2_bf16 == nullptr)
     return S3D_ERR_NULL;
-  sa_dz2_expand_kernel<<<grid_for_rows(G, C, P), kWarps * 32, 0, st(stream)>>>(
-      z2, dout, zsel, ksel, scale, shift, mean, rstd, m1, m2, reinterpret_cast<__nv_bfloat16*>(dz2_bf16), G, K, C);
+  S3D_CUDA_OK(launch_pdl(sa_dz2_expand_kernel, dim3(grid_for_rows(G, C, P)), dim3(kWarps * 32), (size_t)(0), st(stream), 
+      z2, dout, zsel, ksel, scale, shift, mean, rstd, m1, m2, reinterpret_cast<__nv_bfloat16*>(dz2_bf16), G, K, C));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -703,8 +715,8 @@ int s3d_bn_rows_stats(const float* z, int64_t R, int C, float* partials, int P, 
   if (R <= 0 || C <= 0 || P <= 0) return S3D_ERR_BAD_SHAPE;
   if (C & 3) return S3D_ERR_UNSUPPORTED;
   if (z == nullptr || partials == nullptr) return S3D_ERR_NULL;
-  bn_rows_stats_kernel<0><<<grid_for_rows(R, C, P), kWarps * 32, 0, st(stream)>>>(z, nullptr, nullptr, nullptr, nullptr,
-                                                                                   nullptr, R, C, partials);
+  S3D_CUDA_OK(launch_pdl(bn_rows_stats_kernel<0>, dim3(grid_for_rows(R, C, P)), dim3(kWarps * 32), (size_t)(0), st(stream), z, nullptr, nullptr, nullptr, nullptr,
+                                                                                   nullptr, R, C, partials));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -716,8 +728,8 @@ int s3d_bn_rows_bwd_stats(const float* dout, const float* z, const float* scale,
   if (dout == nullptr || z == nullptr || scale == nullptr || shift == nullptr || mean == nullptr || rstd == nullptr ||
       partials == nullptr)
     return S3D_ERR_NULL;
-  bn_rows_stats_kernel<1><<<grid_for_rows(R, C, P), kWarps * 32, 0, st(stream)>>>(z, dout, scale, shift, mean, rstd, R,
-                                                                                   C, partials);
+  S3D_CUDA_OK(launch_pdl(bn_rows_stats_kernel<1>, dim3(grid_for_rows(R, C, P)), dim3(kWarps * 32), (size_t)(0), st(stream), z, dout, scale, shift, mean, rstd, R,
+                                                                                   C, partials));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -728,8 +740,8 @@ int s3d_bn_finalize_fwd(const float* partials, int P, int C, double count, const
   if (P <= 0 || C <= 0 || count <= 0.0) return S3D_ERR_BAD_SHAPE;
   if (partials == nullptr || mean == nullptr || rstd == nullptr || scale == nullptr || shift == nullptr)
     return S3D_ERR_NULL;
-  bn_finalize_fwd_kernel<<<(C + 3) / 4, 128, 0, st(stream)>>>(partials, P, C, count, gamma, beta, eps, momentum,
-                                                                   running_mean, running_var, mean, rstd, scale, shift);
+  S3D_CUDA_OK(launch_pdl(bn_finalize_fwd_kernel, dim3((C + 3) / 4), dim3(128), (size_t)(0), st(stream), partials, P, C, count, gamma, beta, eps, momentum,
+                                                                   running_mean, running_var, mean, rstd, scale, shift));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -738,8 +750,8 @@ int s3d_bn_finalize_bwd(const float* partials, int P, int C, double count, int t
                         float* dgamma, float* dbeta, int accumulate, void* stream) {
   if (P <= 0 || C <= 0 || count <= 0.0) return S3D_ERR_BAD_SHAPE;
   if (partials == nullptr || m1 == nullptr || m2 == nullptr) return S3D_ERR_NULL;
-  bn_finalize_bwd_kernel<<<(C + 3) / 4, 128, 0, st(stream)>>>(partials, P, C, count, training, m1, m2, dgamma, dbeta,
-                                                                   accumulate);
+  S3D_CUDA_OK(launch_pdl(bn_finalize_bwd_kernel, dim3((C + 3) / 4), dim3(128), (size_t)(0), st(stream), partials, P, C, count, training, m1, m2, dgamma, dbeta,
+                                                                   accumulate));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -754,8 +766,8 @@ int s3d_bn_relu_apply(const float* z, const float* scale, const float* shift, fl
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  bn_relu_apply_kernel<<<(int)blocks, 256, 0, st(stream)>>>(z, scale, shift, y_f32,
-                                                            reinterpret_cast<__nv_bfloat16*>(y_bf16), n4, C);
+  S3D_CUDA_OK(launch_pdl(bn_relu_apply_kernel, dim3((int)blocks), dim3(256), (size_t)(0), st(stream), z, scale, shift, y_f32,
+                                                            reinterpret_cast<__nv_bfloat16*>(y_bf16), n4, C));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -772,8 +784,8 @@ int s3d_bn_relu_bwd_apply(const float* dout, const float* z, const float* scale,
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  bn_relu_bwd_apply_kernel<<<(int)blocks, 256, 0, st(stream)>>>(dout, z, scale, shift, mean, rstd, m1, m2,
-                                                                reinterpret_cast<__nv_bfloat16*>(dz_bf16), n4, C);
+  S3D_CUDA_OK(launch_pdl(bn_relu_bwd_apply_kernel, dim3((int)blocks), dim3(256), (size_t)(0), st(stream), dout, z, scale, shift, mean, rstd, m1, m2,
+                                                                reinterpret_cast<__nv_bfloat16*>(dz_bf16), n4, C));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -785,8 +797,8 @@ int s3d_split_bf16x3(const float* x, void* out_bf16, int64_t R, int K, int64_t l
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  split_bf16x3_kernel<<<(int)blocks, 256, 0, st(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), R, K, ldx,
-                                                           weight_layout);
+  S3D_CUDA_OK(launch_pdl(split_bf16x3_kernel, dim3((int)blocks), dim3(256), (size_t)(0), st(stream), x, reinterpret_cast<__nv_bfloat16*>(out_bf16), R, K, ldx,
+                                                           weight_layout));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -799,8 +811,8 @@ int s3d_three_nn_interp_fwd(const float* feats, const int64_t* idx, const float*
   long long blocks = (rows + 7) / 8;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  three_nn_interp_fwd_kernel<<<(int)blocks, 256, 0, st(stream)>>>(feats, reinterpret_cast<const long long*>(idx), dist,
-                                                                  addend, out, rows, N, S, C);
+  S3D_CUDA_OK(launch_pdl(three_nn_interp_fwd_kernel, dim3((int)blocks), dim3(256), (size_t)(0), st(stream), feats, reinterpret_cast<const long long*>(idx), dist,
+                                                                  addend, out, rows, N, S, C));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -814,8 +826,8 @@ int s3d_three_nn_interp_bwd(const float* dout, const int64_t* idx, const float* 
   long long blocks = (rows + 7) / 8;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  three_nn_interp_bwd_kernel<<<(int)blocks, 256, 0, st(stream)>>>(dout, reinterpret_cast<const long long*>(idx), dist,
-                                                                  dfeats, rows, N, S, C);
+  S3D_CUDA_OK(launch_pdl(three_nn_interp_bwd_kernel, dim3((int)blocks), dim3(256), (size_t)(0), st(stream), dout, reinterpret_cast<const long long*>(idx), dist,
+                                                                  dfeats, rows, N, S, C));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
