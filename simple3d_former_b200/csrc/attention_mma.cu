@@ -713,6 +713,143 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   }
 }
 
+// ================================================================================================
+// Forward for tiny sequences (N <= 16): one warp per (batch, head), persistent with two cp.async stages, same structure
+// as attn_bwd_small_kernel. Replaces the generic kernel's INDEP path for the stage-1 sequences of the group-embed model
+// (2820 warp instructions per (batch, head) there, 64 of them MMAs: index arithmetic and per-element rescaling).
+// ================================================================================================
+template <int DH, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) attn_fwd_small_kernel(const AttnParams p) {
+  pdl_prologue();
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  constexpr int kTile = 16 * DH * 2;
+  constexpr int CH = DH / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long BH = (long long)p.B * p.H;
+  const long long gw = (long long)blockIdx.x * NWARPS + warp;
+  const long long gstride = (long long)gridDim.x * NWARPS;
+  const uint32_t wbase = smem_u32(smem_attn) + warp * 6 * kTile;  // two stages of {Q, K, V}
+  uint32_t xs[(CH + 31) / 32][8];
+#pragma unroll
+  for (int c = 0; c < (CH + 31) / 32; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xs[c][k] = (uint32_t)(((c * 32 + lane) ^ k) << 4);
+  for (int i = lane; i < 6 * 16 * CH; i += 32) {  // rows >= N are never written by cp.async: zero them once
+    const int t = i / (16 * CH), r = (i / CH) % 16, ch = i % CH;
+    if (r >= p.N) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tile_addr<DH>(wbase + t * kTile, r, ch)), "r"(0));
+    }
+  }
+  __syncwarp();
+  auto load16 = [&](uint32_t sb, const __nv_bfloat16* g, long long rs) {
+#pragma unroll
+    for (int c = 0; c < (CH + 31) / 32; ++c) {
+      if (CH % 32 == 0 || c * 32 + lane < CH) {
+        const __nv_bfloat16* src = g + (c * 32 + lane) * 8;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          if (r < p.N) {  // warp-uniform
+            cp_async16(sb + r * (DH * 2) + xs[c][r & 7], src, 16);
+            src += rs;
+          }
+        }
+      }
+    }
+  };
+  auto prefetch = [&](long long t, int st) {
+    const int tb = (int)(t / p.H), th = (int)(t % p.H);
+    const long long tq = (long long)tb * p.qkv_bs + (long long)th * p.qkv_hs;
+    const uint32_t sb = wbase + st * 3 * kTile;
+    load16(sb, p.q + tq, p.qkv_rs);
+    load16(sb + kTile, p.k + tq, p.qkv_rs);
+    load16(sb + 2 * kTile, p.v + tq, p.qkv_rs);
+  };
+  if (gw < BH) prefetch(gw, 0);
+  cp_async_commit();
+  const int r0 = lane >> 2, r1 = r0 + 8;
+  const int c0 = 2 * (lane & 3);
+  const bool ok0 = r0 < p.N, ok1 = r1 < p.N;
+  const float sc = p.scale * kLog2e;
+  int it = 0;
+  for (long long bh = gw; bh < BH; bh += gstride, ++it) {
+    if (bh + gstride < BH) prefetch(bh + gstride, (it + 1) & 1);
+    cp_async_commit();
+    const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+    const uint32_t sQ = wbase + (it & 1) * 3 * kTile, sK = sQ + kTile, sV = sQ + 2 * kTile;
+    cp_async_wait<1>();
+    __syncwarp();
+    // ---- S = Q K^T
+    float s[2][4] = {};
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) {
+      uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+      ldsm_x4(tile_addr<DH>(sQ, lane & 15, ks * 2 + (lane >> 4)), a0, a1, a2, a3);
+      ldsm_x4(tile_addr<DH>(sK, (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+      mma16816(s[0], a0, a1, a2, a3, b0, b1);
+      mma16816(s[1], a0, a1, a2, a3, b2, b3);
+    }
+    // ---- softmax over the (<= 16) keys of each row: 4 values per lane and row, the 4 lanes of a quad share a row
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int kidx = nt * 8 + c0;
+      s[nt][0] = kidx < p.N ? s[nt][0] * sc : -INFINITY;
+      s[nt][1] = kidx + 1 < p.N ? s[nt][1] * sc : -INFINITY;
+      s[nt][2] = kidx < p.N ? s[nt][2] * sc : -INFINITY;
+      s[nt][3] = kidx + 1 < p.N ? s[nt][3] * sc : -INFINITY;
+      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - m0);
+      s[nt][1] = exp2f(s[nt][1] - m0);
+      s[nt][2] = exp2f(s[nt][2] - m1);
+      s[nt][3] = exp2f(s[nt][3] - m1);
+      l0 += s[nt][0] + s[nt][1];
+      l1 += s[nt][2] + s[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    if (p.lse != nullptr && (lane & 3) == 0) {  // natural-log units of the scaled scores, as the backward kernels expect
+      float* glse = p.lse + bh * p.N;
+      if (ok0) glse[r0] = (m0 + log2f(l0)) * 0.6931471805599453f;
+      if (ok1) glse[r1] = (m1 + log2f(l1)) * 0.6931471805599453f;
+    }
+    // ---- O = P V with the normalised probabilities as the A operand
+    const uint32_t a0 = pack_bf16x2(s[0][0] * i0, s[0][1] * i0), a1 = pack_bf16x2(s[0][2] * i1, s[0][3] * i1);
+    const uint32_t a2 = pack_bf16x2(s[1][0] * i0, s[1][1] * i0), a3 = pack_bf16x2(s[1][2] * i1, s[1][3] * i1);
+    const long long ooff = (long long)b * p.o_bs + (long long)h * p.o_hs + c0;
+    uint32_t* o0 = reinterpret_cast<uint32_t*>(p.out + ooff + (long long)r0 * p.o_rs);
+    uint32_t* o1 = reinterpret_cast<uint32_t*>(p.out + ooff + (long long)r1 * p.o_rs);
+#pragma unroll
+    for (int dt2 = 0; dt2 < DH / 16; ++dt2) {
+      float acc0[4], acc1[4];
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(tile_addr<DH>(sV, (lane & 7) + (((lane >> 3) & 1) << 3), dt2 * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma16816_z(acc0, a0, a1, a2, a3, b0, b1);
+      mma16816_z(acc1, a0, a1, a2, a3, b2, b3);
+      if (ok0) {
+        o0[dt2 * 8] = pack_bf16x2(acc0[0], acc0[1]);
+        o0[dt2 * 8 + 4] = pack_bf16x2(acc1[0], acc1[1]);
+      }
+      if (ok1) {
+        o1[dt2 * 8] = pack_bf16x2(acc0[2], acc0[3]);
+        o1[dt2 * 8 + 4] = pack_bf16x2(acc1[2], acc1[3]);
+      }
+    }
+    __syncwarp();  // all lanes are done with this stage before it is refilled two pairs later
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host dispatch
 // ------------------------------------------------------------------------------------------------
@@ -732,13 +869,15 @@ static int set_smem(K kern, int bytes) {
 template <int DH>
 static int attn_fwd_dh(const AttnParams& p, cudaStream_t stream) {
   const long long BH = (long long)p.B * p.H;
-  if (p.N <= 16) {
-    constexpr int NW = 4, BKV = 16;
-    constexpr int smem = NW * (16 * DH * 2 + 2 * BKV * DH * 2);
-    auto kern = attn_fwd_kernel<DH, NW, BKV, true>;
+  if (p.N <= 16) {  // persistent, one warp per (batch, head), two stages of {Q, K, V} per warp
+    constexpr int NW = (DH == 64) ? 8 : 4;
+    constexpr int smem = NW * 2 * 3 * 16 * DH * 2;
+    auto kern = attn_fwd_small_kernel<DH, NW>;
     int rc = set_smem(kern, smem);
     if (rc) return rc;
-    S3D_CUDA_OK(launch_pdl(kern, dim3((unsigned)((BH + NW - 1) / NW)), dim3(NW * 32), (size_t)(smem), stream, p));
+    long long ctas = (BH + NW - 1) / NW;
+    if (ctas > num_sms()) ctas = num_sms();
+    S3D_CUDA_OK(launch_pdl(kern, dim3((unsigned)ctas), dim3(NW * 32), (size_t)(smem), stream, p));
   } else if (p.N <= 32) {
     constexpr int NW = 2, BKV = 32;
     constexpr int smem = 32 * DH * 2 + 4 * BKV * DH * 2;

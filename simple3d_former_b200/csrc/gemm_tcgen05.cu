@@ -781,6 +781,27 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
     else if (p.N > 64 && (t128 >= sms / 2 || p.N % 128 == 0)) bn = 128;
     else bn = (p.N > 64 && t128 * 2 > sms) ? 128 : 64;
   }
+  // Small problems (at most one tile per SM even with 256-wide tiles: the cfg2 / point-model shapes) are latency bound,
+  // not throughput bound (in-graph probe, profiles/r01_small_gemm_variants_in_graph.log): a launch costs 6-11 us whatever
+  // the variant, and the best tile width is the one that spreads the work over the most SMs while staying in a single
+  // round (e.g. M=1664: N=1152 -> BN128 = 117 tiles, N=1536 -> BN256 = 78 tiles, N=384 -> BN64 = 78 tiles). Long-K
+  // weight gradients are the exception: split-K supplies the parallelism and a narrow tile only re-reads the A operand.
+  bool small_latency_bound = false;
+  if (g.force_bn == 0 && (long long)num_m * ((p.N + 255) / 256) * nb <= sms) {
+    auto tiles_of = [&](int b) { return (long long)num_m * ((p.N + b - 1) / b) * nb; };
+    auto waste_ok = [&](int b) { const int nn = (p.N + b - 1) / b * b; return (nn - p.N) * 4 <= nn; };
+    if (g.a_mn && g.b_mn && num_kb >= 64) {
+      bn = waste_ok(256) ? 256 : (waste_ok(128) ? 128 : 64);
+    } else {
+      long long best = -1;
+      for (int b : {256, 128, 64}) {
+        if (b != 64 && p.N <= b / 2) continue;
+        const long long t = tiles_of(b);
+        if (t <= sms && t > best) { best = t; bn = b; }
+      }
+      small_latency_bound = true;
+    }
+  }
   if (bn != 64 && bn != 128 && bn != 256) return S3D_ERR_UNSUPPORTED;
   const long long tiles = (long long)num_m * ((p.N + bn - 1) / bn) * nb;
   // cluster size along M (B-tile multicast): needs >= 2 m-tiles and whole 64-wide chunks of B per CTA
@@ -789,6 +810,7 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   if (num_m < 2 || cl < 1) cl = 1;
   if (cl == 4 && (bn != 256 || num_m < 4)) cl = 2;
   if (cl == 3 || cl > 4) cl = 2;
+  if (small_latency_bound && g.force_cluster == 0 && env_cluster == 0) cl = 1;  // single round: a cluster launch only adds latency
   // split-K: plain fp32 output (optionally accumulating onto itself), too few tiles to fill the machine, long K
   const bool split_ok = p.out_fp32 && p.epilogue == EPI_NONE && p.aux_out == nullptr &&
                         (p.residual == nullptr || p.residual == p.D) && nb == 1;
