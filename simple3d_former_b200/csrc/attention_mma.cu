@@ -824,9 +824,10 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_small_kernel(const AttnP
       if (ok0) glse[r0] = (m0 + log2f(l0)) * 0.6931471805599453f;
       if (ok1) glse[r1] = (m1 + log2f(l1)) * 0.6931471805599453f;
     }
-    // ---- O = P V with the normalised probabilities as the A operand
-    const uint32_t a0 = pack_bf16x2(s[0][0] * i0, s[0][1] * i0), a1 = pack_bf16x2(s[0][2] * i1, s[0][3] * i1);
-    const uint32_t a2 = pack_bf16x2(s[1][0] * i0, s[1][1] * i0), a3 = pack_bf16x2(s[1][2] * i1, s[1][3] * i1);
+    // ---- O = (P V) / l: the unnormalised exponentials (row maximum exactly 1) are the bf16 A operand and the division
+    // happens in fp32 on the accumulator, as in the streaming kernels (one rounding fewer than normalising P first)
+    const uint32_t a0 = pack_bf16x2(s[0][0], s[0][1]), a1 = pack_bf16x2(s[0][2], s[0][3]);
+    const uint32_t a2 = pack_bf16x2(s[1][0], s[1][1]), a3 = pack_bf16x2(s[1][2], s[1][3]);
     const long long ooff = (long long)b * p.o_bs + (long long)h * p.o_hs + c0;
     uint32_t* o0 = reinterpret_cast<uint32_t*>(p.out + ooff + (long long)r0 * p.o_rs);
     uint32_t* o1 = reinterpret_cast<uint32_t*>(p.out + ooff + (long long)r1 * p.o_rs);
@@ -838,12 +839,12 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_small_kernel(const AttnP
       mma16816_z(acc0, a0, a1, a2, a3, b0, b1);
       mma16816_z(acc1, a0, a1, a2, a3, b2, b3);
       if (ok0) {
-        o0[dt2 * 8] = pack_bf16x2(acc0[0], acc0[1]);
-        o0[dt2 * 8 + 4] = pack_bf16x2(acc1[0], acc1[1]);
+        o0[dt2 * 8] = pack_bf16x2(acc0[0] * i0, acc0[1] * i0);
+        o0[dt2 * 8 + 4] = pack_bf16x2(acc1[0] * i0, acc1[1] * i0);
       }
       if (ok1) {
-        o1[dt2 * 8] = pack_bf16x2(acc0[2], acc0[3]);
-        o1[dt2 * 8 + 4] = pack_bf16x2(acc1[2], acc1[3]);
+        o1[dt2 * 8] = pack_bf16x2(acc0[2] * i1, acc0[3] * i1);
+        o1[dt2 * 8 + 4] = pack_bf16x2(acc1[2] * i1, acc1[3] * i1);
       }
     }
     __syncwarp();  // all lanes are done with this stage before it is refilled two pairs later

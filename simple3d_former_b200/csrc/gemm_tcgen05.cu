@@ -787,7 +787,8 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   // round (e.g. M=1664: N=1152 -> BN128 = 117 tiles, N=1536 -> BN256 = 78 tiles, N=384 -> BN64 = 78 tiles). Long-K
   // weight gradients are the exception: split-K supplies the parallelism and a narrow tile only re-reads the A operand.
   bool small_latency_bound = false;
-  if (g.force_bn == 0 && (long long)num_m * ((p.N + 255) / 256) * nb <= sms) {
+  static const bool small_rule = []() { const char* v = getenv("S3D_GEMM_SMALL"); return v == nullptr || v[0] != '0'; }();
+  if (small_rule && g.force_bn == 0 && (long long)num_m * ((p.N + 255) / 256) * nb <= sms) {
     auto tiles_of = [&](int b) { return (long long)num_m * ((p.N + b - 1) / b) * nb; };
     auto waste_ok = [&](int b) { const int nn = (p.N + b - 1) / b * b; return (nn - p.N) * 4 <= nn; };
     if (g.a_mn && g.b_mn && num_kb >= 64) {
