@@ -18,6 +18,7 @@ def build():
                            transformer_backbone="deit_base_patch16_224", pretrained=False, pos_embedding="group_embed")
     m.load_state_dict(sd, strict=False)
     m.freeze_image_branch()
+    m.group_embed.dropout_p = float(os.environ.get("S3D_CHECK_DROPOUT", "0"))  # default: deterministic arithmetic
     return m.to(dev).train()
 
 def run(m):
@@ -30,7 +31,9 @@ def run(m):
     return logits.detach().clone(), {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
 
 m = build()
+seed0 = m.group_embed._drop_seed.clone()
 l1, g1 = run(m)
+m.group_embed._drop_seed.copy_(seed0)  # with dropout on, the same seed must reproduce the same masks
 l2, g2 = run(m)
 print("same model, run twice: logits bitwise equal:", torch.equal(l1, l2), "max diff", (l1 - l2).abs().max().item())
 worst = sorted(((g1[n] - g2[n]).abs().max().item() / (g1[n].abs().max().item() + 1e-12), n) for n in g1)[-5:]
