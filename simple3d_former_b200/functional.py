@@ -86,6 +86,50 @@ def _w2d(w16: torch.Tensor) -> torch.Tensor:
     return w16.reshape(w16.shape[0], -1)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# Side stream for the parameter-gradient work of small problems. In a Block's backward only 7 of the 17 launches sit on
+# the activation-gradient chain; the 4 weight-gradient GEMMs, 4 bias column sums (and their split-K memsets) depend on
+# it but nothing depends on them. At the cfg2 sizes (T*D = 0.64 M) every kernel occupies 40-80 of the 148 SMs for
+# 5-12 us, so the off-chain half runs concurrently on a second stream (fork after each producer, one join before the node
+# returns: every tensor the side stream touches is alive until then). Large problems fill the machine with every
+# kernel and keep the single-stream order.
+# ----------------------------------------------------------------------------------------------------------------
+_SIDE_STREAMS = {}
+_OVERLAP_LIMIT = int(__import__("os").environ.get("S3D_OVERLAP_MAX_ELEMS", str(8 * 1024 * 1024)))
+
+
+class _ParamGradStream:
+    """fork(): work issued under `with ctx.fork():` runs on the side stream after everything enqueued so far on the
+    current stream; join(): the current stream waits for all of it. A no-op object when overlap is off."""
+
+    def __init__(self, device, enabled):
+        self.side = None
+        if enabled:
+            key = (device.type, device.index)
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+            self.side = _SIDE_STREAMS[key]
+            self.main = torch.cuda.current_stream(device)
+
+    def fork(self):
+        if self.side is None:
+            return _NullCtx()
+        self.side.wait_stream(self.main)
+        return torch.cuda.stream(self.side)
+
+    def join(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 def _attn_strides_timm(N, H, dh):
     E = H * dh
     return (N * 3 * E, dh, 3 * E), (N * E, dh, E)
@@ -242,23 +286,29 @@ class BlockFn(torch.autograd.Function):
         if dy16 is None or dy16.shape != (T, D) or getattr(dy, "_s3d_bf16_src", None) != dy.data_ptr():
             dy16 = L.cast_bf16(dy2)
         n1b, qkv_b, proj_b, n2b, fc1_b, fc2_b = ctx.refs
+        pg = _ParamGradStream(dy.device, T * D <= _OVERLAP_LIMIT)  # weight / bias gradients off the critical chain
         # MLP
-        dfc2_w = _wgrad(fc2_w, dy16, a16)
-        dfc2_b = _bgrad(fc2_b, dy16)
+        with pg.fork():
+            dfc2_w = _wgrad(fc2_w, dy16, a16)
+            dfc2_b = _bgrad(fc2_b, dy16)
         dpre = L.gemm(dy16, shadow(fc2_w), b_mn=True, epilogue=L.EPI_DGELU, aux_in=pre)
-        dfc1_w = _wgrad(fc1_w, dpre, g16)
-        dfc1_b = _bgrad(fc1_b, dpre)
+        with pg.fork():
+            dfc1_w = _wgrad(fc1_w, dpre, g16)
+            dfc1_b = _bgrad(fc1_b, dpre)
         dg = L.gemm(dpre, shadow(fc1_w), b_mn=True)
         dx1, dx1_16, dn2w, dn2b = _ln_bwd(dg, x1, n2w, n2b, mean2, rstd2, dres=dy2, want_bf16=True)
         # attention
-        dproj_w = _wgrad(proj_w, dx1_16, o16.view(T, D))
-        dproj_b = _bgrad(proj_b, dx1_16)
+        with pg.fork():
+            dproj_w = _wgrad(proj_w, dx1_16, o16.view(T, D))
+            dproj_b = _bgrad(proj_b, dx1_16)
         do16 = L.gemm(dx1_16, shadow(proj_w), b_mn=True)
         dqkv = _attn_core_bwd(qkv, o16, do16.view(B, N, D), lse, B, N, H, dh, scale)
-        dqkv_w = _wgrad(qkv_w, dqkv, h16)
-        dqkv_b = _bgrad(qkv_b, dqkv)
+        with pg.fork():
+            dqkv_w = _wgrad(qkv_w, dqkv, h16)
+            dqkv_b = _bgrad(qkv_b, dqkv)
         dh_ = L.gemm(dqkv, shadow(qkv_w), b_mn=True)
         dx, dx16, dn1w, dn1b = _ln_bwd(dh_, x2, n1w, n1b, mean1, rstd1, dres=dx1, want_bf16=True)
+        pg.join()
         dx = dx.view(B, N, D)
         dx._s3d_bf16 = dx16
         dx._s3d_bf16_src = dx.data_ptr()
