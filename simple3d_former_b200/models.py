@@ -214,7 +214,7 @@ class TransitionUp(nn.Module):
 
     def forward(self, xyz1, points1, xyz2, points2):
         """xyz1 [B,S,3] / points1 [B,S,dim1]: coarse level; xyz2 [B,N,3] / points2 [B,N,dim2]: fine level."""
-        fusable = self.fused and points1.is_cuda and xyz1.shape[1] > 1 and self.fc1[0].out_features % 4 == 0 and \
+        fusable = self.fused and points1.is_cuda and xyz1.shape[1] > 1 and self.fc1[0].out_features % 8 == 0 and \
             points1.shape[-1] % 8 == 0 and points2.shape[-1] % 8 == 0
         if not fusable:
             feats1 = self.fc1(points1)
