@@ -350,7 +350,8 @@ def scatter_add_rows(grad_out, idx, N):
 def _slots(work_items, C):
     """Number of partial-sum slots (CTA row-slices) for a statistics pass over `work_items` warp items of C channels."""
     nchunks = (C + 127) // 128
-    return int(max(1, min((work_items + 7) // 8, 888 // nchunks)))
+    # 148 SMs x 4 resident CTAs (256 threads, <= 64 registers): one full wave, no half-empty second wave
+    return int(max(1, min((work_items + 7) // 8, 592 // nchunks)))
 
 
 def _f32(*shape, device):
@@ -399,9 +400,10 @@ def sa_group_bwd_stats(g, mean, rstd, a1, da1):
 def sa_group_bwd_scatter(g, scale, mean, rstd, m1, m2, a1, da1):
     B, N, S, K, C1 = g.dims
     duf = torch.zeros((B * N, C1), device=g.device, dtype=torch.float32)
-    part = _f32(g.P, 3, C1, device=g.device)
+    P = max(1, min(g.P, 444 // ((C1 + 127) // 128)))  # this pass holds 80 registers: 3 resident CTAs per SM
+    part = _f32(P, 3, C1, device=g.device)
     call("s3d_sa_group_bwd_scatter", *g.head, ptr(scale), ptr(mean), ptr(rstd), ptr(m1), ptr(m2), ptr(a1), ptr(da1),
-         ptr(duf), ptr(part), g.P, stream())
+         ptr(duf), ptr(part), P, stream())
     return duf, part
 
 

@@ -99,7 +99,7 @@ __device__ __forceinline__ void cta_reduce_write(float (&acc)[NSETS][4], float* 
 // MODE 2: sum dy1, sum dy1 * zhat1              (BatchNorm-1 backward statistics; dy1 = dA1 where A1 > 0)
 // MODE 3: dz1 = scale * (dy1 - m1 - zhat1 * m2); duf[idx] += dz1; sum dz1 * (centred xyz)  (dW1x)
 template <int MODE>
-__global__ void __launch_bounds__(kWarps * 32) sa_group_kernel(SaGroup a, SaExtra e) {
+__global__ void __launch_bounds__(kWarps * 32, MODE == 3 ? 3 : 4) sa_group_kernel(SaGroup a, SaExtra e) {
   pdl_prologue();
   constexpr int NSETS = (MODE == 3) ? 3 : 2;
   __shared__ __align__(16) float red[(MODE == 1) ? 4 : kWarps * NSETS * kChunk];
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kWarps * 32) sa_group_kernel(SaGroup a, SaExtr
 
 // z2 [G*K, C] fp32 -> per group and channel: max / min over the K rows and the row (k) where they occur (first on
 // ties), plus the BatchNorm statistics sum z2, sum z2^2 over ALL rows.
-__global__ void __launch_bounds__(kWarps * 32) sa_group_reduce_kernel(const float* __restrict__ z2, long long G, int K,
+__global__ void __launch_bounds__(kWarps * 32, 4) sa_group_reduce_kernel(const float* __restrict__ z2, long long G, int K,
                                                                      int C, float* __restrict__ zmax,
                                                                      float* __restrict__ zmin,
                                                                      unsigned char* __restrict__ kmax,
@@ -267,7 +267,7 @@ __global__ void sa_pool_select_kernel(const float* __restrict__ zmax, const floa
 }
 
 // dz2[r, c] = scale * (dy - m1 - zhat * m2), dy = dout[g, c] at the pooled row (k == ksel) when its output was > 0.
-__global__ void __launch_bounds__(kWarps * 32) sa_dz2_expand_kernel(
+__global__ void __launch_bounds__(kWarps * 32, 4) sa_dz2_expand_kernel(
     const float* __restrict__ z2, const float* __restrict__ dout, const float* __restrict__ zsel,
     const unsigned char* __restrict__ ksel, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ m1,
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kWarps * 32) sa_dz2_expand_kernel(
 // Row kernels for BatchNorm over a plain [R, C] fp32 matrix (Linear -> BatchNorm1d -> ReLU of TransitionUp).
 // MODE 0: sum z, sum z^2.  MODE 1: sum dy, sum dy * zhat with dy = dout where scale * z + shift > 0.
 template <int MODE>
-__global__ void __launch_bounds__(kWarps * 32) bn_rows_stats_kernel(const float* __restrict__ z,
+__global__ void __launch_bounds__(kWarps * 32, 4) bn_rows_stats_kernel(const float* __restrict__ z,
                                                                    const float* __restrict__ dout,
                                                                    const float* __restrict__ scale,
                                                                    const float* __restrict__ shift,
