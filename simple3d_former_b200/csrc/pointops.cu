@@ -4,6 +4,8 @@
 // explicit round-to-nearest intrinsics (no FMA contraction) and ordering is ascending (distance, index).
 // No distance matrix is ever written to HBM: candidate coordinates are staged in shared memory and every query thread
 // keeps its K best in registers.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace s3d {
@@ -80,10 +82,147 @@ __global__ void __launch_bounds__(128) knn_kernel(const float* __restrict__ xyz,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// kNN, warp per query (N <= 2048 candidates, K <= 32). The thread-per-query kernel above pays its K-deep insertion
+// for a whole warp whenever ANY of its 32 queries accepts a candidate, which with K = 16 is true for ~85 % of the 1024
+// candidates (100 k warp instructions per 32 queries). Here lane l of a warp holds the distances of candidates
+// l, l+32, ... in registers and the selection is a filter:
+//   1. T = K-th smallest of the 32 per-lane minima: an upper bound of the K-th nearest distance (they are 32 distinct
+//      candidates), found with one rank computation over warp shuffles;
+//   2. the candidates with d <= T (about 22 for K = 16 on scattered data) are compacted into shared memory with ballots;
+//   3. every survivor's rank under the (distance, index) order is counted against the other survivors; ranks < K are
+//      written straight to their output slot.
+// If massive ties make more than kKnnCap candidates survive, the warp falls back to K rounds of exact warp-wide
+// arg-min extraction. Ordering contract unchanged: ascending (distance, index), distances bit-exact.
+// ------------------------------------------------------------------------------------------------
+constexpr int kKnnCap = 128;        // survivors kept per query in the fast path
+constexpr int kKnnWarps = 8;        // warps per CTA
+constexpr int kKnnQueriesPerWarp = 8;
+
+__device__ __forceinline__ bool knn_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+template <int NPL>
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_warp_kernel(const float* __restrict__ xyz,
+                                                                 const float* __restrict__ query,
+                                                                 long long* __restrict__ idx_out,
+                                                                 float* __restrict__ dist_out, int N, int S, int K) {
+  extern __shared__ float knn_smem[];  // [3][N] candidate coordinates | per warp: kKnnCap distances + kKnnCap indices
+  float* sx = knn_smem;
+  float* sy = sx + N;
+  float* sz = sy + N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sd = sz + N + warp * 2 * kKnnCap;
+  int* si = reinterpret_cast<int*>(sd + kKnnCap);
+  const int b = blockIdx.y;
+  const float* pts = xyz + (size_t)b * N * 3;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    sx[i] = pts[3 * i];
+    sy[i] = pts[3 * i + 1];
+    sz[i] = pts[3 * i + 2];
+  }
+  __syncthreads();
+  const float kInf = __int_as_float(0x7f800000);
+  const int q0 = (blockIdx.x * kKnnWarps + warp) * kKnnQueriesPerWarp;
+  for (int qq = 0; qq < kKnnQueriesPerWarp; ++qq) {
+    const int s = q0 + qq;
+    if (s >= S) break;  // warp-uniform
+    const float* q = query + ((size_t)b * S + s) * 3;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    float d[NPL];
+    float m = kInf;
+#pragma unroll
+    for (int t = 0; t < NPL; ++t) {
+      const int j = lane + 32 * t;
+      d[t] = j < N ? sqdist3(qx, qy, qz, sx[j], sy[j], sz[j]) : kInf;
+      m = fminf(m, d[t]);
+    }
+    // rank of this lane's minimum among the 32 minima (ties by lane id): the lane of rank K-1 holds the threshold
+    int r = 0;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+      const float mo = __shfl_sync(0xffffffffu, m, o);
+      r += (mo < m || (mo == m && o < lane)) ? 1 : 0;
+    }
+    const unsigned holder = __ballot_sync(0xffffffffu, r == K - 1);
+    const float T = __shfl_sync(0xffffffffu, m, __ffs(holder) - 1);
+    // compact the candidates with d <= T
+    int total = 0;
+#pragma unroll
+    for (int t = 0; t < NPL; ++t) {
+      const bool pass = d[t] <= T;
+      const unsigned mask = __ballot_sync(0xffffffffu, pass);
+      const int pos = total + __popc(mask & ((1u << lane) - 1u));
+      if (pass && pos < kKnnCap) {
+        sd[pos] = d[t];
+        si[pos] = lane + 32 * t;
+      }
+      total += __popc(mask);
+    }
+    __syncwarp();
+    long long* o = idx_out + ((size_t)b * S + s) * K;
+    float* od = dist_out != nullptr ? dist_out + ((size_t)b * S + s) * K : nullptr;
+    if (total <= kKnnCap) {
+      for (int e = lane; e < total; e += 32) {
+        const float de = sd[e];
+        const int ie = si[e];
+        int rank = 0;
+        for (int f = 0; f < total; ++f) rank += knn_less(sd[f], si[f], de, ie) ? 1 : 0;
+        if (rank < K) {
+          o[rank] = (long long)ie;
+          if (od != nullptr) od[rank] = de;
+        }
+      }
+    } else {
+      // exact fallback for heavy ties: K rounds of warp-wide lexicographic arg-min over the register-resident candidates
+      for (int k = 0; k < K; ++k) {
+        float bd = kInf;
+        int bj = 0x7fffffff;
+#pragma unroll
+        for (int t = 0; t < NPL; ++t) {
+          const int j = lane + 32 * t;
+          if (j < N && knn_less(d[t], j, bd, bj)) { bd = d[t]; bj = j; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const float od2 = __shfl_xor_sync(0xffffffffu, bd, off);
+          const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+          if (knn_less(od2, oj, bd, bj)) { bd = od2; bj = oj; }
+        }
+        if (lane == 0) {
+          o[k] = (long long)bj;
+          if (od != nullptr) od[k] = bd;
+        }
+#pragma unroll
+        for (int t = 0; t < NPL; ++t)
+          if (lane + 32 * t == bj) d[t] = __int_as_float(0x7fc00000);  // NaN: never "less" again (taken)
+      }
+    }
+    __syncwarp();  // the survivor buffer is reused by the next query
+  }
+}
+
+template <int NPL>
+static int launch_knn_warp(const float* xyz, const float* query, long long* idx, float* dist, int B, int N, int S, int K,
+                           cudaStream_t stream) {
+  const size_t smem = (size_t)3 * N * sizeof(float) + (size_t)kKnnWarps * 2 * kKnnCap * sizeof(float);
+  auto kern = knn_warp_kernel<NPL>;
+  if (smem > 48 * 1024) S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_cta = kKnnWarps * kKnnQueriesPerWarp;
+  dim3 grid((S + per_cta - 1) / per_cta, B);
+  kern<<<grid, kKnnWarps * 32, smem, stream>>>(xyz, query, idx, dist, N, S, K);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
 int knn(const float* xyz, const float* query, long long* idx, float* dist, int B, int N, int S, int K,
         cudaStream_t stream) {
   if (B <= 0 || N <= 0 || S <= 0 || K <= 0 || K > N || K > 64 || B > 65535) return S3D_ERR_BAD_SHAPE;
   if (xyz == nullptr || query == nullptr || idx == nullptr) return S3D_ERR_NULL;
+  static const bool warp_path = []() { const char* v = getenv("S3D_KNN_WARP"); return v == nullptr || v[0] != '0'; }();
+  if (warp_path && K <= 32 && N <= 2048) {  // warp per query, filter + rank (see knn_warp_kernel)
+    if (N <= 1024) return launch_knn_warp<32>(xyz, query, idx, dist, B, N, S, K, stream);
+    return launch_knn_warp<64>(xyz, query, idx, dist, B, N, S, K, stream);
+  }
   dim3 grid((S + 127) / 128, B);
   // The register list holds the KMAX best; its first K entries are the K best (buckets bound compile time).
   if (K <= 4) knn_kernel<4><<<grid, 128, 0, stream>>>(xyz, query, idx, dist, N, S, K);

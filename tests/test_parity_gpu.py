@@ -139,6 +139,22 @@ def test_point_ops_edge_cases_and_full_size_properties():
     far = torch.full((1, 4, 3), 5.0, device=dev)
     assert (P.query_ball_point(0.2, 8, xyz, far) == 16).all()
     assert torch.equal(P.farthest_point_sample(xyz, 4, torch.tensor([3], device=dev))[0].cpu(), torch.tensor([3, 0, 0, 0]))
+    # heavy ties (more tied candidates than the warp kernel's survivor buffer -> its exact arg-min fallback), ragged sizes,
+    # K = 3 / 32, the 2048-candidate variant and the thread-per-query kernel (N > 2048), all against the stable-argsort oracle
+    g = torch.Generator().manual_seed(21)
+    dup = torch.rand(2, 700, 3, generator=g)
+    dup[:, 100:500] = dup[:, 7:8]  # 400 copies of one point
+    cases = [(dup, dup[:, ::9].contiguous(), 16), (torch.zeros(1, 1024, 3), torch.zeros(1, 5, 3), 16),
+             (torch.rand(2, 37, 3, generator=g), torch.rand(2, 11, 3, generator=g), 3),
+             (torch.rand(1, 1500, 3, generator=g), torch.rand(1, 70, 3, generator=g), 32),
+             (torch.rand(1, 2048, 3, generator=g), torch.rand(1, 65, 3, generator=g), 16),
+             (torch.rand(1, 2500, 3, generator=g), torch.rand(1, 33, 3, generator=g), 16)]
+    for pts_c, qry_c, K in cases:
+        got_i, got_d = P.knn_point(K, pts_c.to(dev), qry_c.to(dev), return_dist=True)
+        want = O.knn_np(pts_c.numpy(), qry_c.numpy(), K)
+        assert np.array_equal(got_i.cpu().numpy(), want), (tuple(pts_c.shape), K)
+        d_ref = O.square_distance_np(qry_c.numpy(), pts_c.numpy())
+        assert np.array_equal(got_d.cpu().numpy(), np.take_along_axis(d_ref, want, axis=-1))
     # BASELINE cfg4 sizes (B=128, N=S=1024, K=16): size-independent properties
     x, _ = O.synthetic_points(128, 1024)
     pts = x[..., :3].contiguous().to(dev)
