@@ -318,7 +318,6 @@ def run_ours(args, cfg, rank, world, local_rank):
     xh, yh = xh.pin_memory(), yh.pin_memory()
     x = xh.to(device)
     y = yh.to(device)
-    loss_host = torch.zeros(1).pin_memory()
     if cfg["kind"] == "point":
         model.set_fps_starts([torch.zeros(B, dtype=torch.long, device=device)] * 2)
 

@@ -5,6 +5,8 @@ statistics and softmax, fp32 parameter gradients. PyTorch only allocates tensors
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -95,7 +97,7 @@ def _w2d(w16: torch.Tensor) -> torch.Tensor:
 # kernel and keep the single-stream order.
 # ----------------------------------------------------------------------------------------------------------------
 _SIDE_STREAMS = {}
-_OVERLAP_LIMIT = int(__import__("os").environ.get("S3D_OVERLAP_MAX_ELEMS", str(8 * 1024 * 1024)))
+_OVERLAP_LIMIT = int(os.environ.get("S3D_OVERLAP_MAX_ELEMS", str(8 * 1024 * 1024)))  # token * channel elements
 
 
 class _ParamGradStream:
