@@ -82,3 +82,22 @@ def test_device_expansion_full_size_round_trip():
         assert np.array_equal(BO.read_as_3d_array(files[i]), d)
     # idempotence: re-encoding the device result gives the same file
     assert BO.write(got[0, 0].astype(bool)) == files[0]
+
+
+def test_oracle_round_trip_random_grids():
+    """write -> read is the identity for arbitrary (also non-cubic) grids, run lengths are capped at 255 and the pair
+    stream encodes exactly prod(dims) voxels (the properties the device expansion relies on)."""
+    rng = np.random.default_rng(5)
+    for dims, p in [((1, 1, 1), 0.5), ((3, 5, 7), 0.3), ((16, 16, 16), 0.0), ((16, 16, 16), 1.0), ((9, 40, 2), 0.02),
+                    ((20, 20, 20), 0.97)]:
+        dense = rng.random(dims) < p
+        raw = BO.write(dense)
+        assert np.array_equal(BO.read_as_3d_array(raw), dense)
+        d, _, _, pos = BO.read_header(raw)
+        pairs = np.frombuffer(raw, dtype=np.uint8, offset=pos)
+        assert list(d) == list(dims) and pairs.size % 2 == 0
+        counts = pairs[1::2].astype(np.int64)
+        assert counts.min() >= 1 and counts.max() <= 255 and counts.sum() == int(np.prod(dims))
+        vals = pairs[0::2]
+        same = vals[1:] == vals[:-1]
+        assert np.all(counts[:-1][same] == 255)  # a value only repeats across the 255 cap
