@@ -85,10 +85,11 @@ def test_device_expansion_full_size_round_trip():
 
 
 def test_oracle_round_trip_random_grids():
-    """write -> read is the identity for arbitrary (also non-cubic) grids, run lengths are capped at 255 and the pair
-    stream encodes exactly prod(dims) voxels (the properties the device expansion relies on)."""
+    """write -> read is the identity for cubic grids (the reference's reshape(dims) + transpose is not an identity for
+    non-cubic dims -- its own TODO at utils/binvox_rw.py:228 -- and the product rejects those), run lengths are capped at
+    255 and the pair stream encodes exactly V^3 voxels (the properties the device expansion relies on)."""
     rng = np.random.default_rng(5)
-    for dims, p in [((1, 1, 1), 0.5), ((3, 5, 7), 0.3), ((16, 16, 16), 0.0), ((16, 16, 16), 1.0), ((9, 40, 2), 0.02),
+    for dims, p in [((1, 1, 1), 0.5), ((7, 7, 7), 0.3), ((16, 16, 16), 0.0), ((16, 16, 16), 1.0), ((33, 33, 33), 0.02),
                     ((20, 20, 20), 0.97)]:
         dense = rng.random(dims) < p
         raw = BO.write(dense)
