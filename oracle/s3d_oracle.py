@@ -121,6 +121,17 @@ def voxel_vit_logits(sd, x, backbone, cell, patch, pos_embedding="default"):
     return F.linear(f, sd["voxel_head.weight"], sd["voxel_head.bias"])
 
 
+def voxel_vit_forward_images(sd, x, backbone, patch=16):
+    """Feature3D_ViT2D_V2.forward_images (vit_3d_2d_pretrain.py:435-451): the 2-D DeiT path through the SAME blocks --
+    timm PatchEmbed (Conv2d k = s = 16, flatten(2).transpose(1, 2)), cls token, + pos_embed, blocks, norm, head(x[:, 0])."""
+    cfg = BACKBONES[backbone]
+    B = x.shape[0]
+    t = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=patch).flatten(2).transpose(1, 2)
+    t = torch.cat((sd["cls_token"].expand(B, -1, -1), t), dim=1) + sd["pos_embed"]
+    f = encoder(sd, t, cfg["depth"], cfg["num_heads"])[:, 0]
+    return F.linear(f, sd["head.weight"], sd["head.bias"])
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # point grouping (data/pointnet_util.py) -- integer work in numpy, ordering contract = ascending (distance, index)
 # ----------------------------------------------------------------------------------------------------------------
@@ -324,6 +335,31 @@ def init_voxel_state_dict(backbone, cell, patch, n_classes, pos_embedding, seed=
             sd[f"group_embed.{n}.weight"] = torch.ones(D)
             sd[f"group_embed.{n}.bias"] = torch.zeros(D)
     return sd
+
+
+def init_image_branch_state_dict(backbone, seed=19, img=224, patch=16, n_classes=1000):
+    """The 2-D image branch of Feature3D_ViT2D_V2 (pos_embed, patch_embed.proj, head: timm VisionTransformer members,
+    Appendix A) -- a separate generator so the voxel fixtures' weight stream is unchanged."""
+    g = torch.Generator().manual_seed(seed)
+    D = BACKBONES[backbone]["embed_dim"]
+    k = 3 * patch * patch
+    return {"pos_embed": (torch.randn(1, (img // patch) ** 2 + 1, D, generator=g) * 0.02).clamp_(-2, 2),
+            "patch_embed.proj.weight": (torch.rand(D, 3, patch, patch, generator=g) * 2 - 1) / math.sqrt(k),
+            "patch_embed.proj.bias": (torch.rand(D, generator=g) * 2 - 1) / math.sqrt(k),
+            "head.weight": (torch.randn(n_classes, D, generator=g) * 0.02).clamp_(-2, 2),
+            "head.bias": torch.zeros(n_classes)}
+
+
+def sharpen_point_state_dict(sd, qkv_gain=4.0, head_gain=12.0):
+    """Fixture variant with non-trivial logits and attention: at the reference's init the point models have |logit| < 0.08
+    and near-uniform attention (trunc_normal std .02 everywhere), which makes an absolute 1e-2 tolerance toothless.
+    Scaling the qkv weights (scores x gain^2) and the head puts |logit| ~ 1 and spreads the softmax."""
+    out = dict(sd)
+    for k in sd:
+        if k.endswith("attn.qkv.weight"):
+            out[k] = sd[k] * qkv_gain
+    out["head.weight"] = sd["head.weight"] * head_gain
+    return out
 
 
 def init_point_state_dict(backbone, input_dim, n_classes, seed=9):

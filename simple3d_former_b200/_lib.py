@@ -112,9 +112,19 @@ def stream() -> int:
 
 
 def _need_cuda(*ts):
+    """Every kernel is enqueued on the CURRENT device's current stream (see stream()): tensors must be CUDA tensors of
+    that device, otherwise the launch would hand foreign pointers to the wrong GPU."""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("simple3d_former_b200 ops need CUDA tensors (no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"tensor on {t.device} but the current CUDA device is cuda:{cur}: call "
+                               "torch.cuda.set_device() (one process per GPU) before using simple3d_former_b200")
 
 
 def call(name: str, *args) -> None:
@@ -206,6 +216,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dres=None, want_bf16=False, dgamm
 
 def attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale, drop_seed=None, drop_site=0, drop_p=0.0):
     """drop_seed: int32 CUDA tensor [1] (device-resident seed) enabling attention-probability dropout with rate drop_p."""
+    _need_cuda(out, lse, drop_seed)
     call("s3d_attn_fwd", ptr(q) if hasattr(q, "data_ptr") else q, ptr(k) if hasattr(k, "data_ptr") else k,
          ptr(v) if hasattr(v, "data_ptr") else v, ptr(out), ptr(lse), B, H, N, dh, qs[0], qs[1], qs[2], os_[0], os_[1],
          os_[2], float(scale), ptr(drop_seed), int(drop_site), float(drop_p), stream())
@@ -213,6 +224,7 @@ def attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale, drop_seed=None, dro
 
 def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, B, H, N, dh, qs, os_, scale, drop_seed=None, drop_site=0,
              drop_p=0.0):
+    _need_cuda(out, dout, lse, delta, drop_seed)
     call("s3d_attn_bwd", q, k, v, ptr(out), ptr(dout), ptr(lse), ptr(delta), dq, dk, dv, B, H, N, dh, qs[0], qs[1],
          qs[2], os_[0], os_[1], os_[2], float(scale), ptr(drop_seed), int(drop_site), float(drop_p), stream())
 

@@ -34,7 +34,11 @@ PRETRAINED_URLS = {
     'deit_small_patch16_224': "https://dl.fbaipublicfiles.com/deit/deit_small_patch16_224-cd65a155.pth",
     'deit_base_patch16_224': "https://dl.fbaipublicfiles.com/deit/deit_base_patch16_224-b5f2ef4d.pth",
     'deit_base_distilled_patch16_224': "https://dl.fbaipublicfiles.com/deit/deit_base_distilled_patch16_224-df68dfff.pth",
+    # a LOCAL file in the reference (jax -> PyTorch conversion of ViT-B/16 21k), vit_3d_2d_pretrain.py:331, models/3DViT/model.py:196
+    'vit_base_patch16_224_21k': "./3rd_party/ViT-PyTorch/jax_to_pytorch/weights/B_16.pth",
 }
+# options the reference's scripts expose that are NOT on the hot path named by north_star (INTEGRATION.md lists them)
+UNSUPPORTED_POS_EMBEDDINGS = ("no_embed", "weight_sharing")
 
 
 class _SelfAttnParams(nn.Module):
@@ -83,9 +87,29 @@ class GroupEmbedLayer(nn.Module):
                                      self.norm1.eps, self.dropout_p if drop else 0.0, self._drop_seed if drop else None)
 
 
+def remap_vit21k_keys(ckpt, depth=12):
+    """Key layout of the jax->PyTorch ViT-B/16 21k checkpoint -> timm 0.3.2 names (what the reference's `fit_dict`,
+    vit_3d_2d_pretrain.py:16-36, does): drop the `transformer.` prefix, `pwff` is `mlp`, and the separate
+    `attn.proj_{q,k,v}` Linear layers are stacked row-wise into timm's single `attn.qkv` ([q | k | v], Appendix A)."""
+    out = {}
+    for k, v in ckpt.items():
+        k = k.replace("pwff", "mlp")
+        out[k[len("transformer."):] if k.startswith("transformer.") else k] = v
+    for i in range(depth):
+        for kind in ("weight", "bias"):
+            parts = [out.pop(f"blocks.{i}.attn.proj_{c}.{kind}") for c in "qkv"]
+            out[f"blocks.{i}.attn.qkv.{kind}"] = torch.cat(parts, dim=0)
+    return out
+
+
 def _load_pretrained(model, url, distilled=False):
-    checkpoint = torch.hub.load_state_dict_from_url(url=url, map_location="cpu", check_hash=True)
-    pretrained = {k: v for k, v in checkpoint["model"].items() if k in model.state_dict()}
+    if url is None:
+        raise ValueError(f"no pretrained weights are known for backbone {model.transformer_backbone!r}")
+    if "21k" in model.transformer_backbone:  # local file, as in the reference (vit_3d_2d_pretrain.py:400-403)
+        source = remap_vit21k_keys(torch.load(url, map_location="cpu"))
+    else:
+        source = torch.hub.load_state_dict_from_url(url=url, map_location="cpu", check_hash=True)["model"]
+    pretrained = {k: v for k, v in source.items() if k in model.state_dict()}
     if distilled:
         pretrained['pos_embed'] = pretrained['pos_embed'][:, 1:, :]
     model.load_state_dict(pretrained, strict=False)
@@ -108,7 +132,8 @@ class Feature3D_ViT2D_V2(VisionTransformer):
             self.freeze_image_branch()
         self.voxel_embed = embed_layer
         if kwargs.get('head') == 'AMSoftmax':
-            raise NotImplementedError("AMSoftmax head is outside the hot path")
+            raise NotImplementedError("head='AMSoftmax' (vit_3d_2d_pretrain.py:39-74) is outside the hot path of this "
+                                      "implementation; use the default Linear head")
         self.voxel_head = nn.Linear(self.embed_dim, self.n_classes)
         self.pos_embed_type = pos_embedding
         if pos_embedding is None or pos_embedding == "default":
@@ -120,8 +145,11 @@ class Feature3D_ViT2D_V2(VisionTransformer):
             self.group_embed = GroupEmbedLayer(d_model=self.embed_dim, dim_feedforward=self.embed_dim, nhead=4)
             self.group_pos_embed = nn.Parameter(torch.zeros(1, self.voxel_embed.patch_size + 1, self.embed_dim))
             self.group_cls_token = nn.Parameter(torch.zeros(1, 1, self.embed_dim))
+        elif pos_embedding in UNSUPPORTED_POS_EMBEDDINGS:
+            raise NotImplementedError(f"pos_embedding={pos_embedding!r} is a reference option outside the hot path of "
+                                      "this implementation (supported: None / 'default', 'group_embed')")
         else:
-            raise ValueError("positional embedding scheme not on the hot path: %r" % (pos_embedding,))
+            raise ValueError("Unknown positional embedding scheme!")  # the reference's message (vit_3d_2d_pretrain.py:389)
 
     def freeze_image_branch(self):
         """head / pos_embed / patch_embed only serve forward_images; frozen as on the reference's pretrained path
@@ -199,8 +227,6 @@ class TransitionUp(nn.Module):
         self.fc2 = nn.Sequential(nn.Linear(dim2, dim_out), _SwapAxes(), nn.BatchNorm1d(dim_out), _SwapAxes(), nn.ReLU())
         self.fp = PointNetFeaturePropagation(-1, [])
 
-    fused = True  # class switch: False forces the PyTorch-op path (kernel-vs-torch parity tests)
-
     @staticmethod
     def _fc(seq, x):
         """Linear -> BatchNorm1d -> ReLU of the reference's Sequential as one fused node (GEMM + two HBM passes)."""
@@ -213,23 +239,52 @@ class TransitionUp(nn.Module):
         return y
 
     def forward(self, xyz1, points1, xyz2, points2):
-        """xyz1 [B,S,3] / points1 [B,S,dim1]: coarse level; xyz2 [B,N,3] / points2 [B,N,dim2]: fine level."""
-        fusable = self.fused and points1.is_cuda and xyz1.shape[1] > 1 and self.fc1[0].out_features % 8 == 0 and \
-            points1.shape[-1] % 8 == 0 and points2.shape[-1] % 8 == 0
-        if not fusable:
-            feats1 = self.fc1(points1)
-            feats2 = self.fc2(points2)
-            feats1 = self.fp(xyz2.transpose(1, 2), xyz1.transpose(1, 2), None, feats1.transpose(1, 2)).transpose(1, 2)
-            return feats1 + feats2
+        """xyz1 [B,S,3] / points1 [B,S,dim1]: coarse level; xyz2 [B,N,3] / points2 [B,N,dim2]: fine level.
+        There is no PyTorch-op path: shapes the kernels do not cover raise (every width the reference's backbones
+        produce -- multiples of 8 channels, more than one coarse point -- is covered)."""
+        if not points1.is_cuda:
+            raise RuntimeError("simple3d_former_b200 ops need CUDA tensors (no CPU fallback)")
+        if xyz1.shape[1] < 3 or self.fc1[0].out_features % 8 or points1.shape[-1] % 8 or points2.shape[-1] % 8:
+            raise NotImplementedError(
+                "TransitionUp: the sm_100a path needs >= 3 coarse points and channel counts that are multiples of 8 "
+                f"(got S={xyz1.shape[1]}, dims {points1.shape[-1]}/{points2.shape[-1]}/{self.fc1[0].out_features})")
         feats1 = self._fc(self.fc1, points1)
         feats2 = self._fc(self.fc2, points2)
         idx, dist = knn_point(3, xyz1.detach().contiguous(), xyz2.detach().contiguous(), return_dist=True)
         return Fn.ThreeNNInterpFn.apply(feats1, idx, dist, feats2)
 
 
-class _DeadPointEmbed(nn.Module):
-    """Stand-in for the reference's PointEmbed (models/3DViT/model.py:75-121): built in __init__, never called in
-    forward(). Only `parameters()` is ever touched, so an empty module keeps the attribute without the dead weights."""
+class _LocalOpParams(nn.Module):
+    """Parameter container with the names / shapes of the reference's Local_op (models/3DViT/model.py:75-94)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv1 = nn.Conv1d(in_channels, out_channels, kernel_size=1, bias=False)
+        self.conv2 = nn.Conv1d(out_channels, out_channels, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm1d(out_channels)
+        self.bn2 = nn.BatchNorm1d(out_channels)
+
+
+class PointEmbed(nn.Module):
+    """The reference's PointEmbed (models/3DViT/model.py:96-121) is built in __init__ (:227) and NEVER called in
+    forward(), but its weights are part of every reference checkpoint
+    (`patch_embed.{conv1,conv2,bn1,bn2,gather_local_0,gather_local_1}.*`) and train_cls.py:75 / train_partseg.py:80 load
+    them with strict=True. This keeps exactly those parameters and buffers (same names, shapes and init order) so
+    state dicts round-trip in both directions; there is no forward. The parameters never receive gradients and are
+    listed by `unused_parameter_names()` so the data-parallel trainer leaves them out of its buckets."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.conv1 = nn.Conv1d(cfg.input_dim, 64, kernel_size=1, bias=False)
+        self.conv2 = nn.Conv1d(64, 64, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(64)
+        self.gather_local_0 = _LocalOpParams(128, cfg.embed_dim // 4)
+        self.gather_local_1 = _LocalOpParams(256, cfg.embed_dim // 4)
+
+    def forward(self, x):
+        raise NotImplementedError("PointEmbed is dead code in the reference's forward (models/3DViT/model.py:310-319); "
+                                  "only its parameters are kept for checkpoint compatibility")
 
 
 class _PointTransformerBase(VisionTransformer):
@@ -249,7 +304,7 @@ class _PointTransformerBase(VisionTransformer):
         cfg.embed_dim = self.embed_dim
         if self.pretrained:
             _load_pretrained(self, self.url)
-        self.patch_embed = _DeadPointEmbed()
+        self.patch_embed = PointEmbed(cfg)
         if cfg.model.head == 'AMSoftmax':
             raise NotImplementedError("AMSoftmax head is outside the hot path")
         q = self.embed_dim // 4
@@ -273,7 +328,8 @@ class _PointTransformerBase(VisionTransformer):
 
     def unused_parameter_names(self):
         """Parameters that never receive a gradient (kept only for checkpoint compatibility)."""
-        return [n for n, _ in self.named_parameters() if n == "pos_embed" or "last_pos_embed" in n]
+        return [n for n, _ in self.named_parameters()
+                if n == "pos_embed" or "last_pos_embed" in n or n.startswith("patch_embed.")]
 
     def forward_features(self, x):
         xyz = x[..., :3].contiguous()

@@ -6,14 +6,13 @@ outputs are bit-exact with the reference on tie-free inputs (tie contract: ascen
 `PointNetSetAbstraction` with a two-layer MLP (the only shape the 3DViT models build) runs as
 `functional.SetAbstractionFn`: the grouped tensor [B,S,K,3+C] is never materialised, layer 1 is evaluated per point on
 the tensor cores and gathered, BatchNorm statistics / ReLU / the max over neighbours are fused passes
-(csrc/pointnet_fused.cu). Other layer counts keep their 1x1 conv + BatchNorm layers as PyTorch ops on top of the
-grouping kernels. The reference's dead second kNN (:233-235) and its torch.cuda.empty_cache() stalls (:115-127) are
+(csrc/pointnet_fused.cu). Configurations without a kernel (other layer counts, group_all, widths that are not multiples
+of 8) raise NotImplementedError -- there is no PyTorch-op path. The reference's dead second kNN (:233-235) and its torch.cuda.empty_cache() stalls (:115-127) are
 dropped.
 """
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib as L
 from . import functional as Fn
@@ -93,16 +92,32 @@ class PointNetSetAbstraction(nn.Module):
         self.last_pos_embed = nn.Sequential(nn.Linear(3, last), nn.ReLU(), nn.Linear(last, last))
         self.fps_start = None  # optional explicit FPS start indices (parity tests)
 
-    fused = True  # class switch: False forces the PyTorch-op MLP (used by the kernel-vs-torch parity tests)
-
-    def _fusable(self, xyz, points):
-        if not self.fused or self.group_all or points is None or len(self.mlp_convs) != 2 or not xyz.is_cuda:
-            return False
+    def _unsupported(self, xyz, points):
+        """Reason why this configuration has no sm_100a path (None when it has). The 3DViT models only ever build the
+        two-layer, kNN / ball-query grouped form with 8-aligned widths (models/3DViT/model.py:33-44)."""
+        if not xyz.is_cuda:
+            return "CUDA tensors required (no CPU fallback)"
+        if self.group_all:
+            return "group_all=True is not used by the 3DViT models and has no kernel"
+        if points is None:
+            return "points=None (xyz-only grouping) has no kernel"
+        if len(self.mlp_convs) != 2:
+            return f"{len(self.mlp_convs)}-layer MLP (the fused set abstraction implements the two-layer form)"
         c1, c2 = self.mlp_convs[0].out_channels, self.mlp_convs[1].out_channels
-        bns_ok = all(bn.track_running_stats and bn.affine and bn.momentum is not None for bn in self.mlp_bns)
-        return bns_ok and points.shape[-1] % 8 == 0 and c1 % 8 == 0 and c2 % 8 == 0 and self.nsample <= 32
+        if not all(bn.track_running_stats and bn.affine and bn.momentum is not None for bn in self.mlp_bns):
+            return "BatchNorm2d without running statistics / affine parameters / momentum"
+        if points.shape[-1] % 8 or c1 % 8 or c2 % 8:
+            return f"channel counts must be multiples of 8 (got {points.shape[-1]}, {c1}, {c2})"
+        if self.nsample > 32:
+            return f"nsample {self.nsample} > 32"
+        return None
 
-    def _forward_fused(self, xyz, points):
+    def forward(self, xyz, points):
+        """xyz [B,N,3], points [B,N,C] -> (new_xyz [B,S,3], new_points [B,S,C']). No PyTorch-op path: unsupported
+        configurations raise instead of dispatching elsewhere."""
+        why = self._unsupported(xyz, points)
+        if why is not None:
+            raise NotImplementedError("PointNetSetAbstraction: " + why)
         xyz = xyz.detach().contiguous().float()
         fps_idx = farthest_point_sample(xyz, self.npoint, self.fps_start)
         new_xyz = L.gather_rows(xyz, fps_idx)
@@ -119,19 +134,6 @@ class PointNetSetAbstraction(nn.Module):
                 n2.num_batches_tracked += 1
         return new_xyz, out
 
-    def forward(self, xyz, points):
-        if self._fusable(xyz, points):
-            return self._forward_fused(xyz, points)
-        if self.group_all:
-            new_xyz, new_points = sample_and_group_all(xyz, points)
-        else:
-            new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz, points, knn=self.knn,
-                                                   fps_start=self.fps_start)
-        new_points = new_points.permute(0, 3, 2, 1)  # [B, C+D, nsample, npoint]
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            new_points = F.relu(bn(conv(new_points)))
-        return new_xyz, torch.max(new_points, 2)[0].transpose(1, 2)
-
 
 class PointNetFeaturePropagation(nn.Module):
     def __init__(self, in_channel, mlp):
@@ -145,24 +147,20 @@ class PointNetFeaturePropagation(nn.Module):
             last = out_channel
 
     def forward(self, xyz1, xyz2, points1, points2):
-        """xyz1 [B,C,N], xyz2 [B,C,S], points1 [B,D,N] or None, points2 [B,D,S] -> [B,D',N] (3-NN interpolation)."""
-        xyz1 = xyz1.permute(0, 2, 1)
-        xyz2 = xyz2.permute(0, 2, 1)
-        points2 = points2.permute(0, 2, 1)
+        """xyz1 [B,C,N], xyz2 [B,C,S], points1 [B,D,N] or None, points2 [B,D,S] -> [B,D',N] (3-NN interpolation).
+        The 3DViT models build this with an empty MLP (models/3DViT/model.py:62) -- the only form implemented."""
+        if len(self.mlp_convs):
+            raise NotImplementedError("PointNetFeaturePropagation with a conv MLP is not used by the 3DViT models and "
+                                      "has no sm_100a path")
+        xyz1 = xyz1.permute(0, 2, 1).contiguous()
+        xyz2 = xyz2.permute(0, 2, 1).contiguous()
+        points2 = points2.permute(0, 2, 1).contiguous()
         B, N, _ = xyz1.shape
         S = xyz2.shape[1]
-        if S == 1:
-            interpolated = points2.repeat(1, N, 1)
-        else:
-            idx, dists = knn_point(3, xyz2.contiguous(), xyz1.contiguous(), return_dist=True)  # queries = xyz1
-            recip = 1.0 / (dists + 1e-8)
-            weight = recip / torch.sum(recip, dim=2, keepdim=True)
-            interpolated = torch.sum(index_points(points2, idx) * weight.view(B, N, 3, 1), dim=2)
+        if S < 3:
+            raise NotImplementedError("PointNetFeaturePropagation needs >= 3 source points")
+        idx, dists = knn_point(3, xyz2, xyz1, return_dist=True)  # queries = xyz1
+        interpolated = Fn.ThreeNNInterpFn.apply(points2, idx, dists, None)
         if points1 is not None:
-            new_points = torch.cat([points1.permute(0, 2, 1), interpolated], dim=-1)
-        else:
-            new_points = interpolated
-        new_points = new_points.permute(0, 2, 1)
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            new_points = F.relu(bn(conv(new_points)))
-        return new_points
+            interpolated = torch.cat([points1.permute(0, 2, 1), interpolated], dim=-1)
+        return interpolated.permute(0, 2, 1)

@@ -102,6 +102,9 @@ class Block(nn.Module):
     def _fusable(self):
         if not (isinstance(self.norm1, nn.LayerNorm) and isinstance(self.norm2, nn.LayerNorm)):
             return False
+        if self.training and (self.attn.attn_drop.p > 0 or self.attn.proj_drop.p > 0 or self.mlp.drop.p > 0):
+            # every reference backbone uses rate 0; never train silently without the dropout
+            raise NotImplementedError("Block with attn_drop / proj_drop / mlp drop > 0 is not implemented")
         if isinstance(self.drop_path, DropPath) and self.training and self.drop_path.drop_prob:
             return False
         # forward hooks on sub-modules (e.g. the reference's attention visualiser hooks blocks[i].attn) need the

@@ -17,7 +17,8 @@ def _voxel_sd(fix):
     return sd
 
 
-@pytest.mark.parametrize("name", ["cfg1_deit_small_voxel30", "cfg3_small_deit_base_group36", "cfg3_deit_base_group128"])
+@pytest.mark.parametrize("name", ["cfg1_deit_small_voxel30", "cfg3_small_deit_base_group36", "cfg3_deit_base_group128",
+                                  "cfg3_deit_base_group128_b3"])
 def test_voxel_models_match_reference(golden, name):
     fix = golden(name)
     sd = {k: v.requires_grad_(True) for k, v in _voxel_sd(fix).items()}
@@ -34,11 +35,26 @@ def test_voxel_models_match_reference(golden, name):
         assert torch.allclose(g.flatten()[:16], ref["head"], atol=1e-6 + 1e-3 * float(ref["head"].abs().max())), k
 
 
-@pytest.mark.parametrize("name", ["cfg4_point_cls_tiny1024", "cfg5_point_seg_tiny2048"])
+def test_forward_images_matches_reference(golden):
+    """Feature3D_ViT2D_V2.forward_images (vit_3d_2d_pretrain.py:435-451), SURVEY.md section 8 row a13."""
+    fix = golden("cfg1_forward_images")
+    sd = O.init_voxel_state_dict(fix["backbone"], 6, 5, 40, "default", seed=fix["weight_seed"])
+    sd.update(O.init_image_branch_state_dict(fix["backbone"], seed=fix["image_seed"]))
+    assert abs(O.state_dict_checksum(sd) - fix["sd_checksum"]) <= 1e-6 * abs(fix["sd_checksum"])
+    x = torch.randn(fix["B"], 3, 224, 224, generator=torch.Generator().manual_seed(fix["input_seed"]))
+    with torch.no_grad():
+        logits = O.voxel_vit_forward_images(sd, x, fix["backbone"])
+    assert torch.allclose(logits, fix["logits"], atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["cfg4_point_cls_tiny1024", "cfg5_point_seg_tiny2048", "cfg4_point_cls_tiny1024_sharp",
+                                  "cfg5_point_seg_tiny2048_sharp"])
 @pytest.mark.parametrize("mode", ["eval", "train"])
 def test_point_models_match_reference(golden, name, mode):
     fix = golden(name)
     sd = O.init_point_state_dict(fix["backbone"], fix["input_dim"], fix["n_classes"], seed=fix["weight_seed"])
+    if fix.get("sharp"):
+        sd = O.sharpen_point_state_dict(sd, head_gain=fix["head_gain"])
     assert abs(O.state_dict_checksum(sd) - fix["sd_checksum"]) <= 1e-6 * abs(fix["sd_checksum"])
     x, _ = O.synthetic_points(fix["B"], fix["N"], extra=fix["input_dim"] - 3, seed=fix["input_seed"], n_classes=fix["n_classes"])
     starts = [s.numpy() for s in fix["fps_starts"]]

@@ -63,6 +63,35 @@ def _sa_reference(sa, xyz, pts, training):
     return torch.max(y2, 2)[0].transpose(1, 2)
 
 
+def _sa_unfused(sa, xyz, pts):
+    """The module as the reference writes it (data/pointnet_util.py:220-244): plain fp32 PyTorch ops through the module's
+    own Conv2d / BatchNorm2d children (so `sa`'s running statistics are updated like the reference's would be)."""
+    from simple3d_former_b200 import pointnet_util as P
+    B = xyz.shape[0]
+    bi = torch.arange(B, device=xyz.device)
+    fps_idx = P.farthest_point_sample(xyz, sa.npoint, sa.fps_start)
+    new_xyz = xyz[bi[:, None], fps_idx]
+    idx = P.knn_point(sa.nsample, xyz, new_xyz)
+    x = torch.cat([xyz[bi[:, None, None], idx] - new_xyz[:, :, None], pts[bi[:, None, None], idx]], dim=-1)
+    x = x.permute(0, 3, 2, 1)
+    for conv, bn in zip(sa.mlp_convs, sa.mlp_bns):
+        x = F.relu(bn(conv(x)))
+    return new_xyz, torch.max(x, 2)[0].transpose(1, 2)
+
+
+def _tu_unfused(tu, xyz1, p1, xyz2, p2):
+    """models/3DViT/model.py:47-72 through the module's own Sequential children (plain fp32 PyTorch ops)."""
+    from simple3d_former_b200 import pointnet_util as P
+    f1, f2 = tu.fc1(p1), tu.fc2(p2)
+    B = xyz2.shape[0]
+    dd, ii = P.square_distance(xyz2, xyz1).sort(dim=-1)
+    dd, ii = dd[:, :, :3], ii[:, :, :3]
+    rec = 1.0 / (dd + 1e-8)
+    wgt = rec / rec.sum(dim=2, keepdim=True)
+    bi = torch.arange(B, device=xyz2.device)
+    return (f1[bi[:, None, None], ii] * wgt[..., None]).sum(dim=2) + f2
+
+
 def _tu_reference(tu, xyz1, p1, xyz2, p2, training):
     """models/3DViT/model.py:33-72 + pointnet_util.py:381-420 in fp32 torch ops (bf16-rounded GEMM operands)."""
     from simple3d_former_b200 import pointnet_util as P
@@ -113,14 +142,13 @@ def test_set_abstraction_fused_matches_torch(dims, training):
     sa = sa.to(dev).train(training)
     sa.fps_start = torch.zeros(B, dtype=torch.long, device=dev)
     ref = copy.deepcopy(sa)
-    ref.fused = False
     xyz = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
     pts = torch.randn(B, N, Cf, generator=g).to(dev)
     pa, pb = pts.clone().requires_grad_(True), pts.clone().requires_grad_(True)
     w = torch.randn(B, S, C, generator=g).to(dev)
     xa, ya = sa(xyz, pa)
-    with torch.no_grad():  # module-level check against the unfused fp32 PyTorch-op path (also updates ref's buffers)
-        xb, yb32 = ref(xyz, pts)
+    with torch.no_grad():  # the layer as the reference writes it, in fp32 PyTorch ops (also updates ref's buffers)
+        xb, yb32 = _sa_unfused(ref, xyz, pts)
     assert torch.equal(xa, xb)
     assert ya.shape == yb32.shape == (B, S, C)
     assert _rel(ya, yb32) < 2e-2, _rel(ya, yb32)
@@ -176,7 +204,6 @@ def test_transition_up_fused_matches_torch(training):
     _randomize_bn(tu, g)
     tu = tu.to(dev).train(training)
     ref = copy.deepcopy(tu)
-    ref.fused = False
     xyz2 = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
     xyz1 = xyz2[:, :S].contiguous()
     p1 = torch.randn(B, S, d1, generator=g).to(dev)
@@ -185,8 +212,8 @@ def test_transition_up_fused_matches_torch(training):
     b1, b2 = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
     w = torch.randn(B, N, do, generator=g).to(dev)
     ya = tu(xyz1, a1, xyz2, a2)
-    with torch.no_grad():  # unfused fp32 PyTorch-op path of the same module (also updates ref's buffers)
-        yb32 = ref(xyz1, p1, xyz2, p2)
+    with torch.no_grad():  # the layer as the reference writes it, in fp32 PyTorch ops (also updates ref's buffers)
+        yb32 = _tu_unfused(ref, xyz1, p1, xyz2, p2)
     assert ya.shape == yb32.shape == (B, N, do)
     assert _rel(ya, yb32) < 2e-2, _rel(ya, yb32)
     yb = _tu_reference(ref, xyz1, b1, xyz2, b2, training)
