@@ -119,8 +119,9 @@ def test_point_model_matches_reference(golden, name, mode):
     # At the reference's init the point models have near-uniform attention, so the softmax gradient P*(dP - sum(P*dP))
     # is a difference of nearly equal numbers and bf16 operand rounding is amplified (up to 5.7 % on the L2 norm of
     # blocks.0.attn.qkv.weight.grad): those two fixtures keep 8 %; the sharpened fixtures are held to 3 %.
-    # The seg model discards the cls token output, so that gradient is ~1e-6 and pure rounding noise.
-    _check_grads(model, fix[mode]["grads"], rel=3e-2 if fix.get("sharp") else 8e-2, skip=("cls_token",) if fix["seg"] else ())
+    # Both point models discard the cls token's output row (models/3DViT/model.py:322, :519: `x = x[:, 1:]`), so its
+    # gradient only arrives through the other tokens' attention to it: ~1e-6 and dominated by rounding noise -> skipped.
+    _check_grads(model, fix[mode]["grads"], rel=3e-2 if fix.get("sharp") else 8e-2, skip=("cls_token",))
 
 
 def test_forward_images_matches_reference(golden):
