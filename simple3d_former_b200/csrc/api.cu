@@ -101,11 +101,10 @@ static s3d::AttnParams make_attn(const void* q, const void* k, const void* v, in
 static int set_dropout(s3d::AttnParams& p, const uint32_t* seed, uint32_t site, float prob) {
   if (seed == nullptr || prob <= 0.f) return 0;
   if (prob >= 1.f) return s3d::S3D_ERR_BAD_SHAPE;
-  const float t = prob * 65536.0f + 0.5f;
   p.drop_seed = seed;
   p.drop_site = site;
-  p.drop_thresh16 = t >= 65535.f ? 65535u : (uint32_t)t;
-  p.drop_scale = 1.0f / (1.0f - (float)p.drop_thresh16 / 65536.0f);
+  p.drop_thresh14 = s3d::drop_thresh14(prob);
+  p.drop_scale = s3d::drop_keep_scale(p.drop_thresh14);
   return 0;
 }
 

@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_small_kernel(const AttnP
 // ------------------------------------------------------------------------------------------------
 static int check_attn(const AttnParams& p, int DH) {
   if (p.B <= 0 || p.H <= 0 || p.N <= 0) return S3D_ERR_BAD_SHAPE;
-  if (DH != 64 && DH != 192 && DH != 256) return S3D_ERR_UNSUPPORTED;
+  if (DH != 64 && DH != 192 && DH != 256 && !attn_tc_supported(DH)) return S3D_ERR_UNSUPPORTED;
   if (p.qkv_rs % 8 || p.qkv_hs % 8 || p.qkv_bs % 8 || p.o_rs % 8 || p.o_hs % 8 || p.o_bs % 8) return S3D_ERR_ALIGNMENT;
   return S3D_OK;
 }
@@ -991,11 +991,11 @@ int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream) {
   if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.out == nullptr) return S3D_ERR_NULL;
   // long sequences run on the tcgen05 / TMEM flash kernel; everything else on the warp-level mma.sync kernels
   static const bool tc_enabled = []() { const char* v = getenv("S3D_ATTN_TC"); return v == nullptr || v[0] != '0'; }();
-  if (p.drop_seed != nullptr) {  // attention-probability dropout lives in the tcgen05 kernels only
-    if (DH != 192 && DH != 64) return S3D_ERR_UNSUPPORTED;
-    return attn_fwd_tc(p, DH, stream);
-  }
-  if (tc_enabled && (DH == 192 || DH == 64) && p.N >= 512) {
+  // attention-probability dropout and the head dimensions 48 / 96 (group_embed of deit_tiny / deit_small) live in the
+  // tcgen05 kernels only
+  const bool tc_only = p.drop_seed != nullptr || (DH != 64 && DH != 192 && DH != 256);
+  if (tc_only) return attn_tc_supported(DH) ? attn_fwd_tc(p, DH, stream) : S3D_ERR_UNSUPPORTED;
+  if (tc_enabled && attn_tc_supported(DH) && p.N >= 512) {
     const int rc_tc = attn_fwd_tc(p, DH, stream);
     if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;
   }
@@ -1013,11 +1013,9 @@ int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream) {
       p.dk == nullptr || p.dv == nullptr || p.lse == nullptr || p.delta == nullptr)
     return S3D_ERR_NULL;
   static const bool tc_enabled = []() { const char* v = getenv("S3D_ATTN_TC"); return v == nullptr || v[0] != '0'; }();
-  if (p.drop_seed != nullptr) {
-    if (DH != 192 && DH != 64) return S3D_ERR_UNSUPPORTED;
-    return attn_bwd_tc(p, DH, stream);
-  }
-  if (tc_enabled && (DH == 192 || DH == 64) && p.N >= 512) {
+  const bool tc_only = p.drop_seed != nullptr || (DH != 64 && DH != 192 && DH != 256);
+  if (tc_only) return attn_tc_supported(DH) ? attn_bwd_tc(p, DH, stream) : S3D_ERR_UNSUPPORTED;
+  if (tc_enabled && attn_tc_supported(DH) && p.N >= 512) {
     const int rc_tc = attn_bwd_tc(p, DH, stream);
     if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;
   }

@@ -1,16 +1,30 @@
-// Flash attention forward on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) for long sequences -- the group_embed
-// layer of the reference (nn.TransformerEncoderLayer over S = B*196 = 12544 tokens, dh = 192, vit_3d_2d_pretrain.py:381,479),
-// which the reference evaluates by materialising 15*4 score matrices of S x S fp32 (37.8 GB).
+// Flash attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) for long sequences -- the group_embed layer of the
+// reference (nn.TransformerEncoderLayer over S = B*196 = 12544 tokens, dh = E/4, vit_3d_2d_pretrain.py:381,479), which the
+// reference evaluates by materialising 15*4 score matrices of S x S fp32 (37.8 GB).
 //
-// One CTA owns TWO 128-row query tiles (A, B) of one (batch, head) and streams 64-key K/V tiles through a 2-stage TMA
-// ring. Per tile and K/V block:   S = Q K^T  (tcgen05.mma M128 N64 K16 x DH/16, accumulator in TMEM)
-//                                 P = exp2(S*c - m)  (softmax warps: tcgen05.ld -> registers -> bf16 -> swizzled smem)
-//                                 O += P V   (tcgen05.mma M128 N=DH K16 x 4, V read as an MN-major B operand, O in TMEM)
-// The two tiles ping-pong: while the softmax warps of tile A work on S_A, the tensor core runs S_B / P_B V, so the MMA
-// pipe stays busy. Running maxima are updated lazily (rescale O only when the max grew by more than 2^8), which keeps the
-// TMEM read-modify-write of O off the critical path; row sums absorb the rest exactly.
+// Forward: one CTA owns TWO 128-row query tiles (A, B) of one (batch, head) and streams 64-key K/V tiles through a
+// 2-stage TMA ring. Per tile and K/V block:
+//     S = Q K^T              tcgen05.mma M128 N64 K16 x DH/16, accumulator in TMEM
+//     P = exp2(S*c - m)      softmax warps: tcgen05.ld -> registers -> bf16 -> 128B-swizzled smem
+//     O += P V               tcgen05.mma M128 N=DH K16 x 4, V read as an MN-major B operand, O in TMEM
+// The two tiles ping-pong: while the softmax warps of tile A work on S_A, the tensor core runs S_B / P_B V. Running
+// maxima are updated lazily (O is rescaled only when the max grew by more than 2^8; the row sums absorb the rest exactly).
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = softmax of tile A, warps 6-9 = tile B.
 // TMEM (512 columns): O_A [0,DH)  O_B [DH,2DH)  S_A [2DH, 2DH+64)  S_B [2DH+64, 2DH+128).
+//
+// The element-wise warps are what paces these kernels (ncu, round 1: 16 issued instructions per score element with
+// dropout, ALU pipe 120 % and XU pipe 95 % of the MMA time, 20 % of all issued instructions in mbarrier spin loops), so
+// their loops are written for instruction count, per pipe:
+//   * scale / subtract / row-sum / dS arithmetic on packed fp32 pairs (FFMA2 / FADD2 / FMUL2), 3-input max (FMNMX3);
+//   * every exponential on MUFU.EX2 and nothing else on the XU pipe (the former polynomial path used floorf + float->int
+//     conversions, which also issue on the XU pipe);
+//   * dropout masks from a 5-instruction pair hash whose two 14-bit draws are compared by ONE half2 instruction
+//     (common.cuh); the words of the NEXT block are computed after the current block's hand-over, i.e. while the tensor
+//     core works, so they are off the S -> P critical path;
+//   * mbarrier waits park the warp (try_wait with a suspend-time hint) instead of spinning.
+// Head dimensions: any multiple of 16 up to 192 fits the TMEM / shared-memory budget; 48, 64, 96, 192 are instantiated
+// (group_embed uses nhead = 4: deit_tiny 48, deit_small 96, deit_base 192). Operand rows are loaded in 64-column TMA
+// boxes; for DH % 64 != 0 the tail box carries columns of the neighbouring head that no MMA ever reads.
 #include "kernels.h"
 
 namespace s3d {
@@ -22,8 +36,10 @@ constexpr float kFaLog2e = 1.4426950408889634f;
 
 template <int DH>
 struct FaCfg {
-  static constexpr int kQBytes = kFaBM * DH * 2;          // per query tile
-  static constexpr int kKVBytes = kFaBN * DH * 2;         // K or V block
+  static_assert(DH % 16 == 0 && DH >= 16 && DH <= 192, "head_dim must be a multiple of 16, at most 192");
+  static constexpr int kCh = (DH + 63) / 64;              // 64-column (128-byte) chunks per operand row
+  static constexpr int kQBytes = kFaBM * kCh * 128;       // per query tile
+  static constexpr int kKVBytes = kFaBN * kCh * 128;      // K or V block
   static constexpr int kPBytes = kFaBM * kFaBN * 2;       // P tile (bf16)
   static constexpr int kSmemBytes = 2 * kQBytes + 4 * kKVBytes + 2 * kPBytes + 1024 + 256;
   static constexpr int kTmemCols = 512;
@@ -40,19 +56,25 @@ struct FaParams {
   long long o_bs, o_hs, o_rs;
   float scale;
   const uint32_t* drop_seed;  // attention-probability dropout: device seed (nullptr = off)
-  uint32_t drop_site, drop_thresh16;
+  uint32_t drop_site, drop_thresh14;
   float drop_scale;           // 1 / (1 - p)
 };
 
-template <int DH>
+// k-step kk (16 bf16 = 32 bytes) inside a [chunks][ROWS][128 B] K-major operand tile, as a descriptor-low-word increment
+template <int ROWS>
+__device__ __forceinline__ constexpr uint32_t kstep_off(int kk) {
+  return (uint32_t)(((kk >> 2) * (ROWS * 128) + (kk & 3) * 32) >> 4);
+}
+
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(kFaThreads, 1)
 fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const FaParams p) {
   using Cfg = FaCfg<DH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                  // [2][DH/64][128][128B]
-  uint8_t* sK = sQ + 2 * Cfg::kQBytes;                 // [2 stages][DH/64][64][128B]
-  uint8_t* sV = sK + 2 * Cfg::kKVBytes;                // [2 stages][DH/64][64][128B]
+  uint8_t* sQ = smem;                                  // [2][kCh][128][128B]
+  uint8_t* sK = sQ + 2 * Cfg::kQBytes;                 // [2 stages][kCh][64][128B]
+  uint8_t* sV = sK + 2 * Cfg::kKVBytes;                // [2 stages][kCh][64][128B]
   uint8_t* sP = sV + 2 * Cfg::kKVBytes;                // [2 tiles][128][128B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPBytes);
   uint64_t* q_full = bars;          // [2]
@@ -99,7 +121,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       for (int t = 0; t < 2; ++t) {
         mbar_expect_tx(&q_full[t], Cfg::kQBytes);
 #pragma unroll
-        for (int c = 0; c < DH / 64; ++c)
+        for (int c = 0; c < Cfg::kCh; ++c)
           tma_load_2d(sQ + t * Cfg::kQBytes + c * (kFaBM * 128), &tma_q, &q_full[t], cq + 64 * c, row_base + q0 + t * kFaBM);
       }
       for (int j = 0; j < nkv; ++j) {
@@ -107,11 +129,11 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], Cfg::kKVBytes);
 #pragma unroll
-        for (int c = 0; c < DH / 64; ++c)
+        for (int c = 0; c < Cfg::kCh; ++c)
           tma_load_2d(sK + st * Cfg::kKVBytes + c * (kFaBN * 128), &tma_kv, &k_full[st], ck + 64 * c, row_base + j * kFaBN);
         mbar_expect_tx(&v_full[st], Cfg::kKVBytes);
 #pragma unroll
-        for (int c = 0; c < DH / 64; ++c)
+        for (int c = 0; c < Cfg::kCh; ++c)
           tma_load_2d(sV + st * Cfg::kKVBytes + c * (kFaBN * 128), &tma_kv, &v_full[st], cv + 64 * c, row_base + j * kFaBN);
       }
     }
@@ -119,62 +141,59 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   } else if (warp == 1) {
     // ---------------------------------------------- MMA issuer ----------------------------------------------
     // The whole warp runs the control flow (waits are warp-uniform); one elected lane issues. Descriptor low words are
-    // precomputed so each tcgen05.mma costs a couple of integer adds (at N = 64 an MMA lasts only ~40 cycles, so the
+    // precomputed so each tcgen05.mma costs a couple of integer adds (at N = 64 an MMA lasts only ~32 cycles, so the
     // issue path must stay far below that).
-    {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kFaBM, kFaBN, 0, 0);  // S = Q K^T : both K-major
-      constexpr uint32_t idesc_o = make_idesc_bf16(kFaBM, DH, 0, 1);     // O = P V   : V is MN-major
-      constexpr uint32_t hi = smem_desc_hi_sw128(1024);
-      const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16), k_lo = smem_desc_lo(smem_u32(sK), 16);
-      const uint32_t p_lo = smem_desc_lo(smem_u32(sP), 16), v_lo = smem_desc_lo(smem_u32(sV), kFaBN * 128);
-      auto issue_s = [&](int t, int st) {
-        const uint32_t a = q_lo + t * (Cfg::kQBytes >> 4), b = k_lo + st * (Cfg::kKVBytes >> 4);
-        const uint32_t d = tmem_base + Cfg::kColS + t * kFaBN;
-        if (elect_one()) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(kFaBM, kFaBN, 0, 0);  // S = Q K^T : both K-major
+    constexpr uint32_t idesc_o = make_idesc_bf16(kFaBM, DH, 0, 1);     // O = P V   : V is MN-major
+    constexpr uint32_t hi = smem_desc_hi_sw128(1024);
+    const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16), k_lo = smem_desc_lo(smem_u32(sK), 16);
+    const uint32_t p_lo = smem_desc_lo(smem_u32(sP), 16), v_lo = smem_desc_lo(smem_u32(sV), kFaBN * 128);
+    auto issue_s = [&](int t, int st) {
+      const uint32_t a = q_lo + t * (Cfg::kQBytes >> 4), bb = k_lo + st * (Cfg::kKVBytes >> 4);
+      const uint32_t d = tmem_base + Cfg::kColS + t * kFaBN;
+      if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < DH / 16; ++kk)
-            umma_f16_ss2(d, a + (((kk >> 2) * (kFaBM * 128) + (kk & 3) * 32) >> 4), hi,
-                         b + (((kk >> 2) * (kFaBN * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
-          umma_commit(&s_full[t]);
-        }
-        __syncwarp();
-      };
-      auto issue_pv = [&](int t, int st, int j, uint64_t* done0, uint64_t* done1) {
-        const uint32_t a = p_lo + t * (Cfg::kPBytes >> 4), b = v_lo + st * (Cfg::kKVBytes >> 4);
-        const uint32_t d = tmem_base + t * DH;
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < kFaBN / 16; ++kk)
-            umma_f16_ss2(d, a + ((kk * 32) >> 4), hi, b + ((kk * 2048) >> 4), hi, idesc_o, (j > 0) || (kk != 0));
-          if (done0 != nullptr) umma_commit(done0);
-          if (done1 != nullptr) umma_commit(done1);
-        }
-        __syncwarp();
-      };
-      mbar_wait(&k_full[0], 0);
-      mbar_wait(&q_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      mbar_wait(&q_full[1], 0);
-      tc_fence_after();
-      issue_s(1, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = j & 1;
-        const bool last = (j + 1 == nkv);
-        mbar_wait(&v_full[st], (j >> 1) & 1);
-        if (!last) mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
-        // tile A
-        mbar_wait(&p_full[0], ph);
-        tc_fence_after();
-        issue_pv(0, st, j, last ? &o_full[0] : nullptr, nullptr);
-        if (!last) issue_s(0, st ^ 1);
-        // tile B (its P V is the last reader of K/V stage `st`: the commit frees the stage when those MMAs retire)
-        mbar_wait(&p_full[1], ph);
-        tc_fence_after();
-        issue_pv(1, st, j, &kv_empty[st], last ? &o_full[1] : nullptr);
-        if (!last) issue_s(1, st ^ 1);
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_f16_ss2(d, a + kstep_off<kFaBM>(kk), hi, bb + kstep_off<kFaBN>(kk), hi, idesc_s, kk != 0);
+        umma_commit(&s_full[t]);
       }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int t, int st, int j, uint64_t* done0, uint64_t* done1) {
+      const uint32_t a = p_lo + t * (Cfg::kPBytes >> 4), bb = v_lo + st * (Cfg::kKVBytes >> 4);
+      const uint32_t d = tmem_base + t * DH;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kFaBN / 16; ++kk)
+          umma_f16_ss2(d, a + ((kk * 32) >> 4), hi, bb + ((kk * 2048) >> 4), hi, idesc_o, (j > 0) || (kk != 0));
+        if (done0 != nullptr) umma_commit(done0);
+        if (done1 != nullptr) umma_commit(done1);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&k_full[0], 0);
+    mbar_wait(&q_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    mbar_wait(&q_full[1], 0);
+    tc_fence_after();
+    issue_s(1, 0);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = j & 1;
+      const bool last = (j + 1 == nkv);
+      mbar_wait(&v_full[st], (j >> 1) & 1);
+      if (!last) mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
+      // tile A
+      mbar_wait(&p_full[0], ph);
+      tc_fence_after();
+      issue_pv(0, st, j, last ? &o_full[0] : nullptr, nullptr);
+      if (!last) issue_s(0, st ^ 1);
+      // tile B (its P V is the last reader of K/V stage `st`: the commit frees the stage when those MMAs retire)
+      mbar_wait(&p_full[1], ph);
+      tc_fence_after();
+      issue_pv(1, st, j, &kv_empty[st], last ? &o_full[1] : nullptr);
+      if (!last) issue_s(1, st ^ 1);
     }
   } else {
     // ----------------------------------------------- softmax -----------------------------------------------
@@ -186,13 +205,19 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     const uint32_t o_addr = tmem_base + lane_addr + t * DH;
     uint8_t* prow = sP + t * Cfg::kPBytes + r * 128;
     const float c = p.scale * kFaLog2e;
+    const float2 c2 = make_float2(c, c);
     float m_ref = -INFINITY, l = 0.f;
     // dropout on the attention probabilities (MultiheadAttention(dropout=p) inside nn.TransformerEncoderLayer): P V uses
     // P o mask, the softmax normaliser the full row sum; mask element = (row (b*H + h)*N + query, column key)
-    const bool drop = p.drop_seed != nullptr;
-    const uint32_t drop_row = drop ? (drop_site_seed(*p.drop_seed, p.drop_site) ^
-                                      (((uint32_t)(b * p.H + h) * (uint32_t)p.N + (uint32_t)(q0 + t * kFaBM + r)) * kDropRowMul))
-                                   : 0u;
+    uint32_t mk[DROP ? 32 : 1];  // AND-masks of the 32 packed P pairs of the coming block
+    uint32_t ykey = 0, thresh2 = 0;
+    if (DROP) {
+      ykey = drop_rowkey(drop_site_seed(*p.drop_seed, p.drop_site),
+                         (uint32_t)(b * p.H + h) * (uint32_t)p.N + (uint32_t)(q0 + t * kFaBM + r));
+      thresh2 = p.drop_thresh14 * 0x00010001u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mk[i] = drop_andmask(drop_word(ykey + (uint32_t)i * kDropColMul), thresh2);
+    }
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
@@ -209,15 +234,16 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         for (int i = 0; i < 64; ++i)
           if (key0 + i >= p.N) s[i] = -INFINITY;
       }
-      float mx4[4] = {s[0], s[1], s[2], s[3]};  // 4 independent chains instead of one 64-long dependent chain
+      float mx4[4];  // 4 independent chains of 3-input maxima
 #pragma unroll
-      for (int i = 4; i < 64; i += 4) {
-        mx4[0] = fmaxf(mx4[0], s[i]);
-        mx4[1] = fmaxf(mx4[1], s[i + 1]);
-        mx4[2] = fmaxf(mx4[2], s[i + 2]);
-        mx4[3] = fmaxf(mx4[3], s[i + 3]);
+      for (int q = 0; q < 4; ++q) mx4[q] = fmax3(s[q * 16], s[q * 16 + 1], s[q * 16 + 2]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int i = 3; i < 15; i += 2) mx4[q] = fmax3(mx4[q], s[q * 16 + i], s[q * 16 + i + 1]);
+        mx4[q] = fmaxf(mx4[q], s[q * 16 + 15]);
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]);
       // lazy rescale: keep the reference max unless it grew by more than 2^8 (P stays <= 256, exact in the row sums)
       const bool need = (mx - m_ref) * c > 8.0f;
       if (__any_sync(0xffffffffu, need)) {
@@ -236,44 +262,38 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         }
         if (need) { l *= f; m_ref = mx; }
       }
-      const float mc = m_ref * c;
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float nmc = -m_ref * c;
+      const float2 nmc2 = make_float2(nmc, nmc);
+      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
-        float e[8];
+        uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xs = fmaf(s[ch * 8 + i], c, -mc);
-          e[i] = (i & 1) ? poly_exp2(xs) : fast_exp2(xs);  // half on MUFU, half on the FMA pipe
-          sum4[i & 3] += e[i];
+        for (int i = 0; i < 4; ++i) {
+          const float2 x = ffma2(make_float2(s[ch * 8 + 2 * i], s[ch * 8 + 2 * i + 1]), c2, nmc2);
+          const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+          if (i & 1) sum_b = fadd2(sum_b, e); else sum_a = fadd2(sum_a, e);
+          w[i] = pack_bf16x2(e.x, e.y);
+          if (DROP) w[i] &= mk[ch * 4 + i];
         }
-        if (drop) {
-          const uint32_t cp0 = (uint32_t)(key0 + ch * 8) >> 1;
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const uint32_t hsh = drop_mix(drop_row ^ ((cp0 + (i >> 1)) * kDropColMul));
-            if ((hsh & 0xffffu) < p.drop_thresh16) e[i] = 0.f;
-            if ((hsh >> 16) < p.drop_thresh16) e[i + 1] = 0.f;
-          }
-        }
-        uint4 u;
-        u.x = pack_bf16x2(e[0], e[1]);
-        u.y = pack_bf16x2(e[2], e[3]);
-        u.z = pack_bf16x2(e[4], e[5]);
-        u.w = pack_bf16x2(e[6], e[7]);
-        *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = u;
+        *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
+      if (DROP) {  // masks of block j + 1, computed while the tensor core runs P V / the next S
+        const uint32_t y0 = ykey + (uint32_t)((j + 1) * (kFaBN / 2)) * kDropColMul;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mk[i] = drop_andmask(drop_word(y0 + (uint32_t)i * kDropColMul), thresh2);
+      }
     }
     // epilogue: O / l -> bf16, lse
     mbar_wait(&o_full[t], 0);
     tc_fence_after();
     const int row = q0 + t * kFaBM + r;
-    const float inv = (drop ? p.drop_scale : 1.0f) / l;
+    const float inv = (DROP ? p.drop_scale : 1.0f) / l;
     __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)row * p.o_rs;
 #pragma unroll 1
     for (int cc = 0; cc < DH; cc += 32) {
@@ -283,12 +303,14 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       if (row < p.N) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + cc + i) = u;
+          if (cc + i < DH) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + cc + i) = u;
+          }
         }
       }
     }
@@ -308,7 +330,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 // Supported when q/k/v are slices of one row-major 2-D buffer: either the timm layout [B, N, 3, H, dh] (batch selects
 // rows) or the sequence-first layout [S, Nb, 3, H, dh] (batch selects columns). Returns S3D_ERR_UNSUPPORTED otherwise
 // so the caller can use the generic mma.sync kernel.
-template <int DH>
+template <int DH, bool DROP>
 static int fa_fwd_launch(const AttnParams& a, cudaStream_t stream) {
   using Cfg = FaCfg<DH>;
   const long long E = (long long)a.H * DH;
@@ -348,10 +370,10 @@ static int fa_fwd_launch(const AttnParams& a, cudaStream_t stream) {
   p.scale = a.scale;
   p.drop_seed = a.drop_seed;
   p.drop_site = a.drop_site;
-  p.drop_thresh16 = a.drop_thresh16;
+  p.drop_thresh14 = a.drop_thresh14;
   p.drop_scale = a.drop_scale;
   if ((a.o_rs % 8) || (a.o_hs % 8) || (a.o_bs % 8) || (reinterpret_cast<uintptr_t>(a.out) & 15)) return S3D_ERR_ALIGNMENT;
-  auto kern = fa_fwd_tc_kernel<DH>;
+  auto kern = fa_fwd_tc_kernel<DH, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -370,9 +392,11 @@ static int fa_fwd_launch(const AttnParams& a, cudaStream_t stream) {
 //          dS = P o (dP - delta) -> bf16 smem,  dQ += dS K  (K block re-read as an MN-major B operand)
 //   dKdV : CTA = 128 key rows; per 64-query block S^T = K Q^T, dP^T = V dO^T,  P^T / dS^T -> bf16 smem,
 //          dV += P^T dO,  dK += dS^T Q  (Q / dO blocks re-read as MN-major B operands)
+// A single-pass variant (S and dP computed once) would have to hold dK, dV (2 x DH columns), S^T, dP^T and a dQ partial
+// in TMEM at once -- 704 columns at dh = 192 against the 512 a CTA owns -- or push 48 KB of fp32 dQ partials per 128 x 64
+// tile through L2 reductions (~2.6 TB/s at the target rate); the two-kernel form stays and is made lean instead.
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 element-wise: a TMEM lane (= row) is shared by
-// two threads (warps w and w+4 reach the same lane quadrant), each handling 32 of the 64 columns of a block -- the
-// element-wise phase (exp2, dS, bf16 stores) is what paces these kernels, so it gets 8 warps.
+// two threads (warps w and w+4 reach the same lane quadrant), each handling 32 of the 64 columns of a block.
 // ================================================================================================
 struct FaBwdParams {
   __nv_bfloat16 *dq, *dk, *dv;  // outputs, qkv strides
@@ -385,7 +409,7 @@ struct FaBwdParams {
   long long qkv_bs, qkv_hs, qkv_rs;
   float scale;
   const uint32_t* drop_seed;  // attention-probability dropout (same mask as the forward kernel)
-  uint32_t drop_site, drop_thresh16;
+  uint32_t drop_site, drop_thresh14;
   float drop_scale;
 };
 
@@ -393,37 +417,33 @@ constexpr int kFaBwdThreads = 320;
 
 template <int DH>
 struct FaBwdCfg {
-  static constexpr int kTileBytes = 128 * DH * 2;   // 128-row operand tile
-  static constexpr int kBlkBytes = 64 * DH * 2;     // 64-row streamed block
-  static constexpr int kSBytes = 128 * 64 * 2;      // bf16 P / dS tile
-  static constexpr int kSmemBytes = 2 * kTileBytes + 4 * kBlkBytes + 2 * kSBytes + 1024 + 1024;
+  static constexpr int kCh = (DH + 63) / 64;
+  static constexpr int kTileBytes = 128 * kCh * 128;   // 128-row operand tile
+  static constexpr int kBlkBytes = 64 * kCh * 128;     // 64-row streamed block
+  static constexpr int kSBytes = 128 * 64 * 2;         // bf16 P / dS tile
+  static constexpr int kSmemBytes = 2 * kTileBytes + 4 * kBlkBytes + 2 * kSBytes + 1024 + 2048;
 };
 
 // 32 bf16 (half of a 128-byte row) into the 128B-swizzled tile: logical 16-byte chunks half*4 .. half*4+3 of row r
-__device__ __forceinline__ void store_half_row_bf16_sw128(uint8_t* row_base, int r, int half, const float (&e)[32]) {
+__device__ __forceinline__ void store_half_row_sw128(uint8_t* row_base, int r, int half, const uint32_t (&w)[16]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16x2(e[q * 8 + 0], e[q * 8 + 1]);
-    u.y = pack_bf16x2(e[q * 8 + 2], e[q * 8 + 3]);
-    u.z = pack_bf16x2(e[q * 8 + 4], e[q * 8 + 5]);
-    u.w = pack_bf16x2(e[q * 8 + 6], e[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(row_base + (((half * 4 + q) ^ (r & 7)) << 4)) = u;
-  }
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(row_base + (((half * 4 + q) ^ (r & 7)) << 4)) =
+        make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
 }
 
 // ------------------------------------------------ dQ ------------------------------------------------
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(kFaBwdThreads, 1)
 fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_constant__ CUtensorMap tma_kv64,
                     const __grid_constant__ CUtensorMap tma_do128, const FaBwdParams p) {
   using Cfg = FaBwdCfg<DH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                          // [DH/64][128][128B]
-  uint8_t* sdO = sQ + Cfg::kTileBytes;         // [DH/64][128][128B]
-  uint8_t* sK = sdO + Cfg::kTileBytes;         // [2][DH/64][64][128B]
-  uint8_t* sV = sK + 2 * Cfg::kBlkBytes;       // [2][DH/64][64][128B]
+  uint8_t* sQ = smem;                          // [kCh][128][128B]
+  uint8_t* sdO = sQ + Cfg::kTileBytes;         // [kCh][128][128B]
+  uint8_t* sK = sdO + Cfg::kTileBytes;         // [2][kCh][64][128B]
+  uint8_t* sV = sK + 2 * Cfg::kBlkBytes;       // [2][kCh][64][128B]
   uint8_t* sdS = sV + 2 * Cfg::kBlkBytes;      // [2][128][128B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * Cfg::kSBytes);
   uint64_t* qdo_full = bars;       // [1]
@@ -472,7 +492,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
     if (lane == 0) {
       mbar_expect_tx(qdo_full, 2 * Cfg::kTileBytes);
 #pragma unroll
-      for (int c = 0; c < DH / 64; ++c) {
+      for (int c = 0; c < Cfg::kCh; ++c) {
         tma_load_2d(sQ + c * (128 * 128), &tma_q128, qdo_full, cq + 64 * c, row_base + q0);
         tma_load_2d(sdO + c * (128 * 128), &tma_do128, qdo_full, co + 64 * c, o_row_base + q0);
       }
@@ -481,11 +501,11 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], Cfg::kBlkBytes);
 #pragma unroll
-        for (int c = 0; c < DH / 64; ++c)
+        for (int c = 0; c < Cfg::kCh; ++c)
           tma_load_2d(sK + st * Cfg::kBlkBytes + c * (64 * 128), &tma_kv64, &k_full[st], ck + 64 * c, row_base + j * 64);
         mbar_expect_tx(&v_full[st], Cfg::kBlkBytes);
 #pragma unroll
-        for (int c = 0; c < DH / 64; ++c)
+        for (int c = 0; c < Cfg::kCh; ++c)
           tma_load_2d(sV + st * Cfg::kBlkBytes + c * (64 * 128), &tma_kv64, &v_full[st], cv + 64 * c, row_base + j * 64);
       }
     }
@@ -504,12 +524,10 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          umma_f16_ss2(ds_, q_lo + (((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), hi,
-                       bk + (((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
+          umma_f16_ss2(ds_, q_lo + kstep_off<128>(kk), hi, bk + kstep_off<64>(kk), hi, idesc_s, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          umma_f16_ss2(dp_, do_lo + (((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), hi,
-                       bv + (((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
+          umma_f16_ss2(dp_, do_lo + kstep_off<128>(kk), hi, bv + kstep_off<64>(kk), hi, idesc_s, kk != 0);
         umma_commit(&sp_full[u]);
       }
       __syncwarp();
@@ -530,11 +548,11 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
       }
       mbar_wait(&ds_full[u], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t a = ds_lo + u * (Cfg::kSBytes >> 4), b = kmn_lo + st * (Cfg::kBlkBytes >> 4);
+      const uint32_t a = ds_lo + u * (Cfg::kSBytes >> 4), bb = kmn_lo + st * (Cfg::kBlkBytes >> 4);
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_f16_ss2(tmem_base, a + ((kk * 32) >> 4), hi, b + ((kk * 2048) >> 4), hi, idesc_q, (j > 0) || (kk != 0));
+          umma_f16_ss2(tmem_base, a + ((kk * 32) >> 4), hi, bb + ((kk * 2048) >> 4), hi, idesc_q, (j > 0) || (kk != 0));
         umma_commit(&kv_empty[st]);
         if (j + 1 == nkv) umma_commit(dq_full);
       }
@@ -547,13 +565,25 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
     const int row = q0 + r;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const long long bh = (long long)b * p.H + h;
-    const float lse2 = row < p.N ? p.lse[bh * p.N + row] * kFaLog2e : INFINITY;
-    const float del = row < p.N ? p.delta[bh * p.N + row] : 0.f;
+    // rows >= N (last query tile): lse = +inf -> P = 0 -> dS = 0 (those rows hold the next batch's data in the timm
+    // layout, zeros at the end of the buffer; they are never written back).
+    // keys >= N (last block): dS is zeroed explicitly below -- in the timm layout the K / V rows behind a batch's last key
+    // are the next batch's keys, not TMA zero fill.
+    const float nlse = row < p.N ? -p.lse[bh * p.N + row] * kFaLog2e : -INFINITY;
+    const float ndel = row < p.N ? -p.delta[bh * p.N + row] : 0.f;
     const float c = p.scale * kFaLog2e;
-    const bool drop = p.drop_seed != nullptr;  // dP = mask o (dO V^T) / (1 - p): regenerate the forward mask
-    const uint32_t drop_row = drop ? (drop_site_seed(*p.drop_seed, p.drop_site) ^
-                                      (((uint32_t)bh * (uint32_t)p.N + (uint32_t)row) * kDropRowMul))
-                                   : 0u;
+    const float2 c2 = make_float2(c, c), nlse2 = make_float2(nlse, nlse), ndel2 = make_float2(ndel, ndel);
+    const float ks = DROP ? p.drop_scale : 1.0f;  // dP = mask o (dO V^T) / (1 - p): regenerate the forward mask
+    const float2 ks2 = make_float2(ks, ks);
+    uint32_t z[DROP ? 16 : 1];
+    uint32_t ykey = 0, thresh2 = 0;
+    if (DROP) {
+      ykey = drop_rowkey(drop_site_seed(*p.drop_seed, p.drop_site), (uint32_t)bh * (uint32_t)p.N + (uint32_t)row) +
+             (uint32_t)(half * 16) * kDropColMul;
+      thresh2 = p.drop_thresh14 * 0x00010001u;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) z[i] = drop_word(ykey + (uint32_t)i * kDropColMul);
+    }
     for (int j = 0; j < nkv; ++j) {
       const int u = j & 1;
       mbar_wait(&sp_full[u], (j >> 1) & 1);
@@ -563,42 +593,53 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
       tmem_ld_32x32b_x32(s_addr, a0);
       tmem_ld_32x32b_x32(s_addr + 64, d0);
       tc_wait_ld();
-      float e[32];
-      const int key0 = j * 64 + half * 32;
+      uint32_t w[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x0 = fmaf(__uint_as_float(a0[i]), c, -lse2);
-        const float p0 = (key0 + i < p.N) ? ((i & 1) ? poly_exp2(x0) : fast_exp2(x0)) : 0.f;  // MUFU / FMA pipes alternate
-        float dpv = __uint_as_float(d0[i]);
-        if (drop) {
-          const uint32_t hsh = drop_mix(drop_row ^ (((uint32_t)(key0 + i) >> 1) * kDropColMul));  // CSE'd per pair
-          dpv = (((i & 1) ? (hsh >> 16) : (hsh & 0xffffu)) >= p.drop_thresh16) ? dpv * p.drop_scale : 0.f;
-        }
-        e[i] = p0 * (dpv - del);
+      for (int i = 0; i < 16; ++i) {
+        const float2 x = ffma2(make_float2(__uint_as_float(a0[2 * i]), __uint_as_float(a0[2 * i + 1])), c2, nlse2);
+        const float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        float2 dp = make_float2(__uint_as_float(d0[2 * i]), __uint_as_float(d0[2 * i + 1]));
+        if (DROP) drop_zero2(dp.x, dp.y, z[i], thresh2);
+        const float2 e = fmul2(pr, ffma2(dp, ks2, ndel2));
+        w[i] = pack_bf16x2(e.x, e.y);
       }
-      store_half_row_bf16_sw128(sdS + u * Cfg::kSBytes + r * 128, r, half, e);
+      if (j * 64 + 64 > p.N) {  // last, partial key block
+        const int key0 = j * 64 + half * 32;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (key0 + 2 * i >= p.N) w[i] = 0u;
+          else if (key0 + 2 * i + 1 >= p.N) w[i] &= 0xffffu;
+        }
+      }
+      store_half_row_sw128(sdS + u * Cfg::kSBytes + r * 128, r, half, w);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[u]);
+      if (DROP) {  // mask words of block j + 1, computed while the tensor core runs
+        const uint32_t y0 = ykey + (uint32_t)((j + 1) * 32) * kDropColMul;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = drop_word(y0 + (uint32_t)i * kDropColMul);
+      }
     }
     mbar_wait(dq_full, 0);
     tc_fence_after();
     __nv_bfloat16* orow = p.dq + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)row * p.qkv_rs;
+    // the two threads of a row split the DH columns in 16-column groups: even groups -> half 0, odd groups -> half 1
 #pragma unroll 1
-    for (int cc = half * (DH / 2); cc < (half + 1) * (DH / 2); cc += 32) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + cc, o);
+    for (int cc = half * 16; cc < DH; cc += 32) {
+      uint32_t o[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_addr + cc, o);
       tc_wait_ld();
       if (row < p.N) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[i]) * p.scale, __uint_as_float(o[i + 1]) * p.scale);
-          w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * p.scale, __uint_as_float(o[i + 3]) * p.scale);
-          w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * p.scale, __uint_as_float(o[i + 5]) * p.scale);
-          w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * p.scale, __uint_as_float(o[i + 7]) * p.scale);
-          *reinterpret_cast<uint4*>(orow + cc + i) = w;
+        for (int i = 0; i < 16; i += 8) {
+          uint4 wv;
+          wv.x = pack_bf16x2(__uint_as_float(o[i]) * p.scale, __uint_as_float(o[i + 1]) * p.scale);
+          wv.y = pack_bf16x2(__uint_as_float(o[i + 2]) * p.scale, __uint_as_float(o[i + 3]) * p.scale);
+          wv.z = pack_bf16x2(__uint_as_float(o[i + 4]) * p.scale, __uint_as_float(o[i + 5]) * p.scale);
+          wv.w = pack_bf16x2(__uint_as_float(o[i + 6]) * p.scale, __uint_as_float(o[i + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(orow + cc + i) = wv;
         }
       }
     }
@@ -612,17 +653,17 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
 }
 
 // ----------------------------------------------- dK, dV -----------------------------------------------
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(kFaBwdThreads, 1)
 fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid_constant__ CUtensorMap tma_q64,
                      const __grid_constant__ CUtensorMap tma_do64, const FaBwdParams p) {
   using Cfg = FaBwdCfg<DH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;                          // [DH/64][128][128B]
+  uint8_t* sK = smem;                          // [kCh][128][128B]
   uint8_t* sV = sK + Cfg::kTileBytes;
-  uint8_t* sQ = sV + Cfg::kTileBytes;          // [2][DH/64][64][128B]
-  uint8_t* sdO = sQ + 2 * Cfg::kBlkBytes;      // [2][DH/64][64][128B]
+  uint8_t* sQ = sV + Cfg::kTileBytes;          // [2][kCh][64][128B]
+  uint8_t* sdO = sQ + 2 * Cfg::kBlkBytes;      // [2][kCh][64][128B]
   uint8_t* sPT = sdO + 2 * Cfg::kBlkBytes;     // [128][128B]
   uint8_t* sdST = sPT + Cfg::kSBytes;          // [128][128B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdST + Cfg::kSBytes);
@@ -636,8 +677,9 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
   uint64_t* pds_free = bars + 10;  // [1] dV / dK MMAs that read P^T / dS^T retired
   uint64_t* acc_full = bars + 11;  // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  float* s_lse = reinterpret_cast<float*>(bars + 16);  // [2][64]
-  float* s_del = s_lse + 128;                          // [2][64]
+  float* s_nlse = reinterpret_cast<float*>(bars + 16);          // [2][64]  -lse * log2(e) of the block's queries
+  float* s_ndel = s_nlse + 128;                                 // [2][64]  -delta
+  uint32_t* s_rk = reinterpret_cast<uint32_t*>(s_ndel + 128);   // [2][64]  dropout row keys
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -678,7 +720,7 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * Cfg::kTileBytes);
 #pragma unroll
-      for (int c = 0; c < DH / 64; ++c) {
+      for (int c = 0; c < Cfg::kCh; ++c) {
         tma_load_2d(sK + c * (128 * 128), &tma_kv128, kv_full, ck + 64 * c, row_base + k0);
         tma_load_2d(sV + c * (128 * 128), &tma_kv128, kv_full, cv + 64 * c, row_base + k0);
       }
@@ -687,11 +729,11 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
         mbar_wait(&qdo_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&q_full[st], Cfg::kBlkBytes);
 #pragma unroll
-        for (int c = 0; c < DH / 64; ++c)
+        for (int c = 0; c < Cfg::kCh; ++c)
           tma_load_2d(sQ + st * Cfg::kBlkBytes + c * (64 * 128), &tma_q64, &q_full[st], cq + 64 * c, row_base + j * 64);
         mbar_expect_tx(&do_full[st], Cfg::kBlkBytes);
 #pragma unroll
-        for (int c = 0; c < DH / 64; ++c)
+        for (int c = 0; c < Cfg::kCh; ++c)
           tma_load_2d(sdO + st * Cfg::kBlkBytes + c * (64 * 128), &tma_do64, &do_full[st], co + 64 * c, o_row_base + j * 64);
       }
     }
@@ -710,12 +752,10 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          umma_f16_ss2(dst, k_lo + (((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), hi,
-                       bq + (((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
+          umma_f16_ss2(dst, k_lo + kstep_off<128>(kk), hi, bq + kstep_off<64>(kk), hi, idesc_s, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          umma_f16_ss2(ddp, v_lo + (((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), hi,
-                       bo + (((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), hi, idesc_s, kk != 0);
+          umma_f16_ss2(ddp, v_lo + kstep_off<128>(kk), hi, bo + kstep_off<64>(kk), hi, idesc_s, kk != 0);
         umma_commit(sp_full);
       }
       __syncwarp();
@@ -759,17 +799,41 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const long long bh = (long long)b * p.H + h;
     const float c = p.scale * kFaLog2e;
-    const bool drop = p.drop_seed != nullptr;  // this thread owns key column krow of the mask; queries vary along i
-    const uint32_t drop_col = drop ? (drop_site_seed(*p.drop_seed, p.drop_site) ^ (((uint32_t)krow >> 1) * kDropColMul)) : 0u;
-    const bool drop_hi = (krow & 1) != 0;
+    const float2 c2 = make_float2(c, c);
+    const float ks = DROP ? p.drop_scale : 1.0f;
+    const float2 ks2 = make_float2(ks, ks);
+    // dropout: this thread owns key column krow of the mask, the block's queries are the mask rows. Word of (query, krow >> 1)
+    // = drop_word(rowkey(query) + colterm); the draw is its low / high half for an even / odd key: one byte permute picks
+    // the halves of two consecutive queries into one word for the half2 comparison.
+    const uint32_t site_seed = DROP ? drop_site_seed(*p.drop_seed, p.drop_site) : 0u;
+    const uint32_t colterm = ((uint32_t)krow >> 1) * kDropColMul;
+    const uint32_t sel = (krow & 1) ? 0x7632u : 0x5410u;
+    const uint32_t thresh2 = p.drop_thresh14 * 0x00010001u;
+    uint32_t z[DROP ? 16 : 1];  // per query pair (2i, 2i+1) of this thread's 32 queries
+    auto stage = [&](int j) {   // lse / delta / row keys of query block j (padded queries: lse = +inf -> P = 0)
+      const int u = j & 1;
+      const int qi = j * 64 + (tid & 63);
+      if (tid < 64) s_nlse[u * 64 + tid] = qi < p.N ? -p.lse[bh * p.N + qi] * kFaLog2e : -INFINITY;
+      else if (tid < 128) s_ndel[u * 64 + (tid & 63)] = qi < p.N ? -p.delta[bh * p.N + qi] : 0.f;
+      else if (DROP && tid < 192) s_rk[u * 64 + (tid & 63)] = drop_rowkey(site_seed, (uint32_t)bh * (uint32_t)p.N + (uint32_t)qi);
+    };
+    auto make_words = [&](int j) {
+      const uint4* rk4 = reinterpret_cast<const uint4*>(s_rk + (j & 1) * 64 + half * 32);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 rk = rk4[g];
+        const uint32_t z0 = drop_word(rk.x + colterm), z1 = drop_word(rk.y + colterm);
+        const uint32_t z2 = drop_word(rk.z + colterm), z3 = drop_word(rk.w + colterm);
+        z[2 * g] = __byte_perm(z0, z1, sel);
+        z[2 * g + 1] = __byte_perm(z2, z3, sel);
+      }
+    };
+    stage(0);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (DROP) make_words(0);
     for (int j = 0; j < nq; ++j) {
       const int u = j & 1;
-      if (tid < 128) {  // stage lse / delta of this query block (padded queries: lse = +inf -> P = 0)
-        const int qi = j * 64 + (tid & 63);
-        if (tid < 64) s_lse[u * 64 + tid] = qi < p.N ? p.lse[bh * p.N + qi] * kFaLog2e : INFINITY;
-        else s_del[u * 64 + (tid & 63)] = qi < p.N ? p.delta[bh * p.N + qi] : 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (j + 1 < nq) stage(j + 1);  // buffer u^1: its last readers finished block j-1 before the barrier below of j-1
       mbar_wait(sp_full, j & 1);
       tc_fence_after();
       uint32_t a0[32], d0[32];
@@ -780,70 +844,59 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
-      float pt[32], ds[32];
-      const float* lrow = s_lse + u * 64 + half * 32;
-      const float* drow = s_del + u * 64 + half * 32;
+      uint32_t wp[16], wd[16];
+      const float2* lrow = reinterpret_cast<const float2*>(s_nlse + u * 64 + half * 32);
+      const float2* drow = reinterpret_cast<const float2*>(s_ndel + u * 64 + half * 32);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x0 = fmaf(__uint_as_float(a0[i]), c, -lrow[i]);
-        const float p0 = (i & 1) ? poly_exp2(x0) : fast_exp2(x0);  // MUFU / FMA pipes alternate
-        pt[i] = p0;
-        ds[i] = __uint_as_float(d0[i]);
-      }
-      if (drop) {
-        // Lanes 2m and 2m+1 own keys of the same column pair, i.e. they need the SAME 32-bit hash for a given query and
-        // take different halves of it: each computes the hash for every other query and gets the rest from its partner.
-        const uint32_t q_base = (uint32_t)bh * (uint32_t)p.N + (uint32_t)(j * 64 + half * 32);
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const uint32_t mine = drop_mix(drop_col ^ ((q_base + (uint32_t)(i + (lane & 1))) * kDropRowMul));
-          const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-          const uint32_t h0 = (lane & 1) ? other : mine, h1 = (lane & 1) ? mine : other;  // queries i, i + 1
-          const bool k0 = (drop_hi ? (h0 >> 16) : (h0 & 0xffffu)) >= p.drop_thresh16;
-          const bool k1 = (drop_hi ? (h1 >> 16) : (h1 & 0xffffu)) >= p.drop_thresh16;
-          // dV = (P o mask / (1 - p))^T dO;  dP = mask o (dO V^T) / (1 - p)
-          const float pa = pt[i], pb = pt[i + 1];
-          pt[i] = k0 ? pa * p.drop_scale : 0.f;
-          pt[i + 1] = k1 ? pb * p.drop_scale : 0.f;
-          ds[i] = pa * ((k0 ? ds[i] * p.drop_scale : 0.f) - drow[i]);
-          ds[i + 1] = pb * ((k1 ? ds[i + 1] * p.drop_scale : 0.f) - drow[i + 1]);
+      for (int i = 0; i < 16; ++i) {
+        const float2 x = ffma2(make_float2(__uint_as_float(a0[2 * i]), __uint_as_float(a0[2 * i + 1])), c2, lrow[i]);
+        const float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        float2 dp = make_float2(__uint_as_float(d0[2 * i]), __uint_as_float(d0[2 * i + 1]));
+        float2 pk = pr;
+        if (DROP) {
+          // dV = (P o mask / (1 - p))^T dO  (the 1 / (1 - p) is applied to the dV accumulator at the end);
+          // dP = mask o (dO V^T) / (1 - p)
+          drop_zero2(dp.x, dp.y, z[i], thresh2);
+          drop_zero2(pk.x, pk.y, z[i], thresh2);
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ds[i] = pt[i] * (ds[i] - drow[i]);
+        const float2 e = fmul2(pr, ffma2(dp, ks2, drow[i]));
+        wp[i] = pack_bf16x2(pk.x, pk.y);
+        wd[i] = pack_bf16x2(e.x, e.y);
       }
       if (j > 0) mbar_wait(pds_free, (j - 1) & 1);  // dV / dK MMAs of block j-1 no longer read the smem tiles
-      store_half_row_bf16_sw128(sPT + r * 128, r, half, pt);
-      store_half_row_bf16_sw128(sdST + r * 128, r, half, ds);
+      store_half_row_sw128(sPT + r * 128, r, half, wp);
+      store_half_row_sw128(sdST + r * 128, r, half, wd);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // staging of block j + 1 is complete / buffer u may be refilled
+      if (DROP && j + 1 < nq) make_words(j + 1);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
     __nv_bfloat16* kr = p.dk + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
     __nv_bfloat16* vr = p.dv + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
 #pragma unroll 1
-    for (int cc = half * (DH / 2); cc < (half + 1) * (DH / 2); cc += 32) {
-      uint32_t ov[32], ok[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + cc, ov);
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + DH + cc, ok);
+    for (int cc = half * 16; cc < DH; cc += 32) {
+      uint32_t ov[16], ok[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_addr + cc, ov);
+      tmem_ld_32x32b_x16(tmem_base + lane_addr + DH + cc, ok);
       tc_wait_ld();
       if (krow < p.N) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(ov[i]), __uint_as_float(ov[i + 1]));
-          w.y = pack_bf16x2(__uint_as_float(ov[i + 2]), __uint_as_float(ov[i + 3]));
-          w.z = pack_bf16x2(__uint_as_float(ov[i + 4]), __uint_as_float(ov[i + 5]));
-          w.w = pack_bf16x2(__uint_as_float(ov[i + 6]), __uint_as_float(ov[i + 7]));
-          *reinterpret_cast<uint4*>(vr + cc + i) = w;
-          w.x = pack_bf16x2(__uint_as_float(ok[i]) * p.scale, __uint_as_float(ok[i + 1]) * p.scale);
-          w.y = pack_bf16x2(__uint_as_float(ok[i + 2]) * p.scale, __uint_as_float(ok[i + 3]) * p.scale);
-          w.z = pack_bf16x2(__uint_as_float(ok[i + 4]) * p.scale, __uint_as_float(ok[i + 5]) * p.scale);
-          w.w = pack_bf16x2(__uint_as_float(ok[i + 6]) * p.scale, __uint_as_float(ok[i + 7]) * p.scale);
-          *reinterpret_cast<uint4*>(kr + cc + i) = w;
+        for (int i = 0; i < 16; i += 8) {
+          uint4 wv;
+          wv.x = pack_bf16x2(__uint_as_float(ov[i]) * ks, __uint_as_float(ov[i + 1]) * ks);
+          wv.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * ks, __uint_as_float(ov[i + 3]) * ks);
+          wv.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * ks, __uint_as_float(ov[i + 5]) * ks);
+          wv.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * ks, __uint_as_float(ov[i + 7]) * ks);
+          *reinterpret_cast<uint4*>(vr + cc + i) = wv;
+          wv.x = pack_bf16x2(__uint_as_float(ok[i]) * p.scale, __uint_as_float(ok[i + 1]) * p.scale);
+          wv.y = pack_bf16x2(__uint_as_float(ok[i + 2]) * p.scale, __uint_as_float(ok[i + 3]) * p.scale);
+          wv.z = pack_bf16x2(__uint_as_float(ok[i + 4]) * p.scale, __uint_as_float(ok[i + 5]) * p.scale);
+          wv.w = pack_bf16x2(__uint_as_float(ok[i + 6]) * p.scale, __uint_as_float(ok[i + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(kr + cc + i) = wv;
         }
       }
     }
@@ -875,7 +928,7 @@ __global__ void __launch_bounds__(256) fa_delta_kernel(const __nv_bfloat16* __re
   if (lane == 0) delta[warp] = s;
 }
 
-template <int DH>
+template <int DH, bool DROP>
 static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
   using Cfg = FaBwdCfg<DH>;
   const long long E = (long long)a.H * DH;
@@ -926,15 +979,15 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
   p.scale = a.scale;
   p.drop_seed = a.drop_seed;
   p.drop_site = a.drop_site;
-  p.drop_thresh16 = a.drop_thresh16;
+  p.drop_thresh14 = a.drop_thresh14;
   p.drop_scale = a.drop_scale;
   {
     const long long rows = (long long)a.B * a.H * a.N;
     fa_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a.o, a.dout, a.delta, a.B, a.H, a.N, DH, a.o_bs, a.o_hs, a.o_rs);
     S3D_LAUNCH_OK();
   }
-  auto kq = fa_bwd_dq_tc_kernel<DH>;
-  auto kkv = fa_bwd_dkv_tc_kernel<DH>;
+  auto kq = fa_bwd_dq_tc_kernel<DH, DROP>;
+  auto kkv = fa_bwd_dkv_tc_kernel<DH, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     S3D_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -949,22 +1002,37 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
   return S3D_OK;
 }
 
-int attn_bwd_tc(const AttnParams& p, int DH, cudaStream_t stream) {
-  if (p.B <= 0 || p.H <= 0 || p.N <= 0) return S3D_ERR_BAD_SHAPE;
+bool attn_tc_supported(int DH) { return DH == 48 || DH == 64 || DH == 96 || DH == 192; }
+
+template <bool DROP>
+static int fa_bwd_dispatch(const AttnParams& p, int DH, cudaStream_t stream) {
   switch (DH) {
-    case 192: return fa_bwd_launch<192>(p, stream);
-    case 64: return fa_bwd_launch<64>(p, stream);
+    case 192: return fa_bwd_launch<192, DROP>(p, stream);
+    case 96: return fa_bwd_launch<96, DROP>(p, stream);
+    case 64: return fa_bwd_launch<64, DROP>(p, stream);
+    case 48: return fa_bwd_launch<48, DROP>(p, stream);
+    default: return S3D_ERR_UNSUPPORTED;
+  }
+}
+template <bool DROP>
+static int fa_fwd_dispatch(const AttnParams& p, int DH, cudaStream_t stream) {
+  switch (DH) {
+    case 192: return fa_fwd_launch<192, DROP>(p, stream);
+    case 96: return fa_fwd_launch<96, DROP>(p, stream);
+    case 64: return fa_fwd_launch<64, DROP>(p, stream);
+    case 48: return fa_fwd_launch<48, DROP>(p, stream);
     default: return S3D_ERR_UNSUPPORTED;
   }
 }
 
+int attn_bwd_tc(const AttnParams& p, int DH, cudaStream_t stream) {
+  if (p.B <= 0 || p.H <= 0 || p.N <= 0) return S3D_ERR_BAD_SHAPE;
+  return p.drop_seed != nullptr ? fa_bwd_dispatch<true>(p, DH, stream) : fa_bwd_dispatch<false>(p, DH, stream);
+}
+
 int attn_fwd_tc(const AttnParams& p, int DH, cudaStream_t stream) {
   if (p.B <= 0 || p.H <= 0 || p.N <= 0) return S3D_ERR_BAD_SHAPE;
-  switch (DH) {
-    case 192: return fa_fwd_launch<192>(p, stream);
-    case 64: return fa_fwd_launch<64>(p, stream);
-    default: return S3D_ERR_UNSUPPORTED;
-  }
+  return p.drop_seed != nullptr ? fa_fwd_dispatch<true>(p, DH, stream) : fa_fwd_dispatch<false>(p, DH, stream);
 }
 
 }  // namespace s3d

@@ -112,11 +112,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps (context error) instead of hanging the GPU box.
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires)
+// instead of returning after a few dozen cycles, so a waiting producer / MMA warp stops competing for the issue slots
+// of the element-wise warps on its scheduler (measured on the flash forward kernel: ~20 % of all issued instructions
+// were spin-loop bookkeeping).
+__device__ __forceinline__ bool mbar_try_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (context error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 27)) __trap();
+  while (!mbar_try_wait_parked(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
   }
 }
 
@@ -240,6 +258,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -358,10 +385,20 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // Counter-based dropout mask (nn.Dropout / attention-probability dropout of the group_embed layer, reference
-// vit_3d_2d_pretrain.py:381: nn.TransformerEncoderLayer's default p = 0.1, active in train()). Element (row, col) of a
-// site gets 16 pseudo-random bits; one 32-bit hash serves the column pair (col & ~1, col | 1). keep <=> bits >= thresh,
-// thresh = round(p * 65536). Stateless: backward regenerates the forward mask from (seed, row, col).
+// vit_3d_2d_pretrain.py:381: nn.TransformerEncoderLayer's default p = 0.1, active in train()). Stateless: backward
+// regenerates the forward mask from (seed, site, row, col).
+//   site seed  ss      = mix(seed ^ site * C_site ^ const)
+//   row key    rk(row) = mix(ss ^ row * C_row)                                  (once per row)
+//   pair word  z(row, cp) = fold(fold(rk + cp * C_col, M1), M2) & 0x3FFF3FFF,   fold(x, m) = lo32(x * m) ^ hi32(x * m)
+//   element (row, col) draws the 14-bit value r = col odd ? z >> 16 : z & 0x3FFF of pair cp = col >> 1 and is KEPT when
+//   r >= thresh14 = round(p * 16384); kept values are scaled by 1 / (1 - thresh14 / 16384).
+// The pair word costs 5 integer instructions (IADD, 2 x IMAD.WIDE, 2 x LOP3). Both 14-bit halves are bit patterns of
+// finite non-negative fp16 numbers (< 2.0), whose order equals their integer order, so ONE half2 comparison
+// (set.ge.u32.f16x2 -> HSET2) turns z into the 0xFFFF / 0x0000 AND-masks of a packed bf16x2 pair, and setp.ge.f16x2
+// yields both predicates at once. (One fold round leaves lattice structure -- P(drop, drop) at column distance 2 is 2x
+// off -- two rounds pass the pair / row-sum / column-sum statistics checked in tests/test_dropout_hash.py.)
 constexpr uint32_t kDropRowMul = 0x9E3779B1u, kDropColMul = 0x85EBCA77u, kDropSiteMul = 0x632BE5ABu;
+constexpr uint32_t kDropM1 = 0xD6E8FEB9u, kDropM2 = 0xCA6B1B35u;
 __host__ __device__ __forceinline__ uint32_t drop_mix(uint32_t x) {
   x *= 0x2C1B3C6Du;
   x ^= x >> 15;
@@ -372,14 +409,101 @@ __host__ __device__ __forceinline__ uint32_t drop_mix(uint32_t x) {
 __host__ __device__ __forceinline__ uint32_t drop_site_seed(uint32_t seed, uint32_t site) {
   return drop_mix(seed ^ (site * kDropSiteMul) ^ 0xA511E9B3u);
 }
-// hash of the pair; caller picks the half: low 16 bits for even columns, high 16 bits for odd ones
+__host__ __device__ __forceinline__ uint32_t drop_rowkey(uint32_t site_seed, uint32_t row) {
+  return drop_mix(site_seed ^ (row * kDropRowMul));
+}
+__host__ __device__ __forceinline__ uint32_t drop_fold(uint32_t x, uint32_t m) {
+  const unsigned long long w = (unsigned long long)x * m;
+  return (uint32_t)w ^ (uint32_t)(w >> 32);
+}
+// y = rowkey + cp * kDropColMul (callers step y by kDropColMul from pair to pair)
+__host__ __device__ __forceinline__ uint32_t drop_word(uint32_t y) {
+  return drop_fold(drop_fold(y, kDropM1), kDropM2) & 0x3FFF3FFFu;
+}
 __host__ __device__ __forceinline__ uint32_t drop_pair(uint32_t site_seed, uint32_t row, uint32_t col_pair) {
-  return drop_mix(site_seed ^ (row * kDropRowMul) ^ (col_pair * kDropColMul));
+  return drop_word(drop_rowkey(site_seed, row) + col_pair * kDropColMul);
 }
-__host__ __device__ __forceinline__ bool drop_keep(uint32_t site_seed, uint32_t row, uint32_t col, uint32_t thresh16) {
-  const uint32_t h = drop_pair(site_seed, row, col >> 1);
-  return ((col & 1u) ? (h >> 16) : (h & 0xffffu)) >= thresh16;
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t site_seed, uint32_t row, uint32_t col, uint32_t thresh14) {
+  const uint32_t z = drop_pair(site_seed, row, col >> 1);
+  return ((col & 1u) ? (z >> 16) : (z & 0xffffu)) >= thresh14;
 }
+__host__ __device__ __forceinline__ uint32_t drop_thresh14(float p) {
+  const float t = p * 16384.0f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 16383.f ? 16383u : (uint32_t)t);
+}
+__host__ __device__ __forceinline__ float drop_keep_scale(uint32_t thresh14) {
+  return 1.0f / (1.0f - (float)thresh14 / 16384.0f);
+}
+#ifdef __CUDACC__
+// 0xFFFF / 0x0000 per 16-bit half of z: keep-masks of the pair (thresh2 = thresh14 in both halves)
+__device__ __forceinline__ uint32_t drop_andmask(uint32_t z, uint32_t thresh2) {
+  uint32_t d;
+  asm("set.ge.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(z), "r"(thresh2));
+  return d;
+}
+// zero a (even column) / b (odd column) when dropped
+__device__ __forceinline__ void drop_zero2(float& a, float& b, uint32_t z, uint32_t thresh2) {
+  asm("{\n"
+      ".reg .pred p, q;\n"
+      "setp.ge.f16x2 p|q, %2, %3;\n"
+      "@!p mov.f32 %0, 0f00000000;\n"
+      "@!q mov.f32 %1, 0f00000000;\n"
+      "}\n"
+      : "+f"(a), "+f"(b)
+      : "r"(z), "r"(thresh2));
+}
+#endif
+
+// ------------------------------------------ packed fp32 pairs ------------------------------------------
+// Blackwell executes fma / add / mul on two fp32 lanes per instruction (FFMA2 / FADD2 / FMUL2): the element-wise warps
+// of the attention kernels are instruction-issue bound, so their scale / subtract / accumulate steps run packed.
+#ifdef __CUDACC__
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "add.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mul.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+#endif
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

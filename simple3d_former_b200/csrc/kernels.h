@@ -77,12 +77,14 @@ struct AttnParams {
   // attention-probability dropout (tcgen05 kernels only): device seed (nullptr = off), site id, threshold, 1 / (1 - p)
   const uint32_t* drop_seed;
   uint32_t drop_site;
-  uint32_t drop_thresh16;
+  uint32_t drop_thresh14;  // keep <=> 14-bit draw >= thresh14 = round(p * 16384), see common.cuh
   float drop_scale;
 };
 int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream);
 int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream);
-// attention_tcgen05.cu (long sequences, dh in {64, 192}); S3D_ERR_UNSUPPORTED -> caller falls back to the mma.sync kernels
+// attention_tcgen05.cu (long sequences / dropout, dh in {48, 64, 96, 192}); S3D_ERR_UNSUPPORTED -> the layout is not a
+// slice of one 2-D qkv buffer and the caller uses the mma.sync kernels
+bool attn_tc_supported(int DH);
 int attn_fwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
 int attn_bwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
 

@@ -801,7 +801,7 @@ int colsum_bf16(const void* in, float* out, int T, int C, long long ld, int accu
 // ------------------------------------------------------------------------------------------------
 __global__ void dropout_add_f32_kernel(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ out,
                                        long long n4, int cols, const uint32_t* __restrict__ seed, uint32_t site,
-                                       uint32_t thresh16, float scale) {
+                                       uint32_t thresh14, float scale) {
   pdl_prologue();
   const uint32_t ss = drop_site_seed(*seed, site);
   const int c4 = cols >> 2;
@@ -809,17 +809,18 @@ __global__ void dropout_add_f32_kernel(const float* __restrict__ x, const float*
     const uint32_t row = (uint32_t)(i / c4), col = (uint32_t)(i % c4) * 4u;
     const float4 v = reinterpret_cast<const float4*>(x)[i];
     float4 o = res != nullptr ? reinterpret_cast<const float4*>(res)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t h0 = drop_pair(ss, row, col >> 1), h1 = drop_pair(ss, row, (col >> 1) + 1);
-    if ((h0 & 0xffffu) >= thresh16) o.x += v.x * scale;
-    if ((h0 >> 16) >= thresh16) o.y += v.y * scale;
-    if ((h1 & 0xffffu) >= thresh16) o.z += v.z * scale;
-    if ((h1 >> 16) >= thresh16) o.w += v.w * scale;
+    const uint32_t y = drop_rowkey(ss, row) + (col >> 1) * kDropColMul;
+    const uint32_t h0 = drop_word(y), h1 = drop_word(y + kDropColMul);
+    if ((h0 & 0xffffu) >= thresh14) o.x += v.x * scale;
+    if ((h0 >> 16) >= thresh14) o.y += v.y * scale;
+    if ((h1 & 0xffffu) >= thresh14) o.z += v.z * scale;
+    if ((h1 >> 16) >= thresh14) o.w += v.w * scale;
     reinterpret_cast<float4*>(out)[i] = o;
   }
 }
 
 __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n4,
-                                    int cols, const uint32_t* __restrict__ seed, uint32_t site, uint32_t thresh16,
+                                    int cols, const uint32_t* __restrict__ seed, uint32_t site, uint32_t thresh14,
                                     float scale) {
   pdl_prologue();
   const uint32_t ss = drop_site_seed(*seed, site);
@@ -828,30 +829,26 @@ __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
     const uint32_t row = (uint32_t)(i / c4), col = (uint32_t)(i % c4) * 4u;
     const uint2 u = reinterpret_cast<const uint2*>(x)[i];
     const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-    const uint32_t h0 = drop_pair(ss, row, col >> 1), h1 = drop_pair(ss, row, (col >> 1) + 1);
+    const uint32_t y = drop_rowkey(ss, row) + (col >> 1) * kDropColMul;
+    const uint32_t h0 = drop_word(y), h1 = drop_word(y + kDropColMul);
     uint2 w;
-    w.x = pack_bf16x2((h0 & 0xffffu) >= thresh16 ? a.x * scale : 0.f, (h0 >> 16) >= thresh16 ? a.y * scale : 0.f);
-    w.y = pack_bf16x2((h1 & 0xffffu) >= thresh16 ? b.x * scale : 0.f, (h1 >> 16) >= thresh16 ? b.y * scale : 0.f);
+    w.x = pack_bf16x2((h0 & 0xffffu) >= thresh14 ? a.x * scale : 0.f, (h0 >> 16) >= thresh14 ? a.y * scale : 0.f);
+    w.y = pack_bf16x2((h1 & 0xffffu) >= thresh14 ? b.x * scale : 0.f, (h1 >> 16) >= thresh14 ? b.y * scale : 0.f);
     reinterpret_cast<uint2*>(out)[i] = w;
   }
-}
-
-static inline uint32_t drop_thresh16(float p) {
-  const float t = p * 65536.0f + 0.5f;
-  return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);
 }
 
 int dropout_add_f32(const float* x, const float* res, float* out, long long rows, int cols, const uint32_t* seed,
                     unsigned site, float p, cudaStream_t stream) {
   if (rows <= 0 || cols <= 0 || cols % 4 != 0 || p < 0.f || p >= 1.f) return S3D_ERR_BAD_SHAPE;
   if (x == nullptr || out == nullptr || seed == nullptr) return S3D_ERR_NULL;
-  const uint32_t th = drop_thresh16(p);
+  const uint32_t th = drop_thresh14(p);
   const long long n4 = rows * cols / 4;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   S3D_CUDA_OK(launch_pdl(dropout_add_f32_kernel, dim3((int)blocks), dim3(256), (size_t)(0), stream, x, res, out, n4, cols, seed, site, th,
-                                                          1.0f / (1.0f - (float)th / 65536.0f)));
+                                                          drop_keep_scale(th)));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -860,14 +857,14 @@ int dropout_bf16(const void* x, void* out, long long rows, int cols, const uint3
                  cudaStream_t stream) {
   if (rows <= 0 || cols <= 0 || cols % 4 != 0 || p < 0.f || p >= 1.f) return S3D_ERR_BAD_SHAPE;
   if (x == nullptr || out == nullptr || seed == nullptr) return S3D_ERR_NULL;
-  const uint32_t th = drop_thresh16(p);
+  const uint32_t th = drop_thresh14(p);
   const long long n4 = rows * cols / 4;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   S3D_CUDA_OK(launch_pdl(dropout_bf16_kernel, dim3((int)blocks), dim3(256), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(x),
                                                        reinterpret_cast<__nv_bfloat16*>(out), n4, cols, seed, site, th,
-                                                       1.0f / (1.0f - (float)th / 65536.0f)));
+                                                       drop_keep_scale(th)));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }

@@ -447,7 +447,7 @@ class GroupEmbedFn(torch.autograd.Function):
         drop = drop_p > 0.0
         keep_scale = 1.0
         if drop:
-            keep_scale = 1.0 / (1.0 - int(drop_p * 65536.0 + 0.5) / 65536.0)
+            keep_scale = 1.0 / (1.0 - int(drop_p * 16384.0 + 0.5) / 16384.0)  # csrc/common.cuh::drop_keep_scale
         T = S * Nb
         dy2 = dy.reshape(T, E).contiguous()
         in_b, out_b, l1_b, l2_b, n1b, n2b = ctx.refs

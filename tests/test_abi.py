@@ -44,7 +44,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.s3d_knn(None, None, None, None, 1, 8, 4, 16, None) == -1  # K > N
     assert lib.s3d_fps(None, None, None, 1, 100000, 4, None) == -1  # N too large
     assert lib.s3d_layernorm_fwd(None, None, None, None, None, None, None, None, None, 4, 770, 1e-6, None) == -1
-    assert lib.s3d_attn_fwd(None, None, None, None, None, 1, 1, 4, 48, 0, 0, 0, 0, 0, 0, 1.0, None, 0, 0.0, None) == -2  # head_dim
+    assert lib.s3d_attn_fwd(None, None, None, None, None, 1, 1, 4, 40, 0, 0, 0, 0, 0, 0, 1.0, None, 0, 0.0, None) == -2  # head_dim (48 / 64 / 96 / 192 / 256 exist)
     assert lib.s3d_gemm_bf16(None, None, None, 0, 1, 1, 8, 8, 8, 0, 0, 0, 1.0, None, None, 0, 0, None, 0, None, 0, 1, 0,
                              0, 0, 0, 0, 0, 0, None) == -1
 

@@ -28,18 +28,26 @@ def _site_seed(seed, site):
     return _mix(np.uint64((int(seed) ^ ((site * 0x632BE5AB) & 0xFFFFFFFF) ^ 0xA511E9B3) & 0xFFFFFFFF))
 
 
+def _fold(x, m):
+    w = x * np.uint64(m)  # x, m < 2^32: the product fits uint64
+    return (w & M32) ^ (w >> np.uint64(32))
+
+
 def keep_mask(seed, site, rows, cols, p):
-    """bool [len(rows), len(cols)]: the mask of csrc/common.cuh::drop_keep."""
-    thresh = int(p * 65536.0 + 0.5)
+    """bool [len(rows), len(cols)]: the mask of csrc/common.cuh::drop_keep (row key -> two multiply-fold rounds per
+    column pair -> 14-bit draw per element, kept when >= round(p * 16384))."""
+    thresh = int(p * 16384.0 + 0.5)
     rows = np.asarray(rows, dtype=np.uint64)[:, None]
     cols = np.asarray(cols, dtype=np.uint64)[None, :]
-    h = _mix(_site_seed(seed, site) ^ ((rows * np.uint64(0x9E3779B1)) & M32) ^ (((cols >> np.uint64(1)) * np.uint64(0x85EBCA77)) & M32))
-    bits = np.where((cols & np.uint64(1)) != 0, h >> np.uint64(16), h & np.uint64(0xFFFF))
+    rowkey = _mix(_site_seed(seed, site) ^ ((rows * np.uint64(0x9E3779B1)) & M32))
+    y = (rowkey + (cols >> np.uint64(1)) * np.uint64(0x85EBCA77)) & M32
+    z = _fold(_fold(y, 0xD6E8FEB9), 0xCA6B1B35) & np.uint64(0x3FFF3FFF)
+    bits = np.where((cols & np.uint64(1)) != 0, z >> np.uint64(16), z & np.uint64(0xFFFF))
     return bits >= thresh
 
 
 def keep_scale(p):
-    return 1.0 / (1.0 - int(p * 65536.0 + 0.5) / 65536.0)
+    return 1.0 / (1.0 - int(p * 16384.0 + 0.5) / 16384.0)
 
 
 def _dev():

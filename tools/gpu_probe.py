@@ -299,7 +299,9 @@ def g_attn_tc():
     torch.manual_seed(11)
     print("  S3D_ATTN_TC =", os.environ.get("S3D_ATTN_TC", "1"), flush=True)
     for (B, N, H, dh, layout) in [(2, 1024, 4, 192, "seqfirst"), (3, 700, 4, 192, "seqfirst"), (2, 12544, 4, 192, "seqfirst"),
-                                  (2, 513, 3, 64, "timm"), (3, 640, 2, 192, "timm"), (1, 2048, 3, 64, "timm")]:
+                                  (2, 513, 3, 64, "timm"), (3, 640, 2, 192, "timm"), (1, 2048, 3, 64, "timm"),
+                                  (2, 700, 4, 96, "seqfirst"), (2, 600, 4, 48, "seqfirst"), (3, 100, 4, 96, "seqfirst"),
+                                  (2, 333, 4, 48, "timm")]:
         qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
         lse = torch.empty(B, H, N, device="cuda")
         scale = dh ** -0.5
@@ -311,7 +313,8 @@ def g_attn_tc():
         del ro, rl
     # backward
     for (B, N, H, dh, layout) in [(2, 1024, 4, 192, "seqfirst"), (3, 700, 4, 192, "seqfirst"), (1, 12544, 4, 192, "seqfirst"),
-                                  (2, 513, 3, 64, "timm"), (3, 640, 2, 192, "timm")]:
+                                  (2, 513, 3, 64, "timm"), (3, 640, 2, 192, "timm"), (2, 700, 4, 96, "seqfirst"),
+                                  (2, 600, 4, 48, "seqfirst"), (3, 100, 4, 96, "seqfirst"), (2, 333, 4, 48, "timm")]:
         qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
         lse = torch.empty(B, H, N, device="cuda")
         delta = torch.empty(B, H, N, device="cuda")
@@ -358,6 +361,14 @@ def g_attn_tc():
                                    dk.data_ptr(), dv.data_ptr(), B, H, N, dh, qs, os_, dh ** -0.5))
     print(f"  [PERF] attn bwd group_embed shape B15 H4 S12544 dh192: {ms:.2f} ms  {10.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s "
           f"(algorithmic 5 GEMMs; 7 executed)", flush=True)
+    seed = torch.tensor([20210915], dtype=torch.int32, device="cuda")
+    ms = timeit(lambda: L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, dh ** -0.5, drop_seed=seed, drop_site=1, drop_p=0.1))
+    print(f"  [PERF] attn fwd group_embed shape, dropout p=0.1: {ms:.2f} ms  {4.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s", flush=True)
+    ms = timeit(lambda: L.attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out, dout, lse, delta, dq.data_ptr(),
+                                   dk.data_ptr(), dv.data_ptr(), B, H, N, dh, qs, os_, dh ** -0.5, drop_seed=seed,
+                                   drop_site=1, drop_p=0.1))
+    print(f"  [PERF] attn bwd group_embed shape, dropout p=0.1: {ms:.2f} ms  {10.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s "
+          f"(algorithmic)", flush=True)
 
 
 def g_attn_fwd():
