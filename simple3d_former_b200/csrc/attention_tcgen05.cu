@@ -406,6 +406,7 @@ struct FaBwdParams {
   long long row_bs, col_bs;      // qkv 2-D view
   int col_q, col_k, col_v;
   long long o_row_bs, o_col_bs;  // dout 2-D view
+  long long o_rs_elems;          // dout row pitch (elements)
   long long qkv_bs, qkv_hs, qkv_rs;
   float scale;
   const uint32_t* drop_seed;  // attention-probability dropout (same mask as the forward kernel)
@@ -413,7 +414,15 @@ struct FaBwdParams {
   float drop_scale;
 };
 
-constexpr int kFaBwdThreads = 320;
+// Element-wise group of the backward kernels: kEwParts threads share one TMEM lane (= tile row), each handling
+// 64 / kEwParts columns of a block. Four parts = 16 warps = four per scheduler: the element-wise phase is a chain of
+// dependent steps (TMEM load -> exp2 -> mask -> pack -> smem store -> proxy fence) and with two warps per scheduler the
+// issue slots sat idle 70 % of the time (ncu: 30 % issue-active, stall_long_sb + stall_wait > 50 %).
+constexpr int kEwParts = 4;
+constexpr int kEwCols = 64 / kEwParts;            // columns of a 64-wide block per thread
+constexpr int kEwWarps = 4 * kEwParts;
+constexpr int kEwThreads = 32 * kEwWarps;
+constexpr int kFaBwdThreads = 64 + kEwThreads;
 
 template <int DH>
 struct FaBwdCfg {
@@ -424,61 +433,94 @@ struct FaBwdCfg {
   static constexpr int kSmemBytes = 2 * kTileBytes + 4 * kBlkBytes + 2 * kSBytes + 1024 + 2048;
 };
 
-// 32 bf16 (half of a 128-byte row) into the 128B-swizzled tile: logical 16-byte chunks half*4 .. half*4+3 of row r
-__device__ __forceinline__ void store_half_row_sw128(uint8_t* row_base, int r, int half, const uint32_t (&w)[16]) {
+// kEwCols bf16 (this thread's part of a 128-byte row) into the 128B-swizzled tile: logical 16-byte chunks
+// part * kEwCols / 8 ... of row r
+__device__ __forceinline__ void store_part_row_sw128(uint8_t* row_base, int r, int part, const uint32_t (&w)[kEwCols / 2]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    *reinterpret_cast<uint4*>(row_base + (((half * 4 + q) ^ (r & 7)) << 4)) =
+  for (int q = 0; q < kEwCols / 8; ++q)
+    *reinterpret_cast<uint4*>(row_base + (((part * (kEwCols / 8) + q) ^ (r & 7)) << 4)) =
         make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
 }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x32b_x16(taddr, v); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
 
 // ------------------------------------------------ dQ ------------------------------------------------
+// The resident operands of this kernel -- the CTA's 128 x DH query tile Q and its dO tile, the A operands of S = Q K^T and
+// dP = dO V^T -- live in TENSOR MEMORY (bf16 pairs, DH/2 columns each, written once by the element-wise warps with
+// tcgen05.st), not in shared memory:
+//   * the tensor core no longer re-reads 2 x 128 x DH bf16 of A operand from shared memory for every 64-key block
+//     (ncu, round-2 capture of the smem-A version: tensor-core smem wavefronts 48.6 % of peak at 35 % tensor pipe, i.e. a
+//     75 % ceiling; now 88 KB instead of 184 KB per block);
+//   * the 96 KB they occupied hold a FOUR-stage K/V ring instead of two stages. With two stages the load of block j+1
+//     could only start when dQ(j-1) retired and S(j+1) had to wait for it: load latency sat on the critical path of every
+//     block (3037 cycles per block measured against 1152 cycles of MMA work).
+// TMEM (2 DH + 128 columns): dQ [0,DH)  S [DH,+64)  dP [DH+64,+64)  Q [DH+128,+DH/2)  dO [DH+128+DH/2,+DH/2).
+// S / dP are single-buffered: the element-wise warps pull them into registers and hand the columns back at once
+// (sp_free), so S/dP(j+1) runs on the tensor core while dS(j) is computed; dS tiles are double-buffered in smem.
+struct FaDqCfgBase {
+  static constexpr int kStages = 4;
+};
+template <int DH>
+struct FaDqCfg {
+  static constexpr int kCh = (DH + 63) / 64;
+  static constexpr int kStages = FaDqCfgBase::kStages;
+  static constexpr int kBlkBytes = 64 * kCh * 128;     // 64-row streamed block (K or V)
+  static constexpr int kSBytes = 128 * 64 * 2;         // bf16 dS tile
+  static constexpr int kSmemBytes = 2 * kStages * kBlkBytes + 2 * kSBytes + 1024 + 512;
+  static constexpr int kColS = DH, kColQ = DH + 128, kColdO = DH + 128 + DH / 2;
+  static_assert(2 * DH + 128 <= 512, "TMEM budget");
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+
 template <int DH, bool DROP>
 __global__ void __launch_bounds__(kFaBwdThreads, 1)
-fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_constant__ CUtensorMap tma_kv64,
-                    const __grid_constant__ CUtensorMap tma_do128, const FaBwdParams p) {
-  using Cfg = FaBwdCfg<DH>;
+fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfloat16* __restrict__ qbase,
+                    const __nv_bfloat16* __restrict__ dobase, const FaBwdParams p) {
+  using Cfg = FaDqCfg<DH>;
+  constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                          // [kCh][128][128B]
-  uint8_t* sdO = sQ + Cfg::kTileBytes;         // [kCh][128][128B]
-  uint8_t* sK = sdO + Cfg::kTileBytes;         // [2][kCh][64][128B]
-  uint8_t* sV = sK + 2 * Cfg::kBlkBytes;       // [2][kCh][64][128B]
-  uint8_t* sdS = sV + 2 * Cfg::kBlkBytes;      // [2][128][128B]
+  uint8_t* sK = smem;                                // [NST][kCh][64][128B]
+  uint8_t* sV = sK + NST * Cfg::kBlkBytes;           // [NST][kCh][64][128B]
+  uint8_t* sdS = sV + NST * Cfg::kBlkBytes;          // [2][128][128B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * Cfg::kSBytes);
-  uint64_t* qdo_full = bars;       // [1]
-  uint64_t* k_full = bars + 1;     // [2]
-  uint64_t* v_full = bars + 3;     // [2]
-  uint64_t* kv_empty = bars + 5;   // [2]
-  uint64_t* sp_full = bars + 7;    // [2]
-  uint64_t* ds_full = bars + 9;    // [2]
-  uint64_t* dq_full = bars + 11;   // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* k_full = bars;                 // [NST]
+  uint64_t* v_full = bars + NST;           // [NST]
+  uint64_t* kv_empty = bars + 2 * NST;     // [NST]
+  uint64_t* sp_full = bars + 3 * NST;      // [1] S and dP of a block complete
+  uint64_t* sp_free = sp_full + 1;         // [1] element-wise warps hold them in registers
+  uint64_t* ds_full = sp_full + 2;         // [2] dS tile written
+  uint64_t* ds_free = sp_full + 4;         // [2] dQ MMAs that read the dS tile retired
+  uint64_t* a_ready = sp_full + 6;         // [1] Q / dO are in tensor memory
+  uint64_t* dq_full = sp_full + 7;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
   const int q0 = blockIdx.x * 128;
   const int nkv = (p.N + 63) / 64;
   const int row_base = (int)(b * p.row_bs);
-  const int cq = (int)(b * p.col_bs) + p.col_q + h * DH;
   const int ck = (int)(b * p.col_bs) + p.col_k + h * DH;
   const int cv = (int)(b * p.col_bs) + p.col_v + h * DH;
-  const int o_row_base = (int)(b * p.o_row_bs);
-  const int co = (int)(b * p.o_col_bs) + h * DH;
-  constexpr int kColS = DH;  // TMEM: dQ [0,DH)  then per buffer u: S [DH + 128u, +64), dP [DH + 128u + 64, +64)
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_q128);
     tma_prefetch_desc(&tma_kv64);
-    tma_prefetch_desc(&tma_do128);
-    mbar_init(qdo_full, 1);
-    mbar_init(dq_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
-      mbar_init(&sp_full[i], 1);
-      mbar_init(&ds_full[i], 8);  // one arrive per element-wise warp
+    }
+    mbar_init(sp_full, 1);
+    mbar_init(sp_free, kEwWarps);  // one arrive per element-wise warp
+    mbar_init(a_ready, kEwWarps);
+    mbar_init(dq_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ds_full[i], kEwWarps);
+      mbar_init(&ds_free[i], 1);
     }
     fence_barrier_init();
   }
@@ -490,15 +532,9 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(qdo_full, 2 * Cfg::kTileBytes);
-#pragma unroll
-      for (int c = 0; c < Cfg::kCh; ++c) {
-        tma_load_2d(sQ + c * (128 * 128), &tma_q128, qdo_full, cq + 64 * c, row_base + q0);
-        tma_load_2d(sdO + c * (128 * 128), &tma_do128, qdo_full, co + 64 * c, o_row_base + q0);
-      }
       for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        const int st = j % NST;
+        mbar_wait(&kv_empty[st], ((j / NST) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], Cfg::kBlkBytes);
 #pragma unroll
         for (int c = 0; c < Cfg::kCh; ++c)
@@ -515,37 +551,12 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idesc_q = make_idesc_bf16(128, DH, 0, 1);
     constexpr uint32_t hi = smem_desc_hi_sw128(1024);
-    const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16), do_lo = smem_desc_lo(smem_u32(sdO), 16);
     const uint32_t k_lo = smem_desc_lo(smem_u32(sK), 16), v_lo = smem_desc_lo(smem_u32(sV), 16);
     const uint32_t ds_lo = smem_desc_lo(smem_u32(sdS), 16), kmn_lo = smem_desc_lo(smem_u32(sK), 64 * 128);
-    auto issue_s_dp = [&](int u, int st) {
-      const uint32_t bk = k_lo + st * (Cfg::kBlkBytes >> 4), bv = v_lo + st * (Cfg::kBlkBytes >> 4);
-      const uint32_t ds_ = tmem_base + kColS + u * 128, dp_ = ds_ + 64;
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_f16_ss2(ds_, q_lo + kstep_off<128>(kk), hi, bk + kstep_off<64>(kk), hi, idesc_s, kk != 0);
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_f16_ss2(dp_, do_lo + kstep_off<128>(kk), hi, bv + kstep_off<64>(kk), hi, idesc_s, kk != 0);
-        umma_commit(&sp_full[u]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(qdo_full, 0);
-    mbar_wait(&k_full[0], 0);
-    mbar_wait(&v_full[0], 0);
-    tc_fence_after();
-    issue_s_dp(0, 0);
-    for (int j = 0; j < nkv; ++j) {
-      const int u = j & 1, st = j & 1;
-      if (j + 1 < nkv) {
-        mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
-        mbar_wait(&v_full[st ^ 1], ((j + 1) >> 1) & 1);
-        // TMEM buffer u^1 was released by ds_full[u^1] of block j-1 (waited below in the previous iteration)
-        tc_fence_after();
-        issue_s_dp(u ^ 1, st ^ 1);
-      }
+    const uint32_t t_s = tmem_base + Cfg::kColS, t_dp = t_s + 64;
+    const uint32_t t_q = tmem_base + Cfg::kColQ, t_do = tmem_base + Cfg::kColdO;
+    auto issue_dq = [&](int j) {  // dQ += dS(j) K(j)
+      const int u = j & 1, st = j % NST;
       mbar_wait(&ds_full[u], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t a = ds_lo + u * (Cfg::kSBytes >> 4), bb = kmn_lo + st * (Cfg::kBlkBytes >> 4);
@@ -554,19 +565,60 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
         for (int kk = 0; kk < 4; ++kk)
           umma_f16_ss2(tmem_base, a + ((kk * 32) >> 4), hi, bb + ((kk * 2048) >> 4), hi, idesc_q, (j > 0) || (kk != 0));
         umma_commit(&kv_empty[st]);
+        umma_commit(&ds_free[u]);
         if (j + 1 == nkv) umma_commit(dq_full);
       }
       __syncwarp();
+    };
+    mbar_wait(a_ready, 0);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j % NST;
+      mbar_wait(&k_full[st], (j / NST) & 1);
+      mbar_wait(&v_full[st], (j / NST) & 1);
+      if (j > 0) mbar_wait(sp_free, (j - 1) & 1);  // S / dP of block j-1 are in registers: the columns can be overwritten
+      tc_fence_after();
+      const uint32_t bk = k_lo + st * (Cfg::kBlkBytes >> 4), bv = v_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)  // S = Q K^T, A from tensor memory (8 columns per 16-element k-step)
+          umma_f16_ts(t_s, t_q + kk * 8, ((uint64_t)hi << 32) | (bk + kstep_off<64>(kk)), idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)  // dP = dO V^T
+          umma_f16_ts(t_dp, t_do + kk * 8, ((uint64_t)hi << 32) | (bv + kstep_off<64>(kk)), idesc_s, kk != 0);
+        umma_commit(sp_full);
+      }
+      __syncwarp();
+      if (j > 0) issue_dq(j - 1);
     }
+    issue_dq(nkv - 1);
   } else {
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;  // which 32 of the 64 key columns of a block this thread handles
+    const int part = (warp - 2) >> 2;  // which kEwCols of the 64 key columns of a block this thread handles
     const int r = quad * 32 + lane;
     const int row = q0 + r;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const long long bh = (long long)b * p.H + h;
-    // rows >= N (last query tile): lse = +inf -> P = 0 -> dS = 0 (those rows hold the next batch's data in the timm
-    // layout, zeros at the end of the buffer; they are never written back).
+    // ---- Q / dO rows -> tensor memory (bf16 pairs; element (row, k) = lane row, column k / 2). Rows >= N are zeros.
+    {
+      const __nv_bfloat16* qrow = qbase + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)row * p.qkv_rs;
+      const __nv_bfloat16* orow = dobase + (long long)(b * p.o_row_bs + row) * p.o_rs_elems + b * p.o_col_bs + h * DH;
+      const uint32_t tq = tmem_base + lane_addr + Cfg::kColQ, tdo = tmem_base + lane_addr + Cfg::kColdO;
+#pragma unroll 4
+      for (int g = part; g < DH / 8; g += kEwParts) {  // 8 bf16 = 16 bytes = 4 columns per step
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), d = make_uint4(0u, 0u, 0u, 0u);
+        if (row < p.N) {
+          a = *reinterpret_cast<const uint4*>(qrow + g * 8);
+          d = *reinterpret_cast<const uint4*>(orow + g * 8);
+        }
+        tmem_st_32x32b_x4(tq + g * 4, a.x, a.y, a.z, a.w);
+        tmem_st_32x32b_x4(tdo + g * 4, d.x, d.y, d.z, d.w);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    // rows >= N (last query tile): lse = +inf -> P = 0 -> dS = 0; they are never written back.
     // keys >= N (last block): dS is zeroed explicitly below -- in the timm layout the K / V rows behind a batch's last key
     // are the next batch's keys, not TMA zero fill.
     const float nlse = row < p.N ? -p.lse[bh * p.N + row] * kFaLog2e : -INFINITY;
@@ -575,27 +627,30 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
     const float2 c2 = make_float2(c, c), nlse2 = make_float2(nlse, nlse), ndel2 = make_float2(ndel, ndel);
     const float ks = DROP ? p.drop_scale : 1.0f;  // dP = mask o (dO V^T) / (1 - p): regenerate the forward mask
     const float2 ks2 = make_float2(ks, ks);
-    uint32_t z[DROP ? 16 : 1];
+    uint32_t z[DROP ? kEwCols / 2 : 1];
     uint32_t ykey = 0, thresh2 = 0;
     if (DROP) {
       ykey = drop_rowkey(drop_site_seed(*p.drop_seed, p.drop_site), (uint32_t)bh * (uint32_t)p.N + (uint32_t)row) +
-             (uint32_t)(half * 16) * kDropColMul;
+             (uint32_t)(part * (kEwCols / 2)) * kDropColMul;
       thresh2 = p.drop_thresh14 * 0x00010001u;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) z[i] = drop_word(ykey + (uint32_t)i * kDropColMul);
+      for (int i = 0; i < kEwCols / 2; ++i) z[i] = drop_word(ykey + (uint32_t)i * kDropColMul);
     }
     for (int j = 0; j < nkv; ++j) {
       const int u = j & 1;
-      mbar_wait(&sp_full[u], (j >> 1) & 1);
+      mbar_wait(sp_full, j & 1);
       tc_fence_after();
-      uint32_t a0[32], d0[32];
-      const uint32_t s_addr = tmem_base + lane_addr + kColS + u * 128 + half * 32;
-      tmem_ld_32x32b_x32(s_addr, a0);
-      tmem_ld_32x32b_x32(s_addr + 64, d0);
+      uint32_t a0[kEwCols], d0[kEwCols];
+      const uint32_t s_addr = tmem_base + lane_addr + Cfg::kColS + part * kEwCols;
+      tmem_ld_cols(s_addr, a0);
+      tmem_ld_cols(s_addr + 64, d0);
       tc_wait_ld();
-      uint32_t w[16];
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sp_free);
+      uint32_t w[kEwCols / 2];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < kEwCols / 2; ++i) {
         const float2 x = ffma2(make_float2(__uint_as_float(a0[2 * i]), __uint_as_float(a0[2 * i + 1])), c2, nlse2);
         const float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
         float2 dp = make_float2(__uint_as_float(d0[2 * i]), __uint_as_float(d0[2 * i + 1]));
@@ -604,14 +659,15 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
         w[i] = pack_bf16x2(e.x, e.y);
       }
       if (j * 64 + 64 > p.N) {  // last, partial key block
-        const int key0 = j * 64 + half * 32;
+        const int key0 = j * 64 + part * kEwCols;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < kEwCols / 2; ++i) {
           if (key0 + 2 * i >= p.N) w[i] = 0u;
           else if (key0 + 2 * i + 1 >= p.N) w[i] &= 0xffffu;
         }
       }
-      store_half_row_sw128(sdS + u * Cfg::kSBytes + r * 128, r, half, w);
+      if (j >= 2) mbar_wait(&ds_free[u], ((j >> 1) - 1) & 1);  // dQ MMAs of block j-2 no longer read this dS tile
+      store_part_row_sw128(sdS + u * Cfg::kSBytes + r * 128, r, part, w);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -619,15 +675,15 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_c
       if (DROP) {  // mask words of block j + 1, computed while the tensor core runs
         const uint32_t y0 = ykey + (uint32_t)((j + 1) * 32) * kDropColMul;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) z[i] = drop_word(y0 + (uint32_t)i * kDropColMul);
+        for (int i = 0; i < kEwCols / 2; ++i) z[i] = drop_word(y0 + (uint32_t)i * kDropColMul);
       }
     }
     mbar_wait(dq_full, 0);
     tc_fence_after();
     __nv_bfloat16* orow = p.dq + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)row * p.qkv_rs;
-    // the two threads of a row split the DH columns in 16-column groups: even groups -> half 0, odd groups -> half 1
+    // the threads of a row split the DH columns in 16-column groups: group g -> part g % kEwParts
 #pragma unroll 1
-    for (int cc = half * 16; cc < DH; cc += 32) {
+    for (int cc = part * 16; cc < DH; cc += 16 * kEwParts) {
       uint32_t o[16];
       tmem_ld_32x32b_x16(tmem_base + lane_addr + cc, o);
       tc_wait_ld();
@@ -699,8 +755,8 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     tma_prefetch_desc(&tma_do64);
     mbar_init(kv_full, 1);
     mbar_init(sp_full, 1);
-    mbar_init(s_free, 8);  // one arrive per element-wise warp
-    mbar_init(pds_full, 8);
+    mbar_init(s_free, kEwWarps);  // one arrive per element-wise warp
+    mbar_init(pds_full, kEwWarps);
     mbar_init(pds_free, 1);
     mbar_init(acc_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -750,13 +806,29 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
       const uint32_t bq = q_lo + st * (Cfg::kBlkBytes >> 4), bo = do_lo + st * (Cfg::kBlkBytes >> 4);
       const uint32_t dst = tmem_base + kColS, ddp = dst + 64;
       if (elect_one()) {
+        // the two accumulation chains are interleaved: consecutive tcgen05.mma into the SAME accumulator serialise on the
+        // shared-memory operand fetch, MMAs into different accumulators overlap it
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
+        for (int kk = 0; kk < DH / 16; ++kk) {
           umma_f16_ss2(dst, k_lo + kstep_off<128>(kk), hi, bq + kstep_off<64>(kk), hi, idesc_s, kk != 0);
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
           umma_f16_ss2(ddp, v_lo + kstep_off<128>(kk), hi, bo + kstep_off<64>(kk), hi, idesc_s, kk != 0);
+        }
         umma_commit(sp_full);
+      }
+      __syncwarp();
+    };
+    auto issue_dv_dk = [&](int j) {
+      const int st = j & 1;
+      const uint32_t bo = domn_lo + st * (Cfg::kBlkBytes >> 4), bq = qmn_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {  // dV += P^T dO and dK += dS^T Q, interleaved (independent accumulators)
+          umma_f16_ss2(tmem_base, pt_lo + ((kk * 32) >> 4), hi, bo + ((kk * 2048) >> 4), hi, idesc_a, (j > 0) || (kk != 0));
+          umma_f16_ss2(tmem_base + DH, dst_lo + ((kk * 32) >> 4), hi, bq + ((kk * 2048) >> 4), hi, idesc_a, (j > 0) || (kk != 0));
+        }
+        umma_commit(&qdo_empty[st]);
+        umma_commit(pds_free);
+        if (j + 1 == nq) umma_commit(acc_full);
       }
       __syncwarp();
     };
@@ -765,34 +837,35 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     mbar_wait(&do_full[0], 0);
     tc_fence_after();
     issue_st_dpt(0);
-    for (int j = 0; j < nq; ++j) {
-      const int st = j & 1;
-      if (j + 1 < nq) {
-        mbar_wait(&q_full[st ^ 1], ((j + 1) >> 1) & 1);
-        mbar_wait(&do_full[st ^ 1], ((j + 1) >> 1) & 1);
-        mbar_wait(s_free, j & 1);  // S^T / dP^T of block j are in registers: the TMEM columns can be overwritten
+    // Dynamic issue order. Two kinds of work are pending: S^T/dP^T of block `ns` (needs its Q/dO stage loaded and the
+    // element-wise warps to have pulled block ns-1 out of the single S^T/dP^T TMEM buffer) and dV/dK of block `nd` (needs
+    // P^T/dS^T of block nd in smem). With a fixed order the issuer blocks on whichever comes first in program order -- the
+    // round-2 capture showed it waiting for the load of block j+1 (which can only start when dV/dK(j-1) retire: two stages)
+    // while dV/dK(j) was ready, 3506 cycles per block for 1536 cycles of MMA work. Whatever is ready is issued first.
+    int ns = 1, nd = 0;
+    while (nd < nq) {
+      bool progressed = false;
+      if (ns < nq && ns <= nd + 1) {
+        const int st = ns & 1;
+        const uint32_t ph = (ns >> 1) & 1;
+        if (mbar_try_wait(&q_full[st], ph) && mbar_try_wait(&do_full[st], ph) && mbar_try_wait(s_free, (ns - 1) & 1)) {
+          tc_fence_after();
+          issue_st_dpt(st);
+          ++ns;
+          progressed = true;
+        }
+      }
+      if (!progressed && mbar_try_wait(pds_full, nd & 1)) {
         tc_fence_after();
-        issue_st_dpt(st ^ 1);
+        issue_dv_dk(nd);
+        ++nd;
+        progressed = true;
       }
-      mbar_wait(pds_full, j & 1);
-      tc_fence_after();
-      const uint32_t bo = domn_lo + st * (Cfg::kBlkBytes >> 4), bq = qmn_lo + st * (Cfg::kBlkBytes >> 4);
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO
-          umma_f16_ss2(tmem_base, pt_lo + ((kk * 32) >> 4), hi, bo + ((kk * 2048) >> 4), hi, idesc_a, (j > 0) || (kk != 0));
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q
-          umma_f16_ss2(tmem_base + DH, dst_lo + ((kk * 32) >> 4), hi, bq + ((kk * 2048) >> 4), hi, idesc_a, (j > 0) || (kk != 0));
-        umma_commit(&qdo_empty[st]);
-        umma_commit(pds_free);
-        if (j + 1 == nq) umma_commit(acc_full);
-      }
-      __syncwarp();
+      if (!progressed) __nanosleep(32);
     }
   } else {
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;      // which 32 of the 64 query columns of a block this thread handles
+    const int part = (warp - 2) >> 2;      // which kEwCols of the 64 query columns of a block this thread handles
     const int r = quad * 32 + lane;        // key row within the tile
     const int tid = threadIdx.x - 64;      // 0..255 within the element-wise group
     const int krow = k0 + r;
@@ -809,7 +882,7 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     const uint32_t colterm = ((uint32_t)krow >> 1) * kDropColMul;
     const uint32_t sel = (krow & 1) ? 0x7632u : 0x5410u;
     const uint32_t thresh2 = p.drop_thresh14 * 0x00010001u;
-    uint32_t z[DROP ? 16 : 1];  // per query pair (2i, 2i+1) of this thread's 32 queries
+    uint32_t z[DROP ? kEwCols / 2 : 1];  // per query pair (2i, 2i+1) of this thread's queries
     auto stage = [&](int j) {   // lse / delta / row keys of query block j (padded queries: lse = +inf -> P = 0)
       const int u = j & 1;
       const int qi = j * 64 + (tid & 63);
@@ -818,9 +891,9 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
       else if (DROP && tid < 192) s_rk[u * 64 + (tid & 63)] = drop_rowkey(site_seed, (uint32_t)bh * (uint32_t)p.N + (uint32_t)qi);
     };
     auto make_words = [&](int j) {
-      const uint4* rk4 = reinterpret_cast<const uint4*>(s_rk + (j & 1) * 64 + half * 32);
+      const uint4* rk4 = reinterpret_cast<const uint4*>(s_rk + (j & 1) * 64 + part * kEwCols);
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < kEwCols / 4; ++g) {
         const uint4 rk = rk4[g];
         const uint32_t z0 = drop_word(rk.x + colterm), z1 = drop_word(rk.y + colterm);
         const uint32_t z2 = drop_word(rk.z + colterm), z3 = drop_word(rk.w + colterm);
@@ -829,26 +902,26 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
       }
     };
     stage(0);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEwThreads) : "memory");
     if (DROP) make_words(0);
     for (int j = 0; j < nq; ++j) {
       const int u = j & 1;
       if (j + 1 < nq) stage(j + 1);  // buffer u^1: its last readers finished block j-1 before the barrier below of j-1
       mbar_wait(sp_full, j & 1);
       tc_fence_after();
-      uint32_t a0[32], d0[32];
-      const uint32_t s_addr = tmem_base + lane_addr + kColS + half * 32;
-      tmem_ld_32x32b_x32(s_addr, a0);
-      tmem_ld_32x32b_x32(s_addr + 64, d0);
+      uint32_t a0[kEwCols], d0[kEwCols];
+      const uint32_t s_addr = tmem_base + lane_addr + kColS + part * kEwCols;
+      tmem_ld_cols(s_addr, a0);
+      tmem_ld_cols(s_addr + 64, d0);
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
-      uint32_t wp[16], wd[16];
-      const float2* lrow = reinterpret_cast<const float2*>(s_nlse + u * 64 + half * 32);
-      const float2* drow = reinterpret_cast<const float2*>(s_ndel + u * 64 + half * 32);
+      uint32_t wp[kEwCols / 2], wd[kEwCols / 2];
+      const float2* lrow = reinterpret_cast<const float2*>(s_nlse + u * 64 + part * kEwCols);
+      const float2* drow = reinterpret_cast<const float2*>(s_ndel + u * 64 + part * kEwCols);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < kEwCols / 2; ++i) {
         const float2 x = ffma2(make_float2(__uint_as_float(a0[2 * i]), __uint_as_float(a0[2 * i + 1])), c2, lrow[i]);
         const float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
         float2 dp = make_float2(__uint_as_float(d0[2 * i]), __uint_as_float(d0[2 * i + 1]));
@@ -864,13 +937,13 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
         wd[i] = pack_bf16x2(e.x, e.y);
       }
       if (j > 0) mbar_wait(pds_free, (j - 1) & 1);  // dV / dK MMAs of block j-1 no longer read the smem tiles
-      store_half_row_sw128(sPT + r * 128, r, half, wp);
-      store_half_row_sw128(sdST + r * 128, r, half, wd);
+      store_part_row_sw128(sPT + r * 128, r, part, wp);
+      store_part_row_sw128(sdST + r * 128, r, part, wd);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // staging of block j + 1 is complete / buffer u may be refilled
+      asm volatile("bar.sync 1, %0;" ::"n"(kEwThreads) : "memory");  // staging of block j + 1 is complete / buffer u may be refilled
       if (DROP && j + 1 < nq) make_words(j + 1);
     }
     mbar_wait(acc_full, 0);
@@ -878,7 +951,7 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     __nv_bfloat16* kr = p.dk + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
     __nv_bfloat16* vr = p.dv + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
 #pragma unroll 1
-    for (int cc = half * 16; cc < DH; cc += 32) {
+    for (int cc = part * 16; cc < DH; cc += 16 * kEwParts) {
       uint32_t ov[16], ok[16];
       tmem_ld_32x32b_x16(tmem_base + lane_addr + cc, ov);
       tmem_ld_32x32b_x16(tmem_base + lane_addr + DH + cc, ok);
@@ -957,11 +1030,10 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
     return S3D_ERR_UNSUPPORTED;
   }
   if (a.B > 65535 || a.H > 65535) return S3D_ERR_BAD_SHAPE;
-  CUtensorMap t128, t64, d128, d64;
+  CUtensorMap t128, t64, d64;
   int rc;
   if ((rc = make_tmap_bf16_2d(&t128, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&t64, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&d128, a.dout, (uint64_t)o_width, (uint64_t)rows_total, (uint64_t)a.o_rs, 64, 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&d64, a.dout, (uint64_t)o_width, (uint64_t)rows_total, (uint64_t)a.o_rs, 64, 64))) return rc;
   p.dq = a.dq;
   p.dk = a.dk;
@@ -986,18 +1058,22 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
     fa_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a.o, a.dout, a.delta, a.B, a.H, a.N, DH, a.o_bs, a.o_hs, a.o_rs);
     S3D_LAUNCH_OK();
   }
+  p.o_rs_elems = a.o_rs;
   auto kq = fa_bwd_dq_tc_kernel<DH, DROP>;
   auto kkv = fa_bwd_dkv_tc_kernel<DH, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
-    S3D_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    S3D_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDqCfg<DH>::kSmemBytes));
     S3D_CUDA_OK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
+  if ((a.qkv_rs % 8) || (a.qkv_hs % 8) || (a.qkv_bs % 8) || (a.o_rs % 8) || (reinterpret_cast<uintptr_t>(a.q) & 15) ||
+      (reinterpret_cast<uintptr_t>(a.dout) & 15))
+    return S3D_ERR_ALIGNMENT;  // 16-byte row loads of Q / dO
   dim3 grid((a.N + 127) / 128, a.H, a.B);
   kkv<<<grid, kFaBwdThreads, Cfg::kSmemBytes, stream>>>(t128, t64, d64, p);
   S3D_LAUNCH_OK();
-  kq<<<grid, kFaBwdThreads, Cfg::kSmemBytes, stream>>>(t128, t64, d128, p);
+  kq<<<grid, kFaBwdThreads, FaDqCfg<DH>::kSmemBytes, stream>>>(t64, a.q, a.dout, p);
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
