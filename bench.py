@@ -154,10 +154,60 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ----------------------------------------------------------------------------------------------------------------
+def _reference_modules():
+    """The reference's OWN modules from oracle/_ref (byte-for-byte copies made by oracle/make_ref.py in the build
+    container; they travel with the snapshot) on the plain-PyTorch timm 0.3.2 restatement -- or None when absent."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_harness as H
+    if not os.path.isfile(os.path.join(H.REF_COPY, "models", "vit_3d_2d_pretrain.py")):
+        return None
+    return H, H.load(timm="shim", root=H.REF_COPY)
+
+
+def _build_reference_model(cfg, H, mods, O):
+    if cfg["kind"] == "voxel":
+        D = O.BACKBONES[cfg["backbone"]]["embed_dim"]
+        emb = (mods.embed.VoxelEmbed if cfg["average"] else mods.embed.VoxelEmbed_no_average)(cfg["V"], cfg["cell"],
+                                                                                        cfg["patch"], embed_dim=D)
+        model = mods.vit.Feature3D_ViT2D_V2(embed_layer=emb, n_classes=cfg["n_classes"],
+                                            transformer_backbone=cfg["backbone"], pretrained=False,
+                                            pos_embedding=cfg["pos"])
+        for p_ in [model.head.weight, model.head.bias, model.pos_embed, *model.patch_embed.parameters()]:
+            p_.requires_grad = False  # what the reference's pretrained path does (vit_3d_2d_pretrain.py:428-432)
+        return model
+    return (mods.point.PointTransformerSeg if cfg["seg"] else mods.point.PointTransformerCls)(
+        H.point_cfg(cfg["N"], cfg["n_classes"], cfg["input_dim"], backbone=cfg["backbone"]))
+
+
 def cpu_reference_step_fn(cfg, B):
+    """One training step of the reference on the host cores. Returns (step_fn, kind): kind "reference" = the unmodified
+    reference modules (oracle/_ref) driven exactly as train_cls_voxel.py:270-288 / train_cls.py:103-128 drive them;
+    kind "port" = the functional oracle restatement (only when oracle/_ref is absent)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import s3d_oracle as O
     torch.set_num_threads(os.cpu_count())
+    kind, lr = cfg.get("opt", ("adam", 1e-3))  # voxel: Adam (train_cls_voxel.py:195); point: SGD momentum 0.9
+    x, y = synthetic_batch(cfg, B, seed=9)     # (train_cls.py:91, train_partseg.py:95 with config/*.yaml optimizer: SGD)
+    lf = loss_fn_for(cfg)
+    ref = _reference_modules()
+    if ref is not None:
+        import contextlib
+        H, mods = ref
+        torch.manual_seed(9)
+        with contextlib.redirect_stdout(sys.stderr):  # the reference's constructors print the backbone name
+            model = _build_reference_model(cfg, H, mods, O)
+        model.train()
+        params = [p_ for p_ in model.parameters() if p_.requires_grad]
+        opt = torch.optim.SGD(params, lr=lr, momentum=0.9) if kind == "sgd" else torch.optim.Adam(params, lr=lr)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = lf(model(x), y)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+
+        return step, "reference"
     if cfg["kind"] == "voxel":
         sd = O.init_voxel_state_dict(cfg["backbone"], cfg["cell"], cfg["patch"], cfg["n_classes"], cfg["pos"], seed=9)
         frozen = ()
@@ -166,13 +216,10 @@ def cpu_reference_step_fn(cfg, B):
         frozen = tuple(k for k in sd if "running_" in k)
     params = {k: v.requires_grad_(True) for k, v in sd.items() if k not in frozen}
     sd = {**sd, **params}
-    kind, lr = cfg.get("opt", ("adam", 1e-3))  # voxel: Adam (train_cls_voxel.py:195); point: SGD momentum 0.9
-    if kind == "sgd":                          # (train_cls.py:91, train_partseg.py:95 with config/*.yaml optimizer: SGD)
+    if kind == "sgd":
         opt = torch.optim.SGD(list(params.values()), lr=lr, momentum=0.9)
     else:
         opt = torch.optim.Adam(list(params.values()), lr=lr)
-    x, y = synthetic_batch(cfg, B, seed=9)
-    lf = loss_fn_for(cfg)
     starts = None
     if cfg["kind"] == "point":
         starts = [torch.zeros(B, dtype=torch.long).numpy(), torch.zeros(B, dtype=torch.long).numpy()]
@@ -186,13 +233,13 @@ def cpu_reference_step_fn(cfg, B):
         loss = lf(logits, y)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
-    return step
+    return step, "port"
 
 
 def run_cpu(cfg, B, steps, warmup, budget_s=None):
-    step = cpu_reference_step_fn(cfg, B)
+    step, kind = cpu_reference_step_fn(cfg, B)
     for _ in range(warmup):
         step()
     times = []
@@ -204,7 +251,19 @@ def run_cpu(cfg, B, steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t_begin > budget_s and i >= 1:
             break
     mean = sum(times) / len(times)
-    return B * cfg["per_sample"] / mean, mean * 1e3, len(times)
+    return B * cfg["per_sample"] / mean, mean * 1e3, len(times), kind
+
+
+def cpu_sample_note(cfg, B, n, ms, kind, cores):
+    what = ("the reference's own modules (oracle/_ref: unmodified models/*.py, data/pointnet_util.py on the timm-0.3.2 "
+            "restatement)" if kind == "reference" else "oracle port of the reference modules")
+    note = f"{what}, torch CPU fp32, {cores} threads, batch {B} fwd+bwd+optimizer, {n} steps, {ms:.0f} ms/step"
+    if B != cfg["B"]:
+        note += (f"; the GPU arm runs batch {cfg['B']}/GPU -- the CPU sample is bounded to batch {B} and its rate is per "
+                 f"sample" + ("; group_embed attention costs O(batch^2) per step, so batch " + str(cfg["B"]) +
+                              " would be ~17 % SLOWER per sample on the CPU (a same-batch CPU rate would be lower, "
+                              "the GPU/CPU ratio higher)" if cfg.get("pos") == "group_embed" else ""))
+    return note
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -505,9 +564,10 @@ def run_ours(args, cfg, rank, world, local_rank):
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, ms, n = run_cpu(cfg, cfg["cpu_B"], steps=50, warmup=1, budget_s=15.0)
-        out["cpu_baseline"] = {"value": v, "unit": cfg["unit"], "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"oracle port (torch CPU fp32), batch {cfg['cpu_B']} fwd+bwd+optimizer, {n} steps, {ms:.0f} ms/step"}
+        v, ms, n, kind = run_cpu(cfg, cfg["cpu_B"], steps=50, warmup=1, budget_s=15.0)
+        cores = torch.get_num_threads()
+        out["cpu_baseline"] = {"value": v, "unit": cfg["unit"], "cores": cores, "kind": kind,
+                               "sample": cpu_sample_note(cfg, cfg["cpu_B"], n, ms, kind, cores)}
     return out
 
 
@@ -531,15 +591,15 @@ def main():
         if rank != 0:
             return
         B = cfg["cpu_B"]
-        v, ms, n = run_cpu(cfg, B, steps=args.steps, warmup=args.warmup)
+        v, ms, n, kind = run_cpu(cfg, B, steps=args.steps, warmup=args.warmup)
         cores = torch.get_num_threads()
         print(json.dumps({
             "impl": "reference", "metric": "voxels/sec fwd+bwd" if cfg["kind"] == "voxel" else "points/sec fwd+bwd",
             "value": v, "unit": cfg["unit"], "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {cfg['model']}, CPU fp32, bounded sample batch {B}, fwd+bwd+optimizer"},
-            "cpu_baseline": {"value": v, "unit": cfg["unit"], "cores": cores, "kind": "port",
-                             "sample": f"oracle port of the reference modules (torch CPU fp32, {cores} threads), batch {B} per step"},
+            "cpu_baseline": {"value": v, "unit": cfg["unit"], "cores": cores, "kind": kind,
+                             "sample": cpu_sample_note(cfg, B, n, ms, kind, cores)},
             "e2e": {"value": v, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return

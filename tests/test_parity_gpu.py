@@ -15,9 +15,10 @@ LOGIT_TOL = 1e-2  # north_star: logits / loss within 1e-2 for bf16 operands -- a
 
 
 def _logit_tol(ref_logits):
-    """1e-2 absolute; fixtures whose logits are smaller than 1 get the proportionally TIGHTER bound 1e-2 * max|logit|
-    (an absolute 1e-2 on |logit| < 0.1 would pass a visibly wrong kernel)."""
-    return LOGIT_TOL * min(1.0, float(ref_logits.abs().max()))
+    """1e-2 absolute (north_star); fixtures whose logits are small get the TIGHTER bound of 2 % of max|logit| (an absolute
+    1e-2 on |logit| < 0.1 would pass a visibly wrong kernel; bf16 operand rounding over 12 blocks measures 0.3-1 % of the
+    logit scale on every fixture, tools/parity_report.py)."""
+    return min(LOGIT_TOL, 2e-2 * float(ref_logits.abs().max()))
 
 
 def _dev():

@@ -173,4 +173,4 @@ def test_reference_point_class_body_over_product_modules(golden, name):
     with torch.no_grad():
         logits = model(x.to(_dev()))
     ref_logits = fix["eval"]["logits"]
-    assert (logits.cpu() - ref_logits).abs().max().item() <= TOL * min(1.0, float(ref_logits.abs().max()))
+    assert (logits.cpu() - ref_logits).abs().max().item() <= min(TOL, 2e-2 * float(ref_logits.abs().max()))
