@@ -49,25 +49,18 @@ CONFIGS = {
 # one GPU; configs[1] (cfg2, a 160-us-roofline launch-bound step) is reported alongside it at N=1 as `secondary`.
 DEFAULT_CONFIG = "cfg3"
 
-# `ncu --set full --clock-control none` captures of single launches at the cfg3 shapes (tools/ncu_targets.py; selected raw
-# metrics in profiles/r01_ncu_full_cfg3_kernels_v5_raw_selected.csv): per launch dram__bytes_read.sum +
-# dram__bytes_write.sum ("traffic", bytes), sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active and
-# gpu__time_duration (cold-cache, serialised). Keyed by the (kernel, shape) key of KernelProfile.shape_key.
-NCU = {
-    "s3d_gemm_bf16[M=188160,N=3072,K=768,a_mn=0,b_mn=0,epi=1,f32=0]": dict(traffic=2.558e9, tensor_pipe_pct=51.8, ms=0.930),
-    "s3d_gemm_bf16[M=188160,N=3072,K=768,a_mn=0,b_mn=1,epi=2,f32=0]": dict(traffic=2.579e9, tensor_pipe_pct=48.0, ms=0.980),
-    "s3d_gemm_bf16[M=188160,N=768,K=3072,a_mn=0,b_mn=0,epi=0,f32=1]": dict(traffic=2.520e9, tensor_pipe_pct=72.8, ms=0.717),
-    "s3d_gemm_bf16[M=3072,N=768,K=188160,a_mn=1,b_mn=1,epi=0,f32=1]": dict(traffic=1.467e9, tensor_pipe_pct=87.8, ms=0.607),
-    "s3d_gemm_bf16[M=188160,N=768,K=768,a_mn=0,b_mn=0,epi=0,f32=1]": dict(traffic=1.422e9, tensor_pipe_pct=33.8, ms=0.333),
-    "s3d_gemm_bf16[M=188160,N=2304,K=768,a_mn=0,b_mn=0,epi=0,f32=0]": dict(traffic=1.104e9, tensor_pipe_pct=69.2, ms=0.515),
-    "s3d_attn_fwd[B=12544,H=3,N=15,dh=256]": dict(traffic=1.137e9, tensor_pipe_pct=6.6, ms=0.278),
-    "s3d_attn_bwd[B=12544,H=3,N=15,dh=256]": dict(traffic=1.983e9, tensor_pipe_pct=7.7, ms=0.597),
-    "s3d_attn_fwd[B=15,H=4,N=12544,dh=192]": dict(traffic=1.159e9, tensor_pipe_pct=51.4, ms=6.702),
-    "s3d_attn_bwd[B=15,H=4,N=12544,dh=192]": dict(traffic=3.747e9, tensor_pipe_pct=41.3, ms=28.342),
-    "s3d_layernorm_fwd": dict(traffic=0.821e9, tensor_pipe_pct=0.0, ms=0.123),
-    "s3d_layernorm_bwd": dict(traffic=1.686e9, tensor_pipe_pct=0.0, ms=0.284),
-    "s3d_colsum_bf16": dict(traffic=1.160e9, tensor_pipe_pct=0.0, ms=0.194),
-}
+# ncu evidence: `ncu --set full --clock-control none` captures of single launches at the bench shapes, post-processed by
+# tools/ncu_table.py into profiles/ncu_table.json (per launch: dram__bytes_read.sum + dram__bytes_write.sum = "traffic",
+# sm__pipe_tensor_cycles_active % and gpu__time_duration -- cold-cache, serialised: compare shares, not absolutes).
+# Keys are KernelProfile.shape_key strings; attention kernels carry the dropout flag of the variant that was captured,
+# so the table entry always describes the variant the timed step runs.
+def load_ncu_table():
+    path = os.path.join(ROOT, "profiles", "ncu_table.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return {"entries": {}, "source": None}
 
 
 def peaks():
@@ -337,9 +330,9 @@ class KernelProfile:
         if name == "s3d_gemm_bf16":
             return f"{name}[M={a[3]},N={a[4]},K={a[5]},a_mn={a[9]},b_mn={a[10]},epi={a[16]},f32={a[11]}]"
         if name == "s3d_attn_fwd":
-            return f"{name}[B={a[5]},H={a[6]},N={a[7]},dh={a[8]}]"
+            return f"{name}[B={a[5]},H={a[6]},N={a[7]},dh={a[8]},drop={int(bool(a[16]) and a[18] > 0)}]"
         if name == "s3d_attn_bwd":
-            return f"{name}[B={a[10]},H={a[11]},N={a[12]},dh={a[13]}]"
+            return f"{name}[B={a[10]},H={a[11]},N={a[12]},dh={a[13]},drop={int(bool(a[21]) and a[23] > 0)}]"
         return name
 
     def summary(self):
@@ -389,7 +382,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     eager_step()
     torch.cuda.synchronize()
     launches_per_step = L.LAUNCHES - n_before
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph  # N > 1: the NCCL bucket all-reduces are captured with the step (dp.py)
     step_fn = eager_step
     graph_note = "eager"
     if use_graph:
@@ -409,11 +402,16 @@ def run_ours(args, cfg, rank, world, local_rank):
                 graph.replay()
                 return static_loss
 
-            graph_note = "cuda_graph(whole step)"
+            graph_note = "cuda_graph(whole step" + (", NCCL bucket all-reduces captured)" if world > 1 else ")")
         except Exception as exc:  # capture is an optimisation, never a requirement
-            graph_note = f"eager (graph capture failed: {type(exc).__name__})"
+            graph_note = f"eager (graph capture failed: {type(exc).__name__}: {str(exc)[:120]})"
             step_fn = eager_step
             torch.cuda.synchronize()
+        if world > 1:  # all ranks must run the same mode (a graph rank and an eager rank would still match collectives,
+            ok = torch.tensor([1 if graph_note.startswith("cuda_graph") else 0], device=device)  # but time differently)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0 and graph_note.startswith("cuda_graph"):
+                step_fn, graph_note = eager_step, "eager (graph capture failed on another rank)"
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
@@ -534,6 +532,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                                    "unit": "TFLOP/s" if rate(v)[0] else "GB/s"} for k, v in shapes_sorted[:24]}}
     # ncu evidence: DRAM traffic of the dominant family's largest launch (same launch the algorithmic figure next to it
     # refers to) and the per-launch captures of every top shape that has one
+    ncu = load_ncu_table()
+    NCU = ncu.get("entries", {})
     fam_shapes = [(k, v) for k, v in shapes_sorted if k.split("[")[0] == name]
     if fam_shapes and fam_shapes[0][0] in NCU:
         k0, v0 = fam_shapes[0]
@@ -541,6 +541,12 @@ def run_ours(args, cfg, rank, world, local_rank):
         roofline["traffic_launch"] = k0
         roofline["traffic_algorithmic"] = round((v0["bytes"]) / v0["launches"], 1)
     roofline["ncu"] = {k: NCU[k] for k, _ in shapes_sorted[:24] if k in NCU}
+    roofline["ncu_source"] = ncu.get("source")
+    # whole-step figure, so the dominant family's fraction cannot be mistaken for it: algorithmic tensor FLOPs of ALL
+    # launches of a step (GEMMs 2MNK; attention 4 / 10 N^2 dh per (batch, head) forward / backward) over the timed step
+    step_flops = sum(v["flops"] for v in fam.values()) / 2.0
+    roofline["step_frac"] = round(step_flops / (dev_ms / args.steps * 1e-3) / 1e12 / pk["tf_sustained"], 4)
+    roofline["step_algorithmic_tflop"] = round(step_flops / 1e12, 3)
     samples = B * world * args.steps
     value = samples * cfg["per_sample"] / (dev_ms * 1e-3)
     e2e_value = samples * cfg["per_sample"] / (e2e_ms * 1e-3)
@@ -577,7 +583,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(CONFIGS))
-    ap.add_argument("--no-secondary", action="store_true", help="skip the extra cfg2 measurement at N=1")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the extra cfg2 / cfg4 / cfg5 measurements")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -611,15 +617,23 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     out = run_ours(args, cfg, rank, world, local_rank)
-    if world == 1 and args.config == DEFAULT_CONFIG and not args.no_secondary:
-        # configs[1] (cfg2) measured the same way, reported inside the same JSON line
+    if args.config == DEFAULT_CONFIG and not args.no_secondary:
+        # the other BASELINE configs measured the same way at the same N, reported inside the same JSON line:
+        # configs[1] (cfg2), configs[3] (cfg4: point classification), configs[4] (cfg5: part segmentation)
         import copy
-        a2 = copy.copy(args)
-        a2.config, a2.no_cpu_baseline, a2.steps = "cfg2", True, max(args.steps, 20)
-        torch.cuda.empty_cache()
-        sec = run_ours(a2, CONFIGS["cfg2"], rank, world, local_rank)
-        out["secondary"] = {k: sec[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "gpu_launches")}
-        out["secondary"]["roofline"] = {k: sec["roofline"][k] for k in ("kernel", "achieved", "peak", "unit", "frac", "share_of_kernel_time")}
+        secondary = {}
+        for name in ("cfg2", "cfg4", "cfg5"):
+            a2 = copy.copy(args)
+            a2.config, a2.no_cpu_baseline, a2.steps = name, True, max(args.steps, 20)
+            torch.cuda.empty_cache()
+            sec = run_ours(a2, CONFIGS[name], rank, world, local_rank)
+            if rank == 0:
+                secondary[name] = {k: sec[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "config",
+                                                        "e2e", "gpu_launches")}
+                secondary[name]["roofline"] = {k: sec["roofline"][k] for k in ("kernel", "achieved", "peak", "unit", "frac",
+                                                                               "share_of_kernel_time", "step_frac")}
+        if rank == 0:
+            out["secondary"] = secondary
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

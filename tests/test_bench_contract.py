@@ -17,7 +17,10 @@ def test_reference_arm_json_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "voxels/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # "reference" = the reference's own modules from oracle/_ref (build container / GPU box snapshot), "port" = oracle only
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "models", "vit_3d_2d_pretrain.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
+    assert "batch 64" in d["cpu_baseline"]["sample"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
 
 
