@@ -995,7 +995,9 @@ int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream) {
   // tcgen05 kernels only
   const bool tc_only = p.drop_seed != nullptr || (DH != 64 && DH != 192 && DH != 256);
   if (tc_only) return attn_tc_supported(DH) ? attn_fwd_tc(p, DH, stream) : S3D_ERR_UNSUPPORTED;
-  if (tc_enabled && attn_tc_supported(DH) && p.N >= 512) {
+  // every sequence of at least one 64-key block runs on the tcgen05 kernels (timm Block shapes N = 197 / 257 / 513 and the
+  // group_embed layer); the 15- and 26-token sequences keep the persistent warp-per-sequence mma.sync kernels
+  if (tc_enabled && attn_tc_fwd_supported(DH) && p.N >= 64) {
     const int rc_tc = attn_fwd_tc(p, DH, stream);
     if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;
   }
@@ -1015,7 +1017,7 @@ int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream) {
   static const bool tc_enabled = []() { const char* v = getenv("S3D_ATTN_TC"); return v == nullptr || v[0] != '0'; }();
   const bool tc_only = p.drop_seed != nullptr || (DH != 64 && DH != 192 && DH != 256);
   if (tc_only) return attn_tc_supported(DH) ? attn_bwd_tc(p, DH, stream) : S3D_ERR_UNSUPPORTED;
-  if (tc_enabled && attn_tc_supported(DH) && p.N >= 512) {
+  if (tc_enabled && attn_tc_supported(DH) && p.N >= 128) {  // head_dim 256 does not fit the backward's TMEM budget
     const int rc_tc = attn_bwd_tc(p, DH, stream);
     if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;
   }

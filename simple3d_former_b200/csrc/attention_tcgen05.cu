@@ -27,6 +27,8 @@
 // boxes; for DH % 64 != 0 the tail box carries columns of the neighbouring head that no MMA ever reads.
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace s3d {
 
 constexpr int kFaBM = 128;   // query rows per tile
@@ -59,6 +61,19 @@ struct FaParams {
   uint32_t drop_site, drop_thresh14;
   float drop_scale;           // 1 / (1 - p)
 };
+
+__device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 
 // k-step kk (16 bf16 = 32 bytes) inside a [chunks][ROWS][128 B] K-major operand tile, as a descriptor-low-word increment
 template <int ROWS>
@@ -387,6 +402,351 @@ static int fa_fwd_launch(const AttnParams& a, cudaStream_t stream) {
 }
 
 // ================================================================================================
+// Forward, second generation: ONE 128-row query tile per CTA with every A operand in tensor memory.
+//   * Q (bf16 pairs, DH/2 columns) is written to TMEM once by the softmax warps; S = Q K^T runs in TS mode. Shared-memory
+//     A operands cost the tensor core ~110-130 cycles per tcgen05.mma whatever N is (measured on the backward kernels:
+//     24 SS-mode M128 N64 MMAs per block took ~2700 cycles for 768 cycles of math), so a 64-key S block needs its A
+//     operand in tensor memory to run at the 32-cycle rate.
+//   * P is written back to TMEM as bf16 pairs (32 columns) by the softmax warps -- no shared-memory tile, no proxy fence --
+//     and O += P V runs in TS mode as well (V stays an MN-major B operand in shared memory).
+//   * S is single-buffered: the softmax warps pull a block into registers and hand the columns back at once (s_free), so
+//     S(j+1) runs on the tensor core while P(j) is computed; the K/V ring has 3-4 stages because shared memory now holds
+//     nothing else.
+//   * 8 softmax warps: two threads per row (warps w and w+4 share a TMEM lane quadrant), 32 columns each; the row maximum
+//     is exchanged through shared memory with a 64-thread named barrier per quadrant, row sums are combined once at the end.
+// TMEM: O [0,DH)  S [DH,+64)  P [DH+64,+32)  Q [DH+96,+DH/2)  -- 480 columns at DH = 256, so the timm Block shapes
+// (deit_base: 3 heads of 256) run on tcgen05 too. Any N >= 1, head dims 48 / 64 / 96 / 192 / 256.
+// ================================================================================================
+template <int DH>
+struct Fa1Cfg {
+  static_assert(DH % 16 == 0 && DH >= 16 && DH <= 256, "head_dim must be a multiple of 16, at most 256");
+  static constexpr int kCh = (DH + 63) / 64;
+  static constexpr int kBlkBytes = kFaBN * kCh * 128;      // K or V block
+  static constexpr int kStages = (2 * 4 * kBlkBytes <= 200 * 1024) ? 4 : 3;
+  static constexpr int kSmemBytes = 2 * kStages * kBlkBytes + 1024 + 3072;
+  static constexpr int kColS = DH, kColP = DH + 64, kColQ = DH + 96;
+  static_assert(DH + 96 + DH / 2 <= 512, "TMEM budget");
+};
+
+template <int DH, bool DROP>
+__global__ void __launch_bounds__(kFaThreads, 1)
+fa_fwd1_tc_kernel(const __grid_constant__ CUtensorMap tma_kv, const __nv_bfloat16* __restrict__ qbase, const FaParams p,
+                  long long q_bs, long long q_hs, long long q_rs) {
+  using Cfg = Fa1Cfg<DH>;
+  constexpr int NST = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                                // [NST][kCh][64][128B]
+  uint8_t* sV = sK + NST * Cfg::kBlkBytes;           // [NST][kCh][64][128B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NST * Cfg::kBlkBytes);
+  uint64_t* k_full = bars;                 // [NST]
+  uint64_t* v_full = bars + NST;           // [NST]
+  uint64_t* kv_empty = bars + 2 * NST;     // [NST]
+  uint64_t* s_full = bars + 3 * NST;       // [1]
+  uint64_t* s_free = s_full + 1;           // [1] softmax warps hold S in registers
+  uint64_t* p_full = s_full + 2;           // [1] P written to tensor memory
+  uint64_t* pv_done = s_full + 3;          // [1] P V MMAs of a block retired (P columns and O are idle)
+  uint64_t* q_ready = s_full + 4;          // [1]
+  uint64_t* o_full = s_full + 5;           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  float* xch = reinterpret_cast<float*>(s_full + 8);  // [2 parity][2 halves][128 rows] row-maximum exchange
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * kFaBM;
+  const int nkv = (p.N + kFaBN - 1) / kFaBN;
+  const int row_base = (int)(b * p.row_bs);
+  const int ck = (int)(b * p.col_bs) + p.col_k + h * DH;
+  const int cv = (int)(b * p.col_bs) + p.col_v + h * DH;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_kv);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 8);
+    mbar_init(p_full, 8);
+    mbar_init(pv_done, 1);
+    mbar_init(q_ready, 8);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // --------------------------------------------- TMA producer ---------------------------------------------
+    if (lane == 0) {
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % NST;
+        mbar_wait(&kv_empty[st], ((j / NST) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::kBlkBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kCh; ++c)
+          tma_load_2d(sK + st * Cfg::kBlkBytes + c * (kFaBN * 128), &tma_kv, &k_full[st], ck + 64 * c, row_base + j * kFaBN);
+        mbar_expect_tx(&v_full[st], Cfg::kBlkBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kCh; ++c)
+          tma_load_2d(sV + st * Cfg::kBlkBytes + c * (kFaBN * 128), &tma_kv, &v_full[st], cv + 64 * c, row_base + j * kFaBN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------- MMA issuer ----------------------------------------------
+    constexpr uint32_t idesc_s = make_idesc_bf16(kFaBM, kFaBN, 0, 0);  // S = Q K^T : K block K-major
+    constexpr uint32_t idesc_o = make_idesc_bf16(kFaBM, DH, 0, 1);     // O = P V   : V is MN-major
+    constexpr uint32_t hi = smem_desc_hi_sw128(1024);
+    const uint32_t k_lo = smem_desc_lo(smem_u32(sK), 16), v_lo = smem_desc_lo(smem_u32(sV), kFaBN * 128);
+    const uint32_t t_o = tmem_base, t_s = tmem_base + Cfg::kColS, t_p = tmem_base + Cfg::kColP, t_q = tmem_base + Cfg::kColQ;
+    auto issue_pv = [&](int j) {
+      const int st = j % NST;
+      mbar_wait(&v_full[st], (j / NST) & 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      const uint32_t bb = v_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kFaBN / 16; ++kk)
+          umma_f16_ts(t_o, t_p + kk * 8, ((uint64_t)hi << 32) | (bb + ((kk * 2048) >> 4)), idesc_o, (j > 0) || (kk != 0));
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+        if (j + 1 == nkv) umma_commit(o_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_ready, 0);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j % NST;
+      mbar_wait(&k_full[st], (j / NST) & 1);
+      if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+      tc_fence_after();
+      const uint32_t bk = k_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_f16_ts(t_s, t_q + kk * 8, ((uint64_t)hi << 32) | (bk + kstep_off<kFaBN>(kk)), idesc_s, kk != 0);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      if (j > 0) issue_pv(j - 1);
+    }
+    issue_pv(nkv - 1);
+  } else {
+    // ----------------------------------------------- softmax -----------------------------------------------
+    const int quad = warp & 3;
+    const int hf = (warp - 2) >> 2;    // which 32 of the 64 key columns of a block
+    const int r = quad * 32 + lane;
+    const int row = q0 + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr + Cfg::kColS + hf * 32;
+    const uint32_t p_addr = tmem_base + lane_addr + Cfg::kColP + hf * 16;
+    const uint32_t o_addr = tmem_base + lane_addr;
+    {  // Q row -> tensor memory (element (row, k) = lane row, column k / 2); rows >= N are zeros
+      const __nv_bfloat16* qrow = qbase + (long long)b * q_bs + (long long)h * q_hs + (long long)row * q_rs;
+      const uint32_t tq = tmem_base + lane_addr + Cfg::kColQ;
+#pragma unroll 4
+      for (int g = hf; g < DH / 8; g += 2) {
+        uint4 a = make_uint4(0u, 0u, 0u, 0u);
+        if (row < p.N) a = *reinterpret_cast<const uint4*>(qrow + g * 8);
+        tmem_st_32x32b_x4(tq + g * 4, a.x, a.y, a.z, a.w);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);
+    }
+    const float c = p.scale * kFaLog2e;
+    const float2 c2 = make_float2(c, c);
+    float m_ref = -INFINITY, l = 0.f;
+    uint32_t mk[DROP ? 16 : 1];  // AND-masks of this thread's 16 packed P pairs of the coming block
+    uint32_t ykey = 0, thresh2 = 0;
+    if (DROP) {
+      ykey = drop_rowkey(drop_site_seed(*p.drop_seed, p.drop_site), (uint32_t)(b * p.H + h) * (uint32_t)p.N + (uint32_t)row) +
+             (uint32_t)(hf * 16) * kDropColMul;
+      thresh2 = p.drop_thresh14 * 0x00010001u;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) mk[i] = drop_andmask(drop_word(ykey + (uint32_t)i * kDropColMul), thresh2);
+    }
+    const int bar_id = 1 + quad;  // named barrier of the two warps that share this lane quadrant
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t v0[32];
+      tmem_ld_32x32b_x32(s_addr, v0);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      float s[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v0[i]);
+      const int key0 = j * kFaBN + hf * 32;
+      if (j * kFaBN + kFaBN > p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (key0 + i >= p.N) s[i] = -INFINITY;
+      }
+      float mx4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        mx4[q] = fmax3(s[q * 8], s[q * 8 + 1], s[q * 8 + 2]);
+        mx4[q] = fmax3(mx4[q], s[q * 8 + 3], s[q * 8 + 4]);
+        mx4[q] = fmax3(mx4[q], s[q * 8 + 5], s[q * 8 + 6]);
+        mx4[q] = fmaxf(mx4[q], s[q * 8 + 7]);
+      }
+      float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]);
+      float* xrow = xch + (j & 1) * 256;
+      xrow[hf * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      mx = fmaxf(mx, xrow[(hf ^ 1) * 128 + r]);
+      // lazy rescale: keep the reference max unless it grew by more than 2^8 (P stays <= 256, exact in the row sums);
+      // both threads of a row see the same mx and take the same decision
+      const bool need = (mx - m_ref) * c > 8.0f;
+      bool waited = false;
+      if (__any_sync(0xffffffffu, need)) {
+        const float f = need ? fast_exp2((m_ref - mx) * c) : 1.0f;  // m_ref = -inf -> f = 0 (first block: O is overwritten)
+        if (j > 0) {
+          mbar_wait(pv_done, (j - 1) & 1);  // O is being accumulated by P V of block j-1 until then
+          tc_fence_after();
+          waited = true;
+#pragma unroll 1
+          for (int cc = hf * 16; cc < DH; cc += 32) {  // the two threads of a row take alternate 16-column groups
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(o_addr + cc, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_32x32b_x16(o_addr + cc, o);
+          }
+        }
+        if (need) { l *= f; m_ref = mx; }
+      }
+      const float nmc = -m_ref * c;
+      const float2 nmc2 = make_float2(nmc, nmc);
+      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 x = ffma2(make_float2(s[2 * i], s[2 * i + 1]), c2, nmc2);
+        const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        if (i & 1) sum_b = fadd2(sum_b, e); else sum_a = fadd2(sum_a, e);
+        w[i] = pack_bf16x2(e.x, e.y);
+        if (DROP) w[i] &= mk[i];
+      }
+      l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+      if (j > 0 && !waited) {
+        mbar_wait(pv_done, (j - 1) & 1);  // P V of block j-1 no longer reads the P columns
+        tc_fence_after();
+      }
+      tmem_st_32x32b_x16(p_addr, w);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (DROP) {  // masks of block j + 1, computed while the tensor core runs
+        const uint32_t y0 = ykey + (uint32_t)((j + 1) * (kFaBN / 2)) * kDropColMul;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mk[i] = drop_andmask(drop_word(y0 + (uint32_t)i * kDropColMul), thresh2);
+      }
+    }
+    // epilogue: combine the two partial row sums, O / l -> bf16, lse
+    float* xrow = xch + (nkv & 1) * 256;
+    xrow[hf * 128 + r] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    l += xrow[(hf ^ 1) * 128 + r];
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = (DROP ? p.drop_scale : 1.0f) / l;
+    __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)row * p.o_rs;
+#pragma unroll 1
+    for (int cc = hf * 16; cc < DH; cc += 32) {
+      uint32_t o[16];
+      tmem_ld_32x32b_x16(o_addr + cc, o);
+      tc_wait_ld();
+      if (row < p.N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + cc + i) = u;
+        }
+      }
+    }
+    if (hf == 0 && p.lse != nullptr && row < p.N) p.lse[((long long)b * p.H + h) * p.N + row] = m_ref * p.scale + logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int DH, bool DROP>
+static int fa_fwd1_launch(const AttnParams& a, cudaStream_t stream) {
+  using Cfg = Fa1Cfg<DH>;
+  const long long E = (long long)a.H * DH;
+  const long long koff = a.k - a.q, voff = a.v - a.q;
+  if (koff != E || voff != 2 * E || a.qkv_hs != DH) return S3D_ERR_UNSUPPORTED;
+  FaParams p{};
+  long long rows_total, width;
+  if (a.qkv_rs == 3 * E && (a.qkv_bs == (long long)a.N * 3 * E || a.B == 1)) {  // timm: [B*N, 3E]
+    rows_total = (long long)a.B * a.N;
+    width = 3 * E;
+    p.row_bs = a.N;
+    p.col_bs = 0;
+  } else if (a.qkv_bs == 3 * E && a.qkv_rs == (long long)a.B * 3 * E) {  // sequence-first: [S, Nb*3E]
+    rows_total = a.N;
+    width = (long long)a.B * 3 * E;
+    p.row_bs = 0;
+    p.col_bs = 3 * E;
+  } else {
+    return S3D_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tkv;
+  int rc = make_tmap_bf16_2d(&tkv, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, kFaBN);
+  if (rc) return rc;
+  p.out = a.out;
+  p.lse = a.lse;
+  p.N = a.N;
+  p.H = a.H;
+  p.col_q = 0;
+  p.col_k = (int)E;
+  p.col_v = (int)(2 * E);
+  p.o_bs = a.o_bs;
+  p.o_hs = a.o_hs;
+  p.o_rs = a.o_rs;
+  p.scale = a.scale;
+  p.drop_seed = a.drop_seed;
+  p.drop_site = a.drop_site;
+  p.drop_thresh14 = a.drop_thresh14;
+  p.drop_scale = a.drop_scale;
+  if ((a.o_rs % 8) || (a.o_hs % 8) || (a.o_bs % 8) || (reinterpret_cast<uintptr_t>(a.out) & 15) || (a.qkv_rs % 8) ||
+      (a.qkv_bs % 8) || (reinterpret_cast<uintptr_t>(a.q) & 15))
+    return S3D_ERR_ALIGNMENT;
+  auto kern = fa_fwd1_tc_kernel<DH, DROP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  if (a.B > 65535 || a.H > 65535) return S3D_ERR_BAD_SHAPE;
+  dim3 grid((a.N + kFaBM - 1) / kFaBM, a.H, a.B);
+  kern<<<grid, kFaThreads, Cfg::kSmemBytes, stream>>>(tkv, a.q, p, a.qkv_bs, a.qkv_hs, a.qkv_rs);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+// ================================================================================================
 // Backward on tcgen05. Two kernels (no atomics, no dQ round trips through HBM):
 //   dQ   : CTA = 128 query rows; per 64-key block  S = Q K^T, dP = dO V^T (TMEM, double buffered),
 //          dS = P o (dP - delta) -> bf16 smem,  dQ += dS K  (K block re-read as an MN-major B operand)
@@ -470,11 +830,6 @@ struct FaDqCfg {
   static constexpr int kColS = DH, kColQ = DH + 128, kColdO = DH + 128 + DH / 2;
   static_assert(2 * DH + 128 <= 512, "TMEM budget");
 };
-
-__device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
-}
 
 template <int DH, bool DROP>
 __global__ void __launch_bounds__(kFaBwdThreads, 1)
@@ -1079,6 +1434,7 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
 }
 
 bool attn_tc_supported(int DH) { return DH == 48 || DH == 64 || DH == 96 || DH == 192; }
+bool attn_tc_fwd_supported(int DH) { return attn_tc_supported(DH) || DH == 256; }
 
 template <bool DROP>
 static int fa_bwd_dispatch(const AttnParams& p, int DH, cudaStream_t stream) {
@@ -1090,13 +1446,29 @@ static int fa_bwd_dispatch(const AttnParams& p, int DH, cudaStream_t stream) {
     default: return S3D_ERR_UNSUPPORTED;
   }
 }
+// S3D_FA_FWD=2 selects the first-generation two-tile forward kernel (A operands in shared memory) for A/B measurements
 template <bool DROP>
 static int fa_fwd_dispatch(const AttnParams& p, int DH, cudaStream_t stream) {
+  // With dropout the mask hashes sit on the single tile's softmax critical path (7.3 ms against 6.6 ms for the two-tile
+  // kernel, whose second tile hides them, on the group_embed shape); without dropout the single-tile kernel wins
+  // (5.6 against 6.1 ms). S3D_FA_FWD=1 / 2 forces one of them.
+  static const int forced = []() { const char* v = getenv("S3D_FA_FWD"); return v == nullptr ? 0 : (v[0] == '2' ? 2 : (v[0] == '1' ? 1 : 0)); }();
+  const bool two_tile = forced == 2 || (forced == 0 && DROP && p.N >= 1024);
+  if (two_tile && DH != 256) {
+    switch (DH) {
+      case 192: return fa_fwd_launch<192, DROP>(p, stream);
+      case 96: return fa_fwd_launch<96, DROP>(p, stream);
+      case 64: return fa_fwd_launch<64, DROP>(p, stream);
+      case 48: return fa_fwd_launch<48, DROP>(p, stream);
+      default: return S3D_ERR_UNSUPPORTED;
+    }
+  }
   switch (DH) {
-    case 192: return fa_fwd_launch<192, DROP>(p, stream);
-    case 96: return fa_fwd_launch<96, DROP>(p, stream);
-    case 64: return fa_fwd_launch<64, DROP>(p, stream);
-    case 48: return fa_fwd_launch<48, DROP>(p, stream);
+    case 256: return fa_fwd1_launch<256, DROP>(p, stream);
+    case 192: return fa_fwd1_launch<192, DROP>(p, stream);
+    case 96: return fa_fwd1_launch<96, DROP>(p, stream);
+    case 64: return fa_fwd1_launch<64, DROP>(p, stream);
+    case 48: return fa_fwd1_launch<48, DROP>(p, stream);
     default: return S3D_ERR_UNSUPPORTED;
   }
 }

@@ -64,6 +64,17 @@ __device__ __forceinline__ void epi_load(const GemmParams& p, uint32_t taddr, in
   tmem_ld_32x32b_x32(taddr, v);
   tc_wait_ld();
   const bool full = (n + 32 <= p.N);
+  if (p.bias != nullptr && split == 0 && full) {  // alpha * acc + bias on packed pairs
+    const float2 al = bcast2(p.alpha);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+      const float2 lo = ffma2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), al, make_float2(b4.x, b4.y));
+      const float2 hi = ffma2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), al, make_float2(b4.z, b4.w));
+      f[j] = lo.x; f[j + 1] = lo.y; f[j + 2] = hi.x; f[j + 3] = hi.y;
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
   if (p.bias != nullptr && split == 0 && n < p.N) {
@@ -84,7 +95,11 @@ __device__ __forceinline__ void epi_act(const GemmParams& p, int row, bool row_o
   const bool full = (n + 32 <= p.N);
   if (p.epilogue == EPI_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < 32; j += 2) {
+      const float2 g2 = gelu_erf2(make_float2(f[j], f[j + 1]));
+      f[j] = g2.x;
+      f[j + 1] = g2.y;
+    }
   } else if (p.epilogue == EPI_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -105,7 +120,11 @@ __device__ __forceinline__ void epi_act(const GemmParams& p, int row, bool row_o
     }
     if (p.epilogue == EPI_DGELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(a[j]);
+      for (int j = 0; j < 32; j += 2) {
+        const float2 g2 = fmul2(make_float2(f[j], f[j + 1]), gelu_erf_grad2(make_float2(a[j], a[j + 1])));
+        f[j] = g2.x;
+        f[j + 1] = g2.y;
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = a[j] > 0.f ? f[j] : 0.f;

@@ -84,7 +84,8 @@ int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream);
 int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream);
 // attention_tcgen05.cu (long sequences / dropout, dh in {48, 64, 96, 192}); S3D_ERR_UNSUPPORTED -> the layout is not a
 // slice of one 2-D qkv buffer and the caller uses the mma.sync kernels
-bool attn_tc_supported(int DH);
+bool attn_tc_supported(int DH);      // forward and backward
+bool attn_tc_fwd_supported(int DH);  // forward only: additionally head_dim 256 (all A operands fit tensor memory)
 int attn_fwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
 int attn_bwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
 

@@ -11,7 +11,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-GROUPS = ["attn_tc", "gemm_small", "gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
+GROUPS = ["attn_tc", "gemm_epi_perf", "gemm_small", "gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
 
 
 def rel_err(a, b):
@@ -56,6 +56,47 @@ def g_gemm_perf():
             torch.cuda.synchronize()
             ms = s.elapsed_time(e) / reps
             print(f"  [PERF] {name} M{M} N{N} K{K} BN{bn} cl{cl} split{sp}: {ms * 1e3:9.1f} us  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s", flush=True)
+
+
+def g_gemm_epi_perf():
+    """TFLOP/s of the epilogue-heavy cfg3 shapes (GELU + pre-activation save, dGELU, fp32 residual), default heuristics."""
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(0)
+    T, D = 188160, 768
+
+    def t(fn, reps=5):
+        for _ in range(2):
+            fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+    x = torch.randn(T, D, device="cuda").bfloat16()
+    w1 = torch.randn(4 * D, D, device="cuda").bfloat16()
+    b1 = torch.randn(4 * D, device="cuda")
+    pre = torch.empty(T, 4 * D, device="cuda", dtype=torch.bfloat16)
+    act = torch.empty(T, 4 * D, device="cuda", dtype=torch.bfloat16)
+    ms = t(lambda: L.gemm(x, w1, bias=b1, epilogue=L.EPI_GELU, aux_out=pre, out=act))
+    print(f"  [PERF] fc1 + bias + GELU (+pre-activation): {ms * 1e3:8.1f} us {2.0 * T * 4 * D * D / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    ms = t(lambda: L.gemm(x, w1, bias=b1, out=act))
+    print(f"  [PERF] fc1 + bias (plain epilogue):         {ms * 1e3:8.1f} us {2.0 * T * 4 * D * D / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    dy = torch.randn(T, D, device="cuda").bfloat16()
+    w2 = torch.randn(D, 4 * D, device="cuda").bfloat16()
+    ms = t(lambda: L.gemm(dy, w2, b_mn=True, epilogue=L.EPI_DGELU, aux_in=pre, out=act))
+    print(f"  [PERF] dX of fc2 with dGELU:                {ms * 1e3:8.1f} us {2.0 * T * 4 * D * D / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    res = torch.randn(T, D, device="cuda")
+    o32 = torch.empty(T, D, device="cuda")
+    b2 = torch.randn(D, device="cuda")
+    ms = t(lambda: L.gemm(act, w2, bias=b2, residual=res, out=o32))
+    print(f"  [PERF] fc2 + bias + fp32 residual:          {ms * 1e3:8.1f} us {2.0 * T * 4 * D * D / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    wp = torch.randn(D, D, device="cuda").bfloat16()
+    ms = t(lambda: L.gemm(x, wp, bias=b2, residual=res, out=o32))
+    print(f"  [PERF] proj + bias + fp32 residual:         {ms * 1e3:8.1f} us {2.0 * T * D * D / ms / 1e9:7.1f} TFLOP/s", flush=True)
 
 
 def g_gemm_small():
@@ -301,7 +342,8 @@ def g_attn_tc():
     for (B, N, H, dh, layout) in [(2, 1024, 4, 192, "seqfirst"), (3, 700, 4, 192, "seqfirst"), (2, 12544, 4, 192, "seqfirst"),
                                   (2, 513, 3, 64, "timm"), (3, 640, 2, 192, "timm"), (1, 2048, 3, 64, "timm"),
                                   (2, 700, 4, 96, "seqfirst"), (2, 600, 4, 48, "seqfirst"), (3, 100, 4, 96, "seqfirst"),
-                                  (2, 333, 4, 48, "timm")]:
+                                  (2, 333, 4, 48, "timm"), (4, 197, 3, 256, "timm"), (3, 257, 3, 64, "timm"),
+                                  (2, 64, 3, 256, "timm"), (2, 1000, 2, 256, "seqfirst"), (5, 65, 6, 64, "timm")]:
         qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
         lse = torch.empty(B, H, N, device="cuda")
         scale = dh ** -0.5
@@ -314,7 +356,8 @@ def g_attn_tc():
     # backward
     for (B, N, H, dh, layout) in [(2, 1024, 4, 192, "seqfirst"), (3, 700, 4, 192, "seqfirst"), (1, 12544, 4, 192, "seqfirst"),
                                   (2, 513, 3, 64, "timm"), (3, 640, 2, 192, "timm"), (2, 700, 4, 96, "seqfirst"),
-                                  (2, 600, 4, 48, "seqfirst"), (3, 100, 4, 96, "seqfirst"), (2, 333, 4, 48, "timm")]:
+                                  (2, 600, 4, 48, "seqfirst"), (3, 100, 4, 96, "seqfirst"), (2, 333, 4, 48, "timm"),
+                                  (3, 257, 3, 64, "timm"), (4, 197, 3, 256, "timm"), (2, 129, 6, 64, "timm")]:
         qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
         lse = torch.empty(B, H, N, device="cuda")
         delta = torch.empty(B, H, N, device="cuda")
@@ -361,6 +404,18 @@ def g_attn_tc():
                                    dk.data_ptr(), dv.data_ptr(), B, H, N, dh, qs, os_, dh ** -0.5))
     print(f"  [PERF] attn bwd group_embed shape B15 H4 S12544 dh192: {ms:.2f} ms  {10.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s "
           f"(algorithmic 5 GEMMs; 7 executed)", flush=True)
+    for (Bs, Ns, Hs, ds) in [(64, 197, 3, 256), (128, 257, 3, 64), (32, 513, 3, 64)]:
+        qkv2, q2, k2, v2, qs2, os2, out2, _ = _make_qkv(Bs, Ns, Hs, ds, "timm")
+        lse2 = torch.empty(Bs, Hs, Ns, device="cuda")
+        delta2 = torch.empty(Bs, Hs, Ns, device="cuda")
+        do2 = torch.randn_like(out2.float()).bfloat16()
+        dqkv2 = torch.zeros_like(qkv2)
+        ms = timeit(lambda: L.attn_fwd(q2, k2, v2, out2, lse2, Bs, Hs, Ns, ds, qs2, os2, ds ** -0.5), reps=20)
+        print(f"  [PERF] attn fwd timm B{Bs} N{Ns} H{Hs} dh{ds}: {ms * 1e3:.1f} us  {4.0 * Bs * Hs * Ns * Ns * ds / ms / 1e9:.1f} TFLOP/s", flush=True)
+        ms = timeit(lambda: L.attn_bwd(q2.data_ptr(), k2.data_ptr(), v2.data_ptr(), out2, do2, lse2, delta2,
+                                       dqkv2.select(2, 0).data_ptr(), dqkv2.select(2, 1).data_ptr(), dqkv2.select(2, 2).data_ptr(),
+                                       Bs, Hs, Ns, ds, qs2, os2, ds ** -0.5), reps=20)
+        print(f"  [PERF] attn bwd timm B{Bs} N{Ns} H{Hs} dh{ds}: {ms * 1e3:.1f} us  {10.0 * Bs * Hs * Ns * Ns * ds / ms / 1e9:.1f} TFLOP/s", flush=True)
     seed = torch.tensor([20210915], dtype=torch.int32, device="cuda")
     ms = timeit(lambda: L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, dh ** -0.5, drop_seed=seed, drop_site=1, drop_p=0.1))
     print(f"  [PERF] attn fwd group_embed shape, dropout p=0.1: {ms:.2f} ms  {4.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s", flush=True)
