@@ -1337,6 +1337,511 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
   }
 }
 
+// ------------------------------------------- dK and dV, split -------------------------------------------
+// The fused dK/dV kernel above needs 2 DH accumulator columns + S^T + dP^T = 512 TMEM columns at DH = 192, which leaves
+// no room for its resident A operands (the K and V tiles): they stay in shared memory and every one of its 24 S^T / dP^T
+// MMAs per block pays the ~110-cycle shared-memory A fetch (3800 cycles per block measured for 1536 cycles of math).
+// Split in two, every A operand fits tensor memory:
+//   dK kernel: K, V tiles in TMEM;  S^T = K Q^T, dP^T = V dO^T (TS mode), dS^T -> smem, dK += dS^T Q   (3 GEMM units)
+//   dV kernel: K tile in TMEM;      S^T = K Q^T (TS), P^T -> TMEM as bf16 pairs, dV += P^T dO (TS)     (2 GEMM units)
+// One more GEMM unit than the fused form (S^T twice), but all of it at the tensor-memory rate; both kernels stream the
+// Q / dO blocks through a 4-stage ring. The dK kernel is the dQ kernel with rows and columns exchanged (softmax statistics
+// and dropout rows belong to the streamed queries, i.e. to the COLUMNS of a block, and are staged in shared memory).
+template <int DH>
+struct FaDkCfg {
+  static constexpr int kCh = (DH + 63) / 64;
+  static constexpr int kStages = 4;
+  static constexpr int kBlkBytes = 64 * kCh * 128;     // 64-row streamed block (Q or dO)
+  static constexpr int kSBytes = 128 * 64 * 2;         // bf16 dS^T tile
+  static constexpr int kSmemBytes = 2 * kStages * kBlkBytes + 2 * kSBytes + 1024 + 2048;  // 232448 at DH = 192: the opt-in limit
+  static constexpr int kColS = DH, kColK = DH + 128, kColV = DH + 128 + DH / 2;
+  static_assert(2 * DH + 128 <= 512, "TMEM budget");
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+// rows of a resident 128-row operand tile -> tensor memory (bf16 pairs; element (row, k) = lane row, column k / 2)
+template <int DH>
+__device__ __forceinline__ void fill_tmem_rows(uint32_t taddr, const __nv_bfloat16* grow, bool valid, int part) {
+#pragma unroll 4
+  for (int g = part; g < DH / 8; g += kEwParts) {  // 8 bf16 = 16 bytes = 4 columns per step
+    uint4 a = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) a = *reinterpret_cast<const uint4*>(grow + g * 8);
+    tmem_st_32x32b_x4(taddr + g * 4, a.x, a.y, a.z, a.w);
+  }
+}
+
+template <int DH, bool DROP>
+__global__ void __launch_bounds__(kFaBwdThreads, 1)
+fa_bwd_dk_tc_kernel(const __grid_constant__ CUtensorMap tma_q64, const __grid_constant__ CUtensorMap tma_do64,
+                    const __nv_bfloat16* __restrict__ kbase, const __nv_bfloat16* __restrict__ vbase, const FaBwdParams p) {
+  using Cfg = FaDkCfg<DH>;
+  constexpr int NST = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                // [NST][kCh][64][128B]
+  uint8_t* sdO = sQ + NST * Cfg::kBlkBytes;          // [NST][kCh][64][128B]
+  uint8_t* sdST = sdO + NST * Cfg::kBlkBytes;        // [2][128][128B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdST + 2 * Cfg::kSBytes);
+  uint64_t* qdo_full = bars;               // [NST]
+  uint64_t* qdo_empty = bars + NST;        // [NST]
+  uint64_t* sp_full = bars + 2 * NST;      // [1]
+  uint64_t* s_free = sp_full + 1;          // [1]
+  uint64_t* ds_full = sp_full + 2;         // [2]
+  uint64_t* ds_free = sp_full + 4;         // [2]
+  uint64_t* a_ready = sp_full + 6;         // [1]
+  uint64_t* acc_full = sp_full + 7;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp_full + 8);
+  float* s_nlse = reinterpret_cast<float*>(sp_full + 10);       // [2][64]  -lse * log2(e) of the block's queries
+  float* s_ndel = s_nlse + 128;                                 // [2][64]  -delta
+  uint32_t* s_rk = reinterpret_cast<uint32_t*>(s_ndel + 128);   // [2][64]  dropout row keys
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int k0 = blockIdx.x * 128;
+  const int nq = (p.N + 63) / 64;
+  const int row_base = (int)(b * p.row_bs);
+  const int cq = (int)(b * p.col_bs) + p.col_q + h * DH;
+  const int o_row_base = (int)(b * p.o_row_bs);
+  const int co = (int)(b * p.o_col_bs) + h * DH;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q64);
+    tma_prefetch_desc(&tma_do64);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(sp_full, 1);
+    mbar_init(s_free, kEwWarps);
+    mbar_init(a_ready, kEwWarps);
+    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ds_full[i], kEwWarps);
+      mbar_init(&ds_free[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int j = 0; j < nq; ++j) {
+        const int st = j % NST;
+        mbar_wait(&qdo_empty[st], ((j / NST) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[st], 2 * Cfg::kBlkBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kCh; ++c) {
+          tma_load_2d(sQ + st * Cfg::kBlkBytes + c * (64 * 128), &tma_q64, &qdo_full[st], cq + 64 * c, row_base + j * 64);
+          tma_load_2d(sdO + st * Cfg::kBlkBytes + c * (64 * 128), &tma_do64, &qdo_full[st], co + 64 * c, o_row_base + j * 64);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_a = make_idesc_bf16(128, DH, 0, 1);
+    constexpr uint32_t hi = smem_desc_hi_sw128(1024);
+    const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16), do_lo = smem_desc_lo(smem_u32(sdO), 16);
+    const uint32_t qmn_lo = smem_desc_lo(smem_u32(sQ), 64 * 128), dst_lo = smem_desc_lo(smem_u32(sdST), 16);
+    const uint32_t t_s = tmem_base + Cfg::kColS, t_dp = t_s + 64;
+    const uint32_t t_k = tmem_base + Cfg::kColK, t_v = tmem_base + Cfg::kColV;
+    auto issue_dk = [&](int j) {  // dK += dS^T(j) Q(j)
+      const int u = j & 1, st = j % NST;
+      mbar_wait(&ds_full[u], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a = dst_lo + u * (Cfg::kSBytes >> 4), bb = qmn_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16_ss2(tmem_base, a + ((kk * 32) >> 4), hi, bb + ((kk * 2048) >> 4), hi, idesc_a, (j > 0) || (kk != 0));
+        umma_commit(&qdo_empty[st]);
+        umma_commit(&ds_free[u]);
+        if (j + 1 == nq) umma_commit(acc_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(a_ready, 0);
+    for (int j = 0; j < nq; ++j) {
+      const int st = j % NST;
+      mbar_wait(&qdo_full[st], (j / NST) & 1);
+      if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+      tc_fence_after();
+      const uint32_t bq = q_lo + st * (Cfg::kBlkBytes >> 4), bo = do_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)  // S^T = K Q^T
+          umma_f16_ts(t_s, t_k + kk * 8, ((uint64_t)hi << 32) | (bq + kstep_off<64>(kk)), idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)  // dP^T = V dO^T
+          umma_f16_ts(t_dp, t_v + kk * 8, ((uint64_t)hi << 32) | (bo + kstep_off<64>(kk)), idesc_s, kk != 0);
+        umma_commit(sp_full);
+      }
+      __syncwarp();
+      if (j > 0) issue_dk(j - 1);
+    }
+    issue_dk(nq - 1);
+  } else {
+    const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;      // which kEwCols of the 64 query columns of a block this thread handles
+    const int r = quad * 32 + lane;        // key row within the tile
+    const int tid = threadIdx.x - 64;
+    const int krow = k0 + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const long long bh = (long long)b * p.H + h;
+    {
+      const long long off = (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
+      fill_tmem_rows<DH>(tmem_base + lane_addr + Cfg::kColK, kbase + off, krow < p.N, part);
+      fill_tmem_rows<DH>(tmem_base + lane_addr + Cfg::kColV, vbase + off, krow < p.N, part);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    const float c = p.scale * kFaLog2e;
+    const float2 c2 = make_float2(c, c);
+    const float ks = DROP ? p.drop_scale : 1.0f;
+    const float2 ks2 = make_float2(ks, ks);
+    const uint32_t site_seed = DROP ? drop_site_seed(*p.drop_seed, p.drop_site) : 0u;
+    const uint32_t colterm = ((uint32_t)krow >> 1) * kDropColMul;
+    const uint32_t sel = (krow & 1) ? 0x7632u : 0x5410u;
+    const uint32_t thresh2 = p.drop_thresh14 * 0x00010001u;
+    uint32_t z[DROP ? kEwCols / 2 : 1];
+    // Per-query statistics of a block (-lse, -delta, dropout row key) are staged in shared memory by the first 192
+    // threads. The global loads are issued TWO blocks ahead into a register and stored one block ahead, so their latency
+    // never sits in front of the block barrier (with a plain load-then-store the staging warps stalled ~700 cycles at the
+    // top of every block and everybody waited for them).
+    auto stage_load = [&](int j) -> float {
+      const int qi = j * 64 + (tid & 63);
+      if (tid < 64) return (j < nq && qi < p.N) ? -p.lse[bh * p.N + qi] * kFaLog2e : -INFINITY;
+      if (tid < 128) return (j < nq && qi < p.N) ? -p.delta[bh * p.N + qi] : 0.f;
+      return 0.f;
+    };
+    auto stage_store = [&](int j, float val) {
+      const int u = j & 1;
+      if (tid < 64) s_nlse[u * 64 + tid] = val;
+      else if (tid < 128) s_ndel[u * 64 + (tid & 63)] = val;
+      else if (DROP && tid < 192)
+        s_rk[u * 64 + (tid & 63)] = drop_rowkey(site_seed, (uint32_t)bh * (uint32_t)p.N + (uint32_t)(j * 64 + (tid & 63)));
+    };
+    auto make_words = [&](int j) {
+      const uint4* rk4 = reinterpret_cast<const uint4*>(s_rk + (j & 1) * 64 + part * kEwCols);
+#pragma unroll
+      for (int g = 0; g < kEwCols / 4; ++g) {
+        const uint4 rk = rk4[g];
+        const uint32_t z0 = drop_word(rk.x + colterm), z1 = drop_word(rk.y + colterm);
+        const uint32_t z2 = drop_word(rk.z + colterm), z3 = drop_word(rk.w + colterm);
+        z[2 * g] = __byte_perm(z0, z1, sel);
+        z[2 * g + 1] = __byte_perm(z2, z3, sel);
+      }
+    };
+    stage_store(0, stage_load(0));
+    float pend = stage_load(1);
+    asm volatile("bar.sync 1, %0;" ::"n"(kEwThreads) : "memory");
+    if (DROP) make_words(0);
+    for (int j = 0; j < nq; ++j) {
+      const int u = j & 1;
+      if (j + 1 < nq) stage_store(j + 1, pend);
+      pend = stage_load(j + 2);
+      mbar_wait(sp_full, j & 1);
+      tc_fence_after();
+      uint32_t a0[kEwCols], d0[kEwCols];
+      const uint32_t s_addr = tmem_base + lane_addr + Cfg::kColS + part * kEwCols;
+      tmem_ld_cols(s_addr, a0);
+      tmem_ld_cols(s_addr + 64, d0);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      uint32_t wd[kEwCols / 2];
+      const float2* lrow = reinterpret_cast<const float2*>(s_nlse + u * 64 + part * kEwCols);
+      const float2* drow = reinterpret_cast<const float2*>(s_ndel + u * 64 + part * kEwCols);
+#pragma unroll
+      for (int i = 0; i < kEwCols / 2; ++i) {
+        const float2 x = ffma2(make_float2(__uint_as_float(a0[2 * i]), __uint_as_float(a0[2 * i + 1])), c2, lrow[i]);
+        const float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        float2 dp = make_float2(__uint_as_float(d0[2 * i]), __uint_as_float(d0[2 * i + 1]));
+        if (DROP) drop_zero2(dp.x, dp.y, z[i], thresh2);
+        const float2 e = fmul2(pr, ffma2(dp, ks2, drow[i]));
+        wd[i] = pack_bf16x2(e.x, e.y);
+      }
+      if (j >= 2) mbar_wait(&ds_free[u], ((j >> 1) - 1) & 1);
+      store_part_row_sw128(sdST + u * Cfg::kSBytes + r * 128, r, part, wd);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[u]);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEwThreads) : "memory");  // staging of block j + 1 complete / buffer u reusable
+      if (DROP && j + 1 < nq) make_words(j + 1);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* kr = p.dk + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
+#pragma unroll 1
+    for (int cc = part * 16; cc < DH; cc += 16 * kEwParts) {
+      uint32_t ok[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_addr + cc, ok);
+      tc_wait_ld();
+      if (krow < p.N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          uint4 wv;
+          wv.x = pack_bf16x2(__uint_as_float(ok[i]) * p.scale, __uint_as_float(ok[i + 1]) * p.scale);
+          wv.y = pack_bf16x2(__uint_as_float(ok[i + 2]) * p.scale, __uint_as_float(ok[i + 3]) * p.scale);
+          wv.z = pack_bf16x2(__uint_as_float(ok[i + 4]) * p.scale, __uint_as_float(ok[i + 5]) * p.scale);
+          wv.w = pack_bf16x2(__uint_as_float(ok[i + 6]) * p.scale, __uint_as_float(ok[i + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(kr + cc + i) = wv;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int DH>
+struct FaDvCfg {
+  static constexpr int kCh = (DH + 63) / 64;
+  static constexpr int kStages = 4;
+  static constexpr int kBlkBytes = 64 * kCh * 128;
+  static constexpr int kSmemBytes = 2 * kStages * kBlkBytes + 1024 + 2048;
+  static constexpr int kColS = DH, kColP = DH + 64, kColK = DH + 96;
+};
+
+template <int DH, bool DROP>
+__global__ void __launch_bounds__(kFaBwdThreads, 1)
+fa_bwd_dv_tc_kernel(const __grid_constant__ CUtensorMap tma_q64, const __grid_constant__ CUtensorMap tma_do64,
+                    const __nv_bfloat16* __restrict__ kbase, const FaBwdParams p) {
+  using Cfg = FaDvCfg<DH>;
+  constexpr int NST = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                // [NST][kCh][64][128B]
+  uint8_t* sdO = sQ + NST * Cfg::kBlkBytes;          // [NST][kCh][64][128B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdO + NST * Cfg::kBlkBytes);
+  uint64_t* q_full = bars;                 // [NST]
+  uint64_t* do_full = bars + NST;          // [NST]
+  uint64_t* qdo_empty = bars + 2 * NST;    // [NST]
+  uint64_t* s_full = bars + 3 * NST;       // [1]
+  uint64_t* s_free = s_full + 1;           // [1]
+  uint64_t* p_full = s_full + 2;           // [1] P^T written to tensor memory
+  uint64_t* pv_done = s_full + 3;          // [1] dV MMAs of a block retired
+  uint64_t* a_ready = s_full + 4;          // [1]
+  uint64_t* acc_full = s_full + 5;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  float* s_nlse = reinterpret_cast<float*>(s_full + 8);         // [2][64]
+  uint32_t* s_rk = reinterpret_cast<uint32_t*>(s_nlse + 128);   // [2][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int k0 = blockIdx.x * 128;
+  const int nq = (p.N + 63) / 64;
+  const int row_base = (int)(b * p.row_bs);
+  const int cq = (int)(b * p.col_bs) + p.col_q + h * DH;
+  const int o_row_base = (int)(b * p.o_row_bs);
+  const int co = (int)(b * p.o_col_bs) + h * DH;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q64);
+    tma_prefetch_desc(&tma_do64);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&do_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, kEwWarps);
+    mbar_init(p_full, kEwWarps);
+    mbar_init(pv_done, 1);
+    mbar_init(a_ready, kEwWarps);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int j = 0; j < nq; ++j) {
+        const int st = j % NST;
+        mbar_wait(&qdo_empty[st], ((j / NST) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], Cfg::kBlkBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kCh; ++c)
+          tma_load_2d(sQ + st * Cfg::kBlkBytes + c * (64 * 128), &tma_q64, &q_full[st], cq + 64 * c, row_base + j * 64);
+        mbar_expect_tx(&do_full[st], Cfg::kBlkBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kCh; ++c)
+          tma_load_2d(sdO + st * Cfg::kBlkBytes + c * (64 * 128), &tma_do64, &do_full[st], co + 64 * c, o_row_base + j * 64);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_a = make_idesc_bf16(128, DH, 0, 1);
+    constexpr uint32_t hi = smem_desc_hi_sw128(1024);
+    const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16), domn_lo = smem_desc_lo(smem_u32(sdO), 64 * 128);
+    const uint32_t t_s = tmem_base + Cfg::kColS, t_p = tmem_base + Cfg::kColP, t_k = tmem_base + Cfg::kColK;
+    auto issue_dv = [&](int j) {  // dV += P^T(j) dO(j), A from tensor memory
+      const int st = j % NST;
+      mbar_wait(&do_full[st], (j / NST) & 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      const uint32_t bb = domn_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16_ts(tmem_base, t_p + kk * 8, ((uint64_t)hi << 32) | (bb + ((kk * 2048) >> 4)), idesc_a, (j > 0) || (kk != 0));
+        umma_commit(&qdo_empty[st]);
+        umma_commit(pv_done);
+        if (j + 1 == nq) umma_commit(acc_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(a_ready, 0);
+    for (int j = 0; j < nq; ++j) {
+      const int st = j % NST;
+      mbar_wait(&q_full[st], (j / NST) & 1);
+      if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+      tc_fence_after();
+      const uint32_t bq = q_lo + st * (Cfg::kBlkBytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)  // S^T = K Q^T
+          umma_f16_ts(t_s, t_k + kk * 8, ((uint64_t)hi << 32) | (bq + kstep_off<64>(kk)), idesc_s, kk != 0);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      if (j > 0) issue_dv(j - 1);
+    }
+    issue_dv(nq - 1);
+  } else {
+    const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    const int krow = k0 + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const long long bh = (long long)b * p.H + h;
+    {
+      const long long off = (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
+      fill_tmem_rows<DH>(tmem_base + lane_addr + Cfg::kColK, kbase + off, krow < p.N, part);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    const float c = p.scale * kFaLog2e;
+    const float2 c2 = make_float2(c, c);
+    const uint32_t site_seed = DROP ? drop_site_seed(*p.drop_seed, p.drop_site) : 0u;
+    const uint32_t colterm = ((uint32_t)krow >> 1) * kDropColMul;
+    const uint32_t sel = (krow & 1) ? 0x7632u : 0x5410u;
+    const uint32_t thresh2 = p.drop_thresh14 * 0x00010001u;
+    uint32_t mk[DROP ? kEwCols / 2 : 1];  // AND-masks of the packed P^T pairs (two consecutive queries of this key)
+    auto stage_load = [&](int j) -> float {  // issued two blocks ahead (see the dK kernel)
+      const int qi = j * 64 + (tid & 63);
+      return (tid < 64 && j < nq && qi < p.N) ? -p.lse[bh * p.N + qi] * kFaLog2e : -INFINITY;
+    };
+    auto stage_store = [&](int j, float val) {
+      const int u = j & 1;
+      if (tid < 64) s_nlse[u * 64 + tid] = val;
+      else if (DROP && tid < 128)
+        s_rk[u * 64 + (tid & 63)] = drop_rowkey(site_seed, (uint32_t)bh * (uint32_t)p.N + (uint32_t)(j * 64 + (tid & 63)));
+    };
+    auto make_masks = [&](int j) {
+      const uint4* rk4 = reinterpret_cast<const uint4*>(s_rk + (j & 1) * 64 + part * kEwCols);
+#pragma unroll
+      for (int g = 0; g < kEwCols / 4; ++g) {
+        const uint4 rk = rk4[g];
+        const uint32_t z0 = drop_word(rk.x + colterm), z1 = drop_word(rk.y + colterm);
+        const uint32_t z2 = drop_word(rk.z + colterm), z3 = drop_word(rk.w + colterm);
+        mk[2 * g] = drop_andmask(__byte_perm(z0, z1, sel), thresh2);
+        mk[2 * g + 1] = drop_andmask(__byte_perm(z2, z3, sel), thresh2);
+      }
+    };
+    stage_store(0, stage_load(0));
+    float pend = stage_load(1);
+    asm volatile("bar.sync 1, %0;" ::"n"(kEwThreads) : "memory");
+    if (DROP) make_masks(0);
+    const uint32_t p_addr = tmem_base + lane_addr + Cfg::kColP + part * (kEwCols / 2);
+    for (int j = 0; j < nq; ++j) {
+      const int u = j & 1;
+      if (j + 1 < nq) stage_store(j + 1, pend);
+      pend = stage_load(j + 2);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t a0[kEwCols];
+      tmem_ld_cols(tmem_base + lane_addr + Cfg::kColS + part * kEwCols, a0);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      uint32_t wp[kEwCols / 2];
+      const float2* lrow = reinterpret_cast<const float2*>(s_nlse + u * 64 + part * kEwCols);
+#pragma unroll
+      for (int i = 0; i < kEwCols / 2; ++i) {
+        const float2 x = ffma2(make_float2(__uint_as_float(a0[2 * i]), __uint_as_float(a0[2 * i + 1])), c2, lrow[i]);
+        wp[i] = pack_bf16x2(fast_exp2(x.x), fast_exp2(x.y));
+        if (DROP) wp[i] &= mk[i];  // dV = (P o mask / (1 - p))^T dO; the 1 / (1 - p) is applied to the accumulator at the end
+      }
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // dV MMAs of block j-1 no longer read the P^T columns
+        tc_fence_after();
+      }
+      static_assert(kEwCols / 2 == 8, "P^T store shape");
+      tmem_st_32x32b_x8(p_addr, wp);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEwThreads) : "memory");
+      if (DROP && j + 1 < nq) make_masks(j + 1);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const float ks = DROP ? p.drop_scale : 1.0f;
+    __nv_bfloat16* vr = p.dv + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)krow * p.qkv_rs;
+#pragma unroll 1
+    for (int cc = part * 16; cc < DH; cc += 16 * kEwParts) {
+      uint32_t ov[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_addr + cc, ov);
+      tc_wait_ld();
+      if (krow < p.N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          uint4 wv;
+          wv.x = pack_bf16x2(__uint_as_float(ov[i]) * ks, __uint_as_float(ov[i + 1]) * ks);
+          wv.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * ks, __uint_as_float(ov[i + 3]) * ks);
+          wv.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * ks, __uint_as_float(ov[i + 5]) * ks);
+          wv.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * ks, __uint_as_float(ov[i + 7]) * ks);
+          *reinterpret_cast<uint4*>(vr + cc + i) = wv;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 __global__ void __launch_bounds__(256) fa_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                                       float* __restrict__ delta, int B, int H, int N, int DH, long long o_bs,
                                                       long long o_hs, long long o_rs) {
@@ -1426,8 +1931,32 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
       (reinterpret_cast<uintptr_t>(a.dout) & 15))
     return S3D_ERR_ALIGNMENT;  // 16-byte row loads of Q / dO
   dim3 grid((a.N + 127) / 128, a.H, a.B);
-  kkv<<<grid, kFaBwdThreads, Cfg::kSmemBytes, stream>>>(t128, t64, d64, p);
-  S3D_LAUNCH_OK();
+  // Split dK / dV kernels (all A operands in tensor memory) or the fused dK/dV kernel (K, V tiles in shared memory)?
+  // Measured on the group_embed shape (B = 15, H = 4, S = 12544, dh = 192), dK + dV:
+  //     without dropout   split 7.8 + 5.8 = 13.6 ms (tensor pipe 71 % / 62 %)    fused 15.4 ms (41 %)
+  //     dropout p = 0.1   split 11.4 + 9.3 = 20.7 ms                             fused 16.2 ms
+  // The split form runs the mask hash twice (once per kernel, one hash word per ELEMENT in the key-row orientation) and
+  // is then bound by its element-wise warps; the fused form hides the hash behind its shared-memory operand fetches.
+  // S3D_FA_DKV=fused / split forces one of them.
+  static const int forced = []() { const char* v = getenv("S3D_FA_DKV"); return v == nullptr ? 0 : (v[0] == 'f' ? 1 : (v[0] == 's' ? 2 : 0)); }();
+  const bool fused = forced == 1 || (forced == 0 && DROP);
+  if (fused) {
+    kkv<<<grid, kFaBwdThreads, Cfg::kSmemBytes, stream>>>(t128, t64, d64, p);
+    S3D_LAUNCH_OK();
+  } else {
+    auto kdk = fa_bwd_dk_tc_kernel<DH, DROP>;
+    auto kdv = fa_bwd_dv_tc_kernel<DH, DROP>;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      S3D_CUDA_OK(cudaFuncSetAttribute(kdk, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDkCfg<DH>::kSmemBytes));
+      S3D_CUDA_OK(cudaFuncSetAttribute(kdv, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDvCfg<DH>::kSmemBytes));
+      attr2_set = true;
+    }
+    kdk<<<grid, kFaBwdThreads, FaDkCfg<DH>::kSmemBytes, stream>>>(t64, d64, a.k, a.v, p);
+    S3D_LAUNCH_OK();
+    kdv<<<grid, kFaBwdThreads, FaDvCfg<DH>::kSmemBytes, stream>>>(t64, d64, a.k, p);
+    S3D_LAUNCH_OK();
+  }
   kq<<<grid, kFaBwdThreads, FaDqCfg<DH>::kSmemBytes, stream>>>(t64, a.q, a.dout, p);
   S3D_LAUNCH_OK();
   return S3D_OK;

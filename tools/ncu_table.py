@@ -2,6 +2,7 @@
 bench.py's `roofline.traffic` / `roofline.ncu` are read from (run here, no GPU needed):
 
     python tools/ncu_table.py gpurun_out/r02_shapes.ncu-rep gpurun_out/ncu_shapes_order.json [profiles/ncu_table.json]
+    (or the raw page exported on the GPU box: ncu -i X.ncu-rep --page raw --csv > gpurun_out/r02_shapes_raw.csv)
 
 Per (kernel, shape) key: traffic = dram__bytes_read.sum + dram__bytes_write.sum (bytes, summed over the kernels of the
 call), ms = gpu__time_duration (summed), tensor_pipe_pct = sm__pipe_tensor_cycles_active (duration-weighted mean), plus
@@ -28,7 +29,10 @@ def main():
     rep, order_path = sys.argv[1], sys.argv[2]
     out_path = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                                   "profiles", "ncu_table.json")
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # `ncu -i X.ncu-rep --page raw --csv` run on the GPU box (full reports exceed the copy-back limit)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units, data = rows[0], rows[1], rows[2:]
     col = {n: i for i, n in enumerate(head)}
