@@ -1238,12 +1238,20 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
     const uint32_t sel = (krow & 1) ? 0x7632u : 0x5410u;
     const uint32_t thresh2 = p.drop_thresh14 * 0x00010001u;
     uint32_t z[DROP ? kEwCols / 2 : 1];  // per query pair (2i, 2i+1) of this thread's queries
-    auto stage = [&](int j) {   // lse / delta / row keys of query block j (padded queries: lse = +inf -> P = 0)
-      const int u = j & 1;
+    // lse / delta / row keys of a query block (padded queries: lse = +inf -> P = 0): global loads two blocks ahead into a
+    // register, shared-memory store one block ahead (see the dK kernel below)
+    auto stage_load = [&](int j) -> float {
       const int qi = j * 64 + (tid & 63);
-      if (tid < 64) s_nlse[u * 64 + tid] = qi < p.N ? -p.lse[bh * p.N + qi] * kFaLog2e : -INFINITY;
-      else if (tid < 128) s_ndel[u * 64 + (tid & 63)] = qi < p.N ? -p.delta[bh * p.N + qi] : 0.f;
-      else if (DROP && tid < 192) s_rk[u * 64 + (tid & 63)] = drop_rowkey(site_seed, (uint32_t)bh * (uint32_t)p.N + (uint32_t)qi);
+      if (tid < 64) return (j < nq && qi < p.N) ? -p.lse[bh * p.N + qi] * kFaLog2e : -INFINITY;
+      if (tid < 128) return (j < nq && qi < p.N) ? -p.delta[bh * p.N + qi] : 0.f;
+      return 0.f;
+    };
+    auto stage_store = [&](int j, float val) {
+      const int u = j & 1;
+      if (tid < 64) s_nlse[u * 64 + tid] = val;
+      else if (tid < 128) s_ndel[u * 64 + (tid & 63)] = val;
+      else if (DROP && tid < 192)
+        s_rk[u * 64 + (tid & 63)] = drop_rowkey(site_seed, (uint32_t)bh * (uint32_t)p.N + (uint32_t)(j * 64 + (tid & 63)));
     };
     auto make_words = [&](int j) {
       const uint4* rk4 = reinterpret_cast<const uint4*>(s_rk + (j & 1) * 64 + part * kEwCols);
@@ -1256,12 +1264,14 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid
         z[2 * g + 1] = __byte_perm(z2, z3, sel);
       }
     };
-    stage(0);
+    stage_store(0, stage_load(0));
+    float pend = stage_load(1);
     asm volatile("bar.sync 1, %0;" ::"n"(kEwThreads) : "memory");
     if (DROP) make_words(0);
     for (int j = 0; j < nq; ++j) {
       const int u = j & 1;
-      if (j + 1 < nq) stage(j + 1);  // buffer u^1: its last readers finished block j-1 before the barrier below of j-1
+      if (j + 1 < nq) stage_store(j + 1, pend);  // buffer u^1: its last readers finished block j-1 before the barrier of j-1
+      pend = stage_load(j + 2);
       mbar_wait(sp_full, j & 1);
       tc_fence_after();
       uint32_t a0[kEwCols], d0[kEwCols];

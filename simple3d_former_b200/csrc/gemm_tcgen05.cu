@@ -28,17 +28,24 @@ namespace s3d {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
 
-template <int BN>
+// EPW = epilogue warps per TMEM lane quadrant: 2 (8 warps) by default, 4 (16 warps) for the activation-GRADIENT
+// epilogues (dGELU, dReLU: global aux read -> ~10 packed instructions per element -> pack -> staging -> TMA store is a
+// dependent chain; four warps per scheduler hide more of it). Their 64 KB of staging tiles cost one operand stage at
+// BN = 256, which is why the other epilogues keep 8 warps.
+template <int BN, int EPW>
 struct GemmCfg {
+  static constexpr int kEpiWarps = 4 * EPW;
+  static constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kStagingBytes = (BN >= 128) ? 8 * 4096 : 0;  // TMA-store staging (BN = 64 stores directly)
+  static constexpr int kStagingBytes = (BN >= 128) ? kEpiWarps * 4096 : 0;  // TMA-store staging (BN = 64 stores directly)
+  static constexpr int kMaxStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kFit = (232448 - kStagingBytes - 1024 - 256) / kStageBytes;
+  static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -169,16 +176,16 @@ __device__ __forceinline__ void stage_f32(uint8_t* srow, int r, const float (&f)
     *reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4)) = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
 }
 
-template <int BN, int A_MN, int B_MN, int CL>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BN, int A_MN, int B_MN, int CL, int EPW>
+__global__ void __launch_bounds__(GemmCfg<BN, EPW>::kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
                  const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPW>;
   pdl_trigger();  // the next grid may be scheduled (and run its on-chip prologue) while this one works
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes;  // 8 epilogue warps x 4 KB (TMA-store staging)
+  uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes;  // one 4 KB TMA-store staging tile per epilogue warp
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
@@ -215,7 +222,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], Cfg::kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -337,10 +344,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp >= kEpiWarp0) {
     // -------------------------------------------- epilogue --------------------------------------------
-    const int e = warp - kEpiWarp0;  // 0..7
+    const int e = warp - kEpiWarp0;  // 0 .. 4 * EPW - 1
     const int quad = warp & 3;       // TMEM lane quadrant this warp may access
-    const int half = e >> 2;         // which half of the BN columns
-    constexpr int kColsPerHalf = BN / 2;
+    const int half = e >> 2;         // which part (1 / EPW) of the BN columns
+    constexpr int kColsPerHalf = BN / EPW;
     int as = 0;
     uint32_t aphase = 0;
     const long long boff_d = p.batched ? (long long)batch * p.batch_stride_d : 0;
@@ -686,9 +693,9 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int A_MN, int B_MN, int CL>
+template <int BN, int A_MN, int B_MN, int CL, int EPW>
 static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPW>;
   CUtensorMap ta, tb;
   int rc;
   const GemmParams& p = g.p;
@@ -720,7 +727,7 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CL>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CL, EPW>;
   static bool attr_set = false;
   if (!attr_set) {
     S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -735,7 +742,7 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const int clusters = items < max_clusters ? items : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CL, nb, 1);
-  cfg.blockDim = dim3(kNumThreads, 1, 1);
+  cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -753,10 +760,23 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
 
 template <int BN, int CL>
 static int dispatch_major(const GemmArgs& g, cudaStream_t s) {
-  if (g.a_mn == 0 && g.b_mn == 0) return launch_gemm<BN, 0, 0, CL>(g, s);
-  if (g.a_mn == 1 && g.b_mn == 1) return launch_gemm<BN, 1, 1, CL>(g, s);
-  if (g.a_mn == 0 && g.b_mn == 1) return launch_gemm<BN, 0, 1, CL>(g, s);
-  return launch_gemm<BN, 1, 0, CL>(g, s);
+  // 16 epilogue warps for the activation epilogues (forward K-major x K-major, dX K-major x MN-major), see GemmCfg;
+  // S3D_GEMM_EPW=2 / 4 forces the 8- / 16-warp epilogue wherever it is instantiated
+  static const int forced = []() { const char* v = getenv("S3D_GEMM_EPW"); return v == nullptr ? 0 : atoi(v); }();
+  // measured on the cfg3 MLP shapes: dGELU 1002 -> 968 us with 16 warps; the GELU GEMM (two output tiles, 2.3 GB of
+  // writes in 0.9 ms: DRAM-write bound) and the plain epilogues are faster with 8 warps and the fourth operand stage
+  const bool act = (g.p.epilogue == EPI_DGELU || g.p.epilogue == EPI_DRELU) && g.p.splits == 1 && BN >= 128;
+  const bool heavy = BN >= 128 && g.a_mn == 0 && (forced == 4 || (forced != 2 && act));
+  if (g.a_mn == 0 && g.b_mn == 0) {
+    if constexpr (BN >= 128) { if (heavy) return launch_gemm<BN, 0, 0, CL, 4>(g, s); }
+    return launch_gemm<BN, 0, 0, CL, 2>(g, s);
+  }
+  if (g.a_mn == 1 && g.b_mn == 1) return launch_gemm<BN, 1, 1, CL, 2>(g, s);
+  if (g.a_mn == 0 && g.b_mn == 1) {
+    if constexpr (BN >= 128) { if (heavy) return launch_gemm<BN, 0, 1, CL, 4>(g, s); }
+    return launch_gemm<BN, 0, 1, CL, 2>(g, s);
+  }
+  return launch_gemm<BN, 1, 0, CL, 2>(g, s);
 }
 
 static unsigned env_u32(const char* name, unsigned dflt) {

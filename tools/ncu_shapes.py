@@ -2,7 +2,7 @@
 C ABI, in a fixed order. The order (shape key -> kernel-name patterns) is written to gpurun_out/ncu_shapes_order.json and
 tools/ncu_table.py joins it with the capture:
 
-    ncu --set full --clock-control none -k regex:"gemm_bf16|fa_|attn_|layernorm|colsum" -o gpurun_out/r02_shapes \\
+    ncu --set full --clock-control none -k regex:"gemm_bf16|fa_|attn_|layernorm|colsum" -o /tmp/r02_shapes \\
         python tools/ncu_shapes.py
     python tools/ncu_table.py gpurun_out/r02_shapes.ncu-rep gpurun_out/ncu_shapes_order.json   # -> profiles/ncu_table.json
 """
@@ -94,7 +94,7 @@ def attn(B, N, H, dh, seqfirst, drop):
     db = dqkv.data_ptr()
     L.attn_bwd(b, b + 2 * E, b + 4 * E, o, rn(B * N, E), lse, delta, db, db + 2 * E, db + 4 * E, B, H, N, dh, qs, os_,
                dh ** -0.5, **kw)
-    pats = ["fa_delta", "fa_bwd_dk_", "fa_bwd_dv_", "fa_bwd_dq"] if tc else (["attn_bwd_small"] if N <= 16 else ["attn_delta", "attn_bwd_dq", "attn_bwd_dkv"])
+    pats = (["fa_delta", "fa_bwd_dkv", "fa_bwd_dq"] if drop else ["fa_delta", "fa_bwd_dk_", "fa_bwd_dv_", "fa_bwd_dq"]) if tc else (["attn_bwd_small"] if N <= 16 else ["attn_delta", "attn_bwd_dq", "attn_bwd_dkv"])
     order.append((f"s3d_attn_bwd[B={B},H={H},N={N},dh={dh},drop={int(drop)}]", pats))
     torch.cuda.synchronize()
 
