@@ -36,6 +36,7 @@ constexpr int kEpiWarp0 = 4;
 // BN = 256, which is why the other epilogues keep 8 warps.
 template <int BN, int EPW>
 struct GemmCfg {
+  static_assert(EPW == 2 || (EPW == 4 && BN == 256), "a part of the tile must span whole 128-byte staging rows");
   static constexpr int kEpiWarps = 4 * EPW;
   static constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
   static constexpr int kABytes = BM * BK * 2;
@@ -136,6 +137,58 @@ __device__ __forceinline__ void epi_act(const GemmParams& p, int row, bool row_o
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = a[j] > 0.f ? f[j] : 0.f;
     }
+  }
+}
+
+// Epilogue operands (bf16 aux of dGELU / dReLU, fp32 residual) through the warp's staging tile: the natural layout of
+// the epilogue is lane = row, so a direct read makes every 16-byte load of a warp touch 32 different 128-byte lines
+// (~32 LSU cycles per instruction, ~4 k cycles per 128 x 256 tile -- the dGELU GEMM ran at 48 % tensor pipe). Here the
+// warp loads its 32 x 128-byte operand tile with COALESCED loads (8 lanes per row), parks it in the swizzled staging tile
+// and every lane then reads its own row from shared memory.
+__device__ __forceinline__ void epi_operand_to_stage(uint8_t* stage, const uint8_t* src, long long pitch_bytes, int rows_ok,
+                                                     int lane) {
+  uint4 t[8];
+  const int piece = lane & 7, r0 = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + r0;
+    t[i] = rr < rows_ok ? __ldg(reinterpret_cast<const uint4*>(src + rr * pitch_bytes + piece * 16)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (lane == 0) tma_store_wait_read();  // the previous TMA store has finished reading the tile
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + r0;
+    *reinterpret_cast<uint4*>(stage + rr * 128 + ((piece ^ (rr & 7)) << 4)) = t[i];
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void epi_act_grad_smem(const GemmParams& p, const uint8_t* srow, int r, int hh, float (&f)[32]) {
+  float a[32];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = *reinterpret_cast<const uint4*>(srow + (((hh * 4 + q) ^ (r & 7)) << 4));
+    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+    a[q * 8] = a0.x; a[q * 8 + 1] = a0.y; a[q * 8 + 2] = a1.x; a[q * 8 + 3] = a1.y;
+    a[q * 8 + 4] = a2.x; a[q * 8 + 5] = a2.y; a[q * 8 + 6] = a3.x; a[q * 8 + 7] = a3.y;
+  }
+  if (p.epilogue == EPI_DGELU) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float2 g2 = fmul2(make_float2(f[j], f[j + 1]), gelu_erf_grad2(make_float2(a[j], a[j + 1])));
+      f[j] = g2.x;
+      f[j + 1] = g2.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = a[j] > 0.f ? f[j] : 0.f;
+  }
+}
+__device__ __forceinline__ void epi_residual_smem(const uint8_t* srow, int r, float (&f)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 rv = *reinterpret_cast<const float4*>(srow + ((q ^ (r & 7)) << 4));
+    f[q * 4] += rv.x; f[q * 4 + 1] += rv.y; f[q * 4 + 2] += rv.z; f[q * 4 + 3] += rv.w;
   }
 }
 
@@ -408,14 +461,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 tma_store_commit();
               }
             }
+            // operand of this 128-byte-wide chunk through the staging tile (full chunks only; tails read directly)
+            const bool grad_epi = (p.epilogue == EPI_DGELU || p.epilogue == EPI_DRELU);
+            const bool op_aux = grad_epi && !p.out_fp32 && n + 64 <= p.N;
+            const bool op_res = !grad_epi && p.residual != nullptr && p.out_fp32 && n + 32 <= p.N;
+            if (op_aux)
+              epi_operand_to_stage(stage, reinterpret_cast<const uint8_t*>(p.aux_in + (long long)m_box * p.ld_aux_in + n),
+                                   (long long)p.ld_aux_in * 2, p.M - m_box, lane);
+            else if (op_res)
+              epi_operand_to_stage(stage, reinterpret_cast<const uint8_t*>(p.residual + boff_r + (long long)m_box * p.ldr + n),
+                                   (long long)p.ldr * 4, p.M - m_box, lane);
 #pragma unroll 1
             for (int hh = 0; hh < nh; ++hh) {
               float f[32];
               const int nn = n + 32 * hh;
               epi_load(p, trow + col0 + 32 * hh, nn, split, f);
-              epi_act(p, row, row_ok, nn, f);
-              epi_residual(p, boff_r, row, row_ok, nn, f);
-              if (hh == 0) {  // the previous store has finished reading the staging tile
+              if (op_aux) epi_act_grad_smem(p, srow, lane, hh, f);
+              else epi_act(p, row, row_ok, nn, f);
+              if (op_res) epi_residual_smem(srow, lane, f);
+              else epi_residual(p, boff_r, row, row_ok, nn, f);
+              if (hh == 0 && !op_aux && !op_res) {  // the previous store has finished reading the staging tile
                 if (lane == 0) tma_store_wait_read();
                 __syncwarp();
               }
@@ -765,15 +830,16 @@ static int dispatch_major(const GemmArgs& g, cudaStream_t s) {
   static const int forced = []() { const char* v = getenv("S3D_GEMM_EPW"); return v == nullptr ? 0 : atoi(v); }();
   // measured on the cfg3 MLP shapes: dGELU 1002 -> 968 us with 16 warps; the GELU GEMM (two output tiles, 2.3 GB of
   // writes in 0.9 ms: DRAM-write bound) and the plain epilogues are faster with 8 warps and the fourth operand stage
-  const bool act = (g.p.epilogue == EPI_DGELU || g.p.epilogue == EPI_DRELU) && g.p.splits == 1 && BN >= 128;
-  const bool heavy = BN >= 128 && g.a_mn == 0 && (forced == 4 || (forced != 2 && act));
+  const bool act = (g.p.epilogue == EPI_DGELU || g.p.epilogue == EPI_DRELU) && g.p.splits == 1;
+  // BN = 256 only: a 16-warp part must span at least one 128-byte staging row (64 bf16 columns = BN / 4)
+  const bool heavy = BN == 256 && g.a_mn == 0 && (forced == 4 || (forced != 2 && act));
   if (g.a_mn == 0 && g.b_mn == 0) {
-    if constexpr (BN >= 128) { if (heavy) return launch_gemm<BN, 0, 0, CL, 4>(g, s); }
+    if constexpr (BN == 256) { if (heavy) return launch_gemm<BN, 0, 0, CL, 4>(g, s); }
     return launch_gemm<BN, 0, 0, CL, 2>(g, s);
   }
   if (g.a_mn == 1 && g.b_mn == 1) return launch_gemm<BN, 1, 1, CL, 2>(g, s);
   if (g.a_mn == 0 && g.b_mn == 1) {
-    if constexpr (BN >= 128) { if (heavy) return launch_gemm<BN, 0, 1, CL, 4>(g, s); }
+    if constexpr (BN == 256) { if (heavy) return launch_gemm<BN, 0, 1, CL, 4>(g, s); }
     return launch_gemm<BN, 0, 1, CL, 2>(g, s);
   }
   return launch_gemm<BN, 1, 0, CL, 2>(g, s);

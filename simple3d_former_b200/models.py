@@ -166,7 +166,7 @@ class Feature3D_ViT2D_V2(VisionTransformer):
         x = self.pos_drop(x + self.pos_embed)
         for blk in self.blocks:
             x = blk(x)
-        return self.head(self.norm(x)[:, 0])
+        return self.head(self.norm(x[:, 0]))
 
     def _tokens(self, x):
         emb = self.voxel_embed
@@ -183,7 +183,7 @@ class Feature3D_ViT2D_V2(VisionTransformer):
             t = self.pos_drop(t + self.voxel_pos_embed)
             for blk in self.blocks:
                 t = blk(t)
-            return self.norm(t)[:, 0]
+            return self.norm(t[:, 0])  # LayerNorm is per token: identical to the reference's norm(t)[:, 0] (:469-470)
         p = self.voxel_embed.patch_size
         D = self.embed_dim
         t = self._tokens(x).reshape(B * p * p, p, D)  # '(b px py) pz c'
@@ -192,12 +192,12 @@ class Feature3D_ViT2D_V2(VisionTransformer):
         t = self.group_embed(t)
         for blk in self.blocks:
             t = blk(t)
-        t = self.norm(t)[:, 0].reshape(B, p * p, D)
+        t = self.norm(t[:, 0]).reshape(B, p * p, D)  # = norm(t)[:, 0] (:484-485) without normalising the 14 discarded rows
         t = torch.cat((self.cls_token.expand(B, -1, -1), t), dim=1)
         t = self.pos_drop(t + self.voxel_pos_embed)
         for blk in self.blocks:
             t = blk(t)
-        return self.norm(t)[:, 0]
+        return self.norm(t[:, 0])
 
     def forward(self, x):
         return self.voxel_head(self.forward_features(x))

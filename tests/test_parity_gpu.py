@@ -215,6 +215,8 @@ def test_trainer_sgd_matches_torch_on_point_model(golden):
     for n, p in model.named_parameters():
         if n in dead:
             continue
+        if n.endswith(".bias") and ("mlp_convs" in n or (".fc" in n and n.endswith(".0.bias") and "transition_ups" in n)):
+            continue  # a bias in front of a training-mode BatchNorm has an exactly-zero gradient: both sides are noise
         # the UPDATE (p_after - p_before) of both sides, compared in L2: the two runs are separate executions whose fp32
         # atomics (scatter-adds of the point path, split-K) sum in different orders, and training-mode BatchNorms over a
         # batch of 2 clouds amplify that for single entries -- element-wise bounds on one step are flaky, the norm is not
