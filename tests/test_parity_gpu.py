@@ -215,11 +215,14 @@ def test_trainer_sgd_matches_torch_on_point_model(golden):
     for n, p in model.named_parameters():
         if n in dead:
             continue
-        if n.endswith(".bias") and ("mlp_convs" in n or (".fc" in n and n.endswith(".0.bias") and "transition_ups" in n)):
-            continue  # a bias in front of a training-mode BatchNorm has an exactly-zero gradient: both sides are noise
         # the UPDATE (p_after - p_before) of both sides, compared in L2: the two runs are separate executions whose fp32
         # atomics (scatter-adds of the point path, split-K) sum in different orders, and training-mode BatchNorms over a
         # batch of 2 clouds amplify that for single entries -- element-wise bounds on one step are flaky, the norm is not
         upd, upd_ref = p.detach() - init[n], ref_named[n].detach() - init[n]
         scale = float(upd_ref.norm())
+        if scale < 1e-3 * 0.01 * upd_ref.numel() ** 0.5:
+            # gradient RMS below 1e-3: biases in front of a training-mode BatchNorm (conv / Linear biases of the set
+            # abstraction, TransitionUp and the input MLPs) have an exactly-zero true gradient -- both sides are noise
+            assert float(upd.norm()) < 1e-3 * 0.01 * upd_ref.numel() ** 0.5, n
+            continue
         assert float((upd - upd_ref).norm()) <= 5e-2 * scale + 1e-7, (n, float((upd - upd_ref).norm()), scale)
