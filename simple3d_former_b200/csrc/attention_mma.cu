@@ -1017,7 +1017,10 @@ int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream) {
   static const bool tc_enabled = []() { const char* v = getenv("S3D_ATTN_TC"); return v == nullptr || v[0] != '0'; }();
   const bool tc_only = p.drop_seed != nullptr || (DH != 64 && DH != 192 && DH != 256);
   if (tc_only) return attn_tc_supported(DH) ? attn_bwd_tc(p, DH, stream) : S3D_ERR_UNSUPPORTED;
-  if (tc_enabled && attn_tc_supported(DH) && p.N >= 128) {  // head_dim 256 does not fit the backward's TMEM budget
+  // Backward on tcgen05 from N = 1024: it is three kernels (dK, dV, dQ) whose per-CTA prologue (operand tile -> tensor
+  // memory, ring start-up) only amortises over long sequences -- measured in the cfg4 / cfg5 steps (N = 257 / 513, dh 64):
+  // 2.61 / 1.84 ms per step against 2.11 / 1.61 ms for the mma.sync kernels. head_dim 256 does not fit its TMEM budget.
+  if (tc_enabled && attn_tc_supported(DH) && p.N >= 1024) {
     const int rc_tc = attn_bwd_tc(p, DH, stream);
     if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;
   }

@@ -87,7 +87,7 @@ def attn(B, N, H, dh, seqfirst, drop):
     kw = dict(drop_seed=seed, drop_site=1, drop_p=0.1) if drop else {}
     L.attn_fwd(b, b + 2 * E, b + 4 * E, o, lse, B, H, N, dh, qs, os_, dh ** -0.5, **kw)
     tc_f = drop or N >= 64          # forward: tcgen05 for every sequence of at least one 64-key block
-    tc = drop or (N >= 128 and dh != 256)  # backward: head_dim 256 does not fit its TMEM budget
+    tc = drop or (N >= 1024 and dh != 256)  # backward: long sequences only; head_dim 256 does not fit its TMEM budget
     order.append((f"s3d_attn_fwd[B={B},H={H},N={N},dh={dh},drop={int(drop)}]", ["fa_fwd" if tc_f else "attn_fwd"]))
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
