@@ -320,7 +320,7 @@ class KernelProfile:
             return 0.0, a[9] * a[10] * per
         if name == "s3d_layernorm_bwd":  # read x, dy (bf16 / f32), [dres]; write dx, [bf16 copy]
             per = 4.0 + (2.0 if a[1] else 4.0) + (4.0 if a[6] else 0.0) + 4.0 + (2.0 if a[8] else 0.0)
-            return 0.0, a[11] * a[12] * per
+            return 0.0, a[12] * a[13] * per
         if name == "s3d_colsum_bf16":
             return 0.0, a[2] * a[3] * 2.0
         return 0.0, 0.0

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define S3D_ABI_VERSION 2
+#define S3D_ABI_VERSION 3
 
 enum {
   S3D_OK = 0,
@@ -65,13 +65,15 @@ int s3d_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
  * LayerNorm (timm Block.norm1/norm2, VisionTransformer.norm: eps 1e-6, vit_3d_2d_pretrain.py:287; post-norm layers of
  * nn.TransformerEncoderLayer: eps 1e-5). x f32 [T,D]; optional addend fuses "x + addend" (and writes it to sum_out).
  * y_bf16 / y_f32 / mean / rstd may each be NULL. Backward adds `dres` (gradient through the residual branch) and can
- * emit a bf16 copy of dx for the next GEMM; dgamma/dbeta are ACCUMULATED (caller zeroes them).
+ * emit a bf16 copy of dx for the next GEMM; dgamma/dbeta are ACCUMULATED (caller zeroes them). dx_colsum (optional, f32
+ * [D], ACCUMULATED, needs dgamma/dbeta) receives the column sums of dx: dx is the gradient of a Linear layer's output
+ * (attn.proj / mlp.fc2 of the timm Block), so this is that layer's bias gradient without a pass of its own.
  * ------------------------------------------------------------------------------------------------------------- */
 int s3d_layernorm_fwd(const float* x, const float* addend, float* sum_out, const float* gamma, const float* beta,
                       void* y_bf16, float* y_f32, float* mean, float* rstd, int T, int D, float eps, void* stream);
 int s3d_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,
                       const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
-                      int T, int D, void* stream);
+                      float* dx_colsum, int T, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Attention core (timm-0.3.2 Attention.forward: softmax(q k^T * scale) v; F.multi_head_attention_forward inside the

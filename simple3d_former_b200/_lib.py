@@ -25,7 +25,7 @@ SIGNATURES = {
                               _P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_int64, c_int64, c_int64,
                               c_int64, c_int, c_int, c_int, _P]),
     "s3d_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
-    "s3d_layernorm_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "s3d_layernorm_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "s3d_attn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64,
                              c_int64, c_int64, c_float, _P, c_uint32, c_float, _P]),
     "s3d_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64,
@@ -92,7 +92,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
-        if _lib.s3d_abi_version() != 2:
+        if _lib.s3d_abi_version() != 3:
             raise RuntimeError("libs3d_b200.so ABI version mismatch")
     return _lib
 
@@ -199,18 +199,29 @@ def layernorm_fwd(x, gamma, beta, eps, *, addend=None, want_sum=False, want_bf16
     return y16, y32, s, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, *, dres=None, want_bf16=False, dgamma=None, dbeta=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, dres=None, want_bf16=False, dgamma=None, dbeta=None, dxsum=None,
+                  want_dxsum=False):
+    """dxsum: f32 [D] that the column sums of dx are ACCUMULATED into (bias gradient of the Linear whose output gradient
+    dx is); want_dxsum=True allocates a zeroed one. Returns (dx, dx_bf16, dgamma, dbeta[, dxsum])."""
     _need_cuda(dy, x)
     assert x.dtype == torch.float32 and x.is_contiguous() and dy.is_contiguous()
     D = x.shape[-1]
     T = x.numel() // D
     dx = torch.empty_like(x)
     dx16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
-    if dgamma is None:
-        dgamma = torch.zeros(D, device=x.device, dtype=torch.float32)
-        dbeta = torch.zeros(D, device=x.device, dtype=torch.float32)
+    need = (dgamma is None) + (dgamma is None) + (want_dxsum and dxsum is None)
+    if need:
+        z = torch.zeros((need, D), device=x.device, dtype=torch.float32)  # one fill for every fresh accumulator
+        i = 0
+        if dgamma is None:
+            dgamma, dbeta = z[0], z[1]
+            i = 2
+        if want_dxsum and dxsum is None:
+            dxsum = z[i]
     call("s3d_layernorm_bwd", ptr(dy), int(dy.dtype == torch.bfloat16), ptr(x), ptr(gamma), ptr(mean), ptr(rstd),
-         ptr(dres), ptr(dx), ptr(dx16), ptr(dgamma), ptr(dbeta), T, D, stream())
+         ptr(dres), ptr(dx), ptr(dx16), ptr(dgamma), ptr(dbeta), ptr(dxsum), T, D, stream())
+    if want_dxsum or dxsum is not None:
+        return dx, dx16, dgamma, dbeta, dxsum
     return dx, dx16, dgamma, dbeta
 
 

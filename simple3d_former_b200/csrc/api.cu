@@ -74,8 +74,8 @@ int s3d_layernorm_fwd(const float* x, const float* addend, float* sum_out, const
 
 int s3d_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,
                       const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
-                      int T, int D, void* stream) {
-  return s3d::layernorm_bwd(dy, dy_is_bf16, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, T, D,
+                      float* dx_colsum, int T, int D, void* stream) {
+  return s3d::layernorm_bwd(dy, dy_is_bf16, x, gamma, mean, rstd, dres, dx, dx_bf16, dgamma, dbeta, dx_colsum, T, D,
                             as_stream(stream));
 }
 

@@ -44,7 +44,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 int layernorm_fwd(const float* x, const float* addend, float* sum_out, const float* gamma, const float* beta,
                   void* y_bf16, float* y_f32, float* mean, float* rstd, int T, int D, float eps, cudaStream_t stream);
 int layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,
-                  const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T,
+                  const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int T,
                   int D, cudaStream_t stream);
 int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
 int transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int C, long long ld_in, long long ld_out,

@@ -287,23 +287,24 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                                                            const float* __restrict__ rstd_in,
                                                            const float* __restrict__ dres, float* __restrict__ dx,
                                                            __nv_bfloat16* __restrict__ dx_bf16,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int T,
-                                                           int D) {
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           float* __restrict__ dxsum, int T, int D) {
   pdl_prologue();
-  extern __shared__ float red[];  // [2][D]
+  extern __shared__ float red[];  // [3][D]
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = D >> 2;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
 
-  float4 acc_g[VEC_ITERS], acc_b[VEC_ITERS];
+  float4 acc_g[VEC_ITERS], acc_b[VEC_ITERS], acc_x[VEC_ITERS];
 #pragma unroll
   for (int i = 0; i < VEC_ITERS; ++i) {
     acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = warp; row < T; row += nwarps) {
     const float mean = mean_in[row];
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         reinterpret_cast<float4*>(dx + (size_t)row * D)[c] = o;
+        acc_x[i].x += o.x; acc_x[i].y += o.y; acc_x[i].z += o.z; acc_x[i].w += o.w;
         if (dx_bf16 != nullptr) {
           uint2 u;
           u.x = pack_bf16x2(o.x, o.y);
@@ -370,6 +372,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
             float* rb = red + D + 4 * c;
             rg[0] += acc_g[i].x; rg[1] += acc_g[i].y; rg[2] += acc_g[i].z; rg[3] += acc_g[i].w;
             rb[0] += acc_b[i].x; rb[1] += acc_b[i].y; rb[2] += acc_b[i].z; rb[3] += acc_b[i].w;
+            if (dxsum != nullptr) {
+              float* rx = red + 2 * D + 4 * c;
+              rx[0] += acc_x[i].x; rx[1] += acc_x[i].y; rx[2] += acc_x[i].z; rx[3] += acc_x[i].w;
+            }
           }
         }
       }
@@ -378,7 +384,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
       atomicAdd(dgamma + i, red[i]);
       atomicAdd(dbeta + i, red[D + i]);
-    }
+      if (dxsum != nullptr) atomicAdd(dxsum + i, red[2 * D + i]);  // column sums of dx: the bias gradient of the Linear that
+    }                                                                // produced this LayerNorm's input's other branch
   }
 }
 
@@ -398,7 +405,8 @@ __global__ void __launch_bounds__(kLnWarps * 32, 1)
     layernorm_bwd_pipe_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
                               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                               const float* __restrict__ dres, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
-                              float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int D) {
+                              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, int T,
+                              int D) {
   pdl_prologue();
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31;
@@ -408,11 +416,11 @@ __global__ void __launch_bounds__(kLnWarps * 32, 1)
   const uint32_t dy_bytes = DY_BF16 ? (uint32_t)D * 2u : (uint32_t)D * 4u;
   const uint32_t dres_bytes = dres != nullptr ? (uint32_t)D * 4u : 0u;
   const uint32_t row_bytes = x_bytes + dy_bytes + dres_bytes;
-  // layout: [kLnWarps][kLnStages][row_bytes] | red [2][D] f32 | mbarriers [kLnWarps][kLnStages]
+  // layout: [kLnWarps][kLnStages][row_bytes] | red [3][D] f32 | mbarriers [kLnWarps][kLnStages]
   uint8_t* ring = ln_smem + (size_t)wib * kLnStages * row_bytes;
   float* red = reinterpret_cast<float*>(ln_smem + (size_t)kLnWarps * kLnStages * row_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * D) + wib * kLnStages;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 3 * D) + wib * kLnStages;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.f;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kLnStages; ++s) mbar_init(&bars[s], 1);
@@ -437,13 +445,14 @@ __global__ void __launch_bounds__(kLnWarps * 32, 1)
     }
   }
   float4 gm[VEC_ITERS];
-  float4 acc_g[VEC_ITERS], acc_b[VEC_ITERS];
+  float4 acc_g[VEC_ITERS], acc_b[VEC_ITERS], acc_x[VEC_ITERS];
 #pragma unroll
   for (int i = 0; i < VEC_ITERS; ++i) {
     const int c = lane + 32 * i;
     gm[i] = c < nvec ? reinterpret_cast<const float4*>(gamma)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
     acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   int it = 0;
   for (long long row = warp; row < T; row += nwarps, ++it) {
@@ -493,6 +502,7 @@ __global__ void __launch_bounds__(kLnWarps * 32, 1)
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         reinterpret_cast<float4*>(dx + (size_t)row * D)[c] = o;
+        acc_x[i].x += o.x; acc_x[i].y += o.y; acc_x[i].z += o.z; acc_x[i].w += o.w;
         if (dx_bf16 != nullptr) {
           uint2 u;
           u.x = pack_bf16x2(o.x, o.y);
@@ -517,6 +527,10 @@ __global__ void __launch_bounds__(kLnWarps * 32, 1)
             float* rb = red + D + 4 * c;
             rg[0] += acc_g[i].x; rg[1] += acc_g[i].y; rg[2] += acc_g[i].z; rg[3] += acc_g[i].w;
             rb[0] += acc_b[i].x; rb[1] += acc_b[i].y; rb[2] += acc_b[i].z; rb[3] += acc_b[i].w;
+            if (dxsum != nullptr) {
+              float* rx = red + 2 * D + 4 * c;
+              rx[0] += acc_x[i].x; rx[1] += acc_x[i].y; rx[2] += acc_x[i].z; rx[3] += acc_x[i].w;
+            }
           }
         }
       }
@@ -525,31 +539,33 @@ __global__ void __launch_bounds__(kLnWarps * 32, 1)
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
       atomicAdd(dgamma + i, red[i]);
       atomicAdd(dbeta + i, red[D + i]);
-    }
+      if (dxsum != nullptr) atomicAdd(dxsum + i, red[2 * D + i]);  // column sums of dx: the bias gradient of the Linear that
+    }                                                                // produced this LayerNorm's input's other branch
   }
 }
 
 template <int I, bool BF>
 static int launch_ln_bwd_pipe(const void* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
-                              const float* dres, float* dx, __nv_bfloat16* dxb, float* dgamma, float* dbeta, int T, int D,
-                              cudaStream_t stream) {
+                              const float* dres, float* dx, __nv_bfloat16* dxb, float* dgamma, float* dbeta, float* dxsum,
+                              int T, int D, cudaStream_t stream) {
   const size_t row_bytes = (size_t)D * 4 + (BF ? (size_t)D * 2 : (size_t)D * 4) + (dres != nullptr ? (size_t)D * 4 : 0);
-  const size_t shmem = (size_t)kLnWarps * kLnStages * row_bytes + 2 * (size_t)D * sizeof(float) +
+  const size_t shmem = (size_t)kLnWarps * kLnStages * row_bytes + 3 * (size_t)D * sizeof(float) +
                        (size_t)kLnWarps * kLnStages * sizeof(uint64_t);
   if (shmem > 227 * 1024) return S3D_ERR_UNSUPPORTED;
   auto kern = layernorm_bwd_pipe_kernel<I, BF>;
   S3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
   long long blocks = ((long long)T + kLnWarps - 1) / kLnWarps;
   if (blocks > num_sms()) blocks = num_sms();
-  S3D_CUDA_OK(launch_pdl(kern, dim3((int)blocks), dim3(kLnWarps * 32), (size_t)(shmem), stream, dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, T, D));
+  S3D_CUDA_OK(launch_pdl(kern, dim3((int)blocks), dim3(kLnWarps * 32), (size_t)(shmem), stream, dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dxsum, T, D));
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
 
 int layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,
-                  const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T,
-                  int D, cudaStream_t stream) {
+                  const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                  float* dxsum, int T, int D, cudaStream_t stream) {
   if (T <= 0 || D <= 0 || D % 4 != 0 || D > 1024) return S3D_ERR_BAD_SHAPE;
+  if (dxsum != nullptr && dgamma == nullptr) return S3D_ERR_NULL;  // the column sums share the parameter-gradient reduction
   if (dy == nullptr || x == nullptr || gamma == nullptr || mean == nullptr || rstd == nullptr || dx == nullptr)
     return S3D_ERR_NULL;
   const int warps_per_block = 8;
@@ -557,7 +573,7 @@ int layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* g
   const long long cap = (long long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   const int iters = (D / 4 + 31) / 32;
-  const size_t shmem = 2 * (size_t)D * sizeof(float);
+  const size_t shmem = 3 * (size_t)D * sizeof(float);
   auto dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   // large problems with 16-byte-aligned rows: bulk-async pipelined variant (rows streamed through shared memory)
   static const bool no_pipe = getenv("S3D_LN_BWD_NO_PIPE") != nullptr;
@@ -566,8 +582,8 @@ int layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* g
   if (!no_pipe && D % 8 == 0 && aligned && (long long)T >= (long long)num_sms() * kLnWarps * 4 && iters <= 8) {
     int rc = S3D_ERR_UNSUPPORTED;
 #define S3D_LN_PIPE(I)                                                                                            \
-  rc = dy_is_bf16 ? launch_ln_bwd_pipe<I, true>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, T, D, stream) \
-                  : launch_ln_bwd_pipe<I, false>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, T, D, stream)
+  rc = dy_is_bf16 ? launch_ln_bwd_pipe<I, true>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dxsum, T, D, stream) \
+                  : launch_ln_bwd_pipe<I, false>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dxsum, T, D, stream)
     switch (iters) {
       case 1: S3D_LN_PIPE(1); break;
       case 2: S3D_LN_PIPE(2); break;
@@ -586,11 +602,11 @@ int layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* g
     if (dy_is_bf16)                                                                                                   \
       S3D_CUDA_OK(launch_pdl(layernorm_bwd_kernel<I, true>, dim3((int)blocks), dim3(warps_per_block * 32), (size_t)(shmem), stream, dy, x, gamma, mean, rstd,  \
                                                                                           dres, dx, dxb, dgamma,      \
-                                                                                          dbeta, T, D));               \
+                                                                                          dbeta, dxsum, T, D));        \
     else                                                                                                              \
       S3D_CUDA_OK(launch_pdl(layernorm_bwd_kernel<I, false>, dim3((int)blocks), dim3(warps_per_block * 32), (size_t)(shmem), stream, dy, x, gamma, mean, rstd, \
                                                                                            dres, dx, dxb, dgamma,     \
-                                                                                           dbeta, T, D));              \
+                                                                                           dbeta, dxsum, T, D));       \
   } while (0)
   switch (iters) {
     case 1: S3D_LN_BWD(1); break;

@@ -84,6 +84,31 @@ def _ln_bwd(dy, x, gamma, beta, mean, rstd, **kw):
     return L.layernorm_bwd(dy, x, gamma, mean, rstd, **kw)
 
 
+def _ln_bwd_colsum(dy, x, gamma, beta, mean, rstd, bias, **kw):
+    """LayerNorm backward whose dx is the output gradient of a Linear layer with bias parameter `bias`: the kernel also
+    accumulates the column sums of dx, i.e. that bias gradient, so no separate pass over dx is needed. `bias` = None asks
+    for a fresh accumulator (the caller hands it to whoever owns the bias). Returns (dx, dx16, dgamma, dbeta, dbias)
+    where dbias is None when it went straight into the bias parameter's gradient sink."""
+    sg, sb = _sink(gamma), _sink(beta)
+    sk = _sink(bias)
+    args = dict(kw)
+    if sk is not None:
+        args["dxsum"] = sk
+    else:
+        args["want_dxsum"] = True
+    if sg is not None and sb is not None:
+        dx, dx16, _, _, dxsum = L.layernorm_bwd(dy, x, gamma, mean, rstd, dgamma=sg, dbeta=sb, **args)
+        gamma._s3d_owner.note_write(gamma)
+        beta._s3d_owner.note_write(beta)
+        dg = db = None
+    else:
+        dx, dx16, dg, db, dxsum = L.layernorm_bwd(dy, x, gamma, mean, rstd, **args)
+    if sk is not None:
+        bias._s3d_owner.note_write(bias)
+        dxsum = None
+    return dx, dx16, dg, db, dxsum
+
+
 def _w2d(w16: torch.Tensor) -> torch.Tensor:
     return w16.reshape(w16.shape[0], -1)
 
@@ -290,30 +315,50 @@ class BlockFn(torch.autograd.Function):
         n1b, qkv_b, proj_b, n2b, fc1_b, fc2_b = ctx.refs
         pg = _ParamGradStream(dy.device, T * D <= _OVERLAP_LIMIT)  # weight / bias gradients off the critical chain
         # MLP
+        # bias gradient of fc2 = column sums of dy: the LayerNorm backward that PRODUCED dy (the downstream block's norm1)
+        # has accumulated them on the way (see the end of this function); otherwise one pass over dy
+        dy_colsum = getattr(dy, "_s3d_colsum", None)
+        if dy_colsum is not None and getattr(dy, "_s3d_bf16_src", None) != dy.data_ptr():
+            dy_colsum = None
         with pg.fork():
             dfc2_w = _wgrad(fc2_w, dy16, a16)
-            dfc2_b = _bgrad(fc2_b, dy16)
+            if fc2_b is None:
+                dfc2_b = None
+            elif dy_colsum is None:
+                dfc2_b = _bgrad(fc2_b, dy16)
+            elif _sink(fc2_b) is not None:
+                _sink(fc2_b).add_(dy_colsum)
+                fc2_b._s3d_owner.note_write(fc2_b)
+                dfc2_b = None
+            else:
+                dfc2_b = dy_colsum
         dpre = L.gemm(dy16, shadow(fc2_w), b_mn=True, epilogue=L.EPI_DGELU, aux_in=pre)
         with pg.fork():
             dfc1_w = _wgrad(fc1_w, dpre, g16)
             dfc1_b = _bgrad(fc1_b, dpre)
         dg = L.gemm(dpre, shadow(fc1_w), b_mn=True)
-        dx1, dx1_16, dn2w, dn2b = _ln_bwd(dg, x1, n2w, n2b, mean2, rstd2, dres=dy2, want_bf16=True)
+        # dx1 is the output gradient of attn.proj: its column sums (= the proj bias gradient) come out of this kernel
+        if proj_b is not None:
+            dx1, dx1_16, dn2w, dn2b, dproj_b = _ln_bwd_colsum(dg, x1, n2w, n2b, mean2, rstd2, proj_b, dres=dy2, want_bf16=True)
+        else:
+            dx1, dx1_16, dn2w, dn2b = _ln_bwd(dg, x1, n2w, n2b, mean2, rstd2, dres=dy2, want_bf16=True)
+            dproj_b = None
         # attention
         with pg.fork():
             dproj_w = _wgrad(proj_w, dx1_16, o16.view(T, D))
-            dproj_b = _bgrad(proj_b, dx1_16)
         do16 = L.gemm(dx1_16, shadow(proj_w), b_mn=True)
         dqkv = _attn_core_bwd(qkv, o16, do16.view(B, N, D), lse, B, N, H, dh, scale)
         with pg.fork():
             dqkv_w = _wgrad(qkv_w, dqkv, h16)
             dqkv_b = _bgrad(qkv_b, dqkv)
         dh_ = L.gemm(dqkv, shadow(qkv_w), b_mn=True)
-        dx, dx16, dn1w, dn1b = _ln_bwd(dh_, x2, n1w, n1b, mean1, rstd1, dres=dx1, want_bf16=True)
+        # dx is the output gradient of the upstream block's mlp.fc2: leave its column sums on the tensor for that block
+        dx, dx16, dn1w, dn1b, dx_colsum = _ln_bwd_colsum(dh_, x2, n1w, n1b, mean1, rstd1, None, dres=dx1, want_bf16=True)
         pg.join()
         dx = dx.view(B, N, D)
         dx._s3d_bf16 = dx16
         dx._s3d_bf16_src = dx.data_ptr()
+        dx._s3d_colsum = dx_colsum
         return (dx, dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w,
                 dfc2_b, None, None, None, None)
 

@@ -276,7 +276,8 @@ def g_ln():
         dy = torch.randn(T, D, device="cuda")
         dres = torch.randn(T, D, device="cuda")
         F.layer_norm(xr, (D,), gr, br, 1e-6).backward(dy)
-        dx, dx16, dg, db = L.layernorm_bwd(dy, x, g, mean, rstd, dres=dres, want_bf16=True)
+        dx, dx16, dg, db, dxs = L.layernorm_bwd(dy, x, g, mean, rstd, dres=dres, want_bf16=True, want_dxsum=True)
+        report(f"ln bwd dx column sums T{T}", rel_err(dxs, dx.sum(0)), 1e-4)
         report(f"ln bwd dx T{T} D{D}", rel_err(dx, xr.grad + dres), 1e-4)
         report(f"ln bwd dx16 T{T} D{D}", rel_err(dx16, xr.grad + dres), 1e-2)
         report(f"ln bwd dgamma T{T} D{D}", rel_err(dg, gr.grad), 1e-4)
