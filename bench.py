@@ -567,6 +567,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                        "overlapping the previous step) -> step -> loss copied to pinned host memory"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
+        "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:

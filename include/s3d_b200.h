@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define S3D_ABI_VERSION 3
+#define S3D_ABI_VERSION 4
 
 enum {
   S3D_OK = 0,
@@ -94,7 +94,11 @@ int s3d_attn_bwd(const void* q, const void* k, const void* v, const void* out, c
                  float* delta, void* dq, void* dk, void* dv, int B, int H, int N, int head_dim,
                  int64_t qkv_batch_stride, int64_t qkv_head_stride, int64_t qkv_row_stride, int64_t o_batch_stride,
                  int64_t o_head_stride, int64_t o_row_stride, float scale, const uint32_t* dropout_seed,
-                 uint32_t dropout_site, float dropout_p, void* stream);
+                 uint32_t dropout_site, float dropout_p, void* workspace, int64_t workspace_bytes, void* stream);
+/* Scratch (bytes, 1 KiB aligned) with which s3d_attn_bwd runs its single-score-pass form on long sequences: the dQ kernel
+ * writes the bf16 matrices P o mask and dS ([B*H, N, ceil64(N)] each) once and dK / dV are batched GEMMs over them.
+ * 0 = not applicable for this shape; passing workspace = NULL (or fewer bytes) selects the recomputing two-kernel form. */
+int64_t s3d_attn_bwd_workspace_bytes(int B, int H, int N, int head_dim);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Elementwise / data-movement helpers of the path

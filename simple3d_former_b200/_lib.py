@@ -28,8 +28,9 @@ SIGNATURES = {
     "s3d_layernorm_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "s3d_attn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64,
                              c_int64, c_int64, c_float, _P, c_uint32, c_float, _P]),
+    "s3d_attn_bwd_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "s3d_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64,
-                             c_int64, c_int64, c_int64, c_int64, c_float, _P, c_uint32, c_float, _P]),
+                             c_int64, c_int64, c_int64, c_int64, c_float, _P, c_uint32, c_float, _P, c_int64, _P]),
     "s3d_dropout_add_f32": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_uint32, c_float, _P]),
     "s3d_dropout_bf16": (c_int, [_P, _P, c_int64, c_int, _P, c_uint32, c_float, _P]),
     "s3d_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
@@ -92,7 +93,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
-        if _lib.s3d_abi_version() != 3:
+        if _lib.s3d_abi_version() != 4:
             raise RuntimeError("libs3d_b200.so ABI version mismatch")
     return _lib
 
@@ -233,11 +234,26 @@ def attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale, drop_seed=None, dro
          os_[2], float(scale), ptr(drop_seed), int(drop_site), float(drop_p), stream())
 
 
+_ATTN_WS_MAX = int(float(os.environ.get("S3D_ATTN_WS_MAX_GB", "64")) * (1 << 30))
+
+
 def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, B, H, N, dh, qs, os_, scale, drop_seed=None, drop_site=0,
-             drop_p=0.0):
+             drop_p=0.0, workspace=True):
+    """workspace=True: long sequences run the single-score-pass backward (the library says how much scratch it wants for
+    the shape; it is allocated here for the duration of the call, up to S3D_ATTN_WS_MAX_GB, default 64 GiB);
+    workspace=False forces the recomputing two-kernel form."""
     _need_cuda(out, dout, lse, delta, drop_seed)
+    ws, ws_ptr, ws_bytes = None, None, 0
+    if workspace:
+        need = int(lib().s3d_attn_bwd_workspace_bytes(B, H, N, dh))
+        if 0 < need <= _ATTN_WS_MAX:
+            ws = torch.empty(need + 1024, device=out.device, dtype=torch.uint8)
+            ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+            ws_bytes = need
     call("s3d_attn_bwd", q, k, v, ptr(out), ptr(dout), ptr(lse), ptr(delta), dq, dk, dv, B, H, N, dh, qs[0], qs[1],
-         qs[2], os_[0], os_[1], os_[2], float(scale), ptr(drop_seed), int(drop_site), float(drop_p), stream())
+         qs[2], os_[0], os_[1], os_[2], float(scale), ptr(drop_seed), int(drop_site), float(drop_p), ws_ptr, ws_bytes,
+         stream())
+    del ws  # allocated and consumed on the current stream: the caching allocator reuses it in stream order
 
 
 def dropout_add(x, residual, seed, site, p):

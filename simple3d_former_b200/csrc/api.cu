@@ -33,7 +33,7 @@ int s3d_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
                   int64_t batch_stride_r, int force_bn, int force_cluster, int force_splits, void* stream) {
   if (epilogue < S3D_EPI_NONE || epilogue > S3D_EPI_DRELU) return S3D_ERR_UNSUPPORTED;
   if (batch < 1 || batch > 65535) return S3D_ERR_BAD_SHAPE;
-  s3d::GemmArgs g;
+  s3d::GemmArgs g{};
   g.A = A;
   g.B = B;
   g.lda = lda;
@@ -120,14 +120,21 @@ int s3d_attn_fwd(const void* q, const void* k, const void* v, void* out, float* 
   return s3d::attn_fwd(p, head_dim, as_stream(stream));
 }
 
+int64_t s3d_attn_bwd_workspace_bytes(int B, int H, int N, int head_dim) {
+  return s3d::attn_bwd_workspace_bytes(B, H, N, head_dim);
+}
+
 int s3d_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                  float* delta, void* dq, void* dk, void* dv, int B, int H, int N, int head_dim,
                  int64_t qkv_batch_stride, int64_t qkv_head_stride, int64_t qkv_row_stride, int64_t o_batch_stride,
                  int64_t o_head_stride, int64_t o_row_stride, float scale, const uint32_t* dropout_seed,
-                 uint32_t dropout_site, float dropout_p, void* stream) {
+                 uint32_t dropout_site, float dropout_p, void* workspace, int64_t workspace_bytes, void* stream) {
   s3d::AttnParams p = make_attn(q, k, v, B, H, N, qkv_batch_stride, qkv_head_stride, qkv_row_stride, o_batch_stride,
                                 o_head_stride, o_row_stride, scale);
   if (int rc = set_dropout(p, dropout_seed, dropout_site, dropout_p)) return rc;
+  if (workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return S3D_ERR_ALIGNMENT;
+  p.workspace = workspace;
+  p.workspace_bytes = workspace_bytes;
   p.o = reinterpret_cast<const __nv_bfloat16*>(out);
   p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
   p.lse = const_cast<float*>(lse);

@@ -772,6 +772,7 @@ struct FaBwdParams {
   const uint32_t* drop_seed;  // attention-probability dropout (same mask as the forward kernel)
   uint32_t drop_site, drop_thresh14;
   float drop_scale;
+  int dbg;  // S3D_FA_DBG bring-up switches (0 in production)
 };
 
 // Element-wise group of the backward kernels: kEwParts threads share one TMEM lane (= tile row), each handling
@@ -801,6 +802,14 @@ __device__ __forceinline__ void store_part_row_sw128(uint8_t* row_base, int r, i
     *reinterpret_cast<uint4*>(row_base + (((part * (kEwCols / 8) + q) ^ (r & 7)) << 4)) =
         make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
 }
+// streaming store (L2 evict-first: the workspace is read back only after the whole kernel, the K / V operands are what
+// should stay L2-resident)
+__device__ __forceinline__ void fa_tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2,
+                                                int c3, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x32b_x16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
 
@@ -817,32 +826,46 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[32]) 
 // TMEM (2 DH + 128 columns): dQ [0,DH)  S [DH,+64)  dP [DH+64,+64)  Q [DH+128,+DH/2)  dO [DH+128+DH/2,+DH/2).
 // S / dP are single-buffered: the element-wise warps pull them into registers and hand the columns back at once
 // (sp_free), so S/dP(j+1) runs on the tensor core while dS(j) is computed; dS tiles are double-buffered in smem.
-struct FaDqCfgBase {
-  static constexpr int kStages = 4;
-};
-template <int DH>
+//
+// SPILL variant (long sequences, see fa_bwd_launch): this kernel is then the ONLY pass over the score matrix of the
+// backward. Besides dQ it writes the two bf16 [query, key] matrices the key-side gradients contract over queries,
+//     Pd = P o mask          (dV = Pd^T dO / (1 - p))          dS = P o (mask o dP / (1 - p) - delta)     (dK = dS^T Q scale)
+// tile by tile (the dS tile is the A operand of the dQ MMAs and sits in shared memory anyway; the Pd tile gets a buffer
+// of its own, paid for with one K/V stage) with one TMA store per tile, and dK / dV become two batched MN-major x MN-major
+// GEMMs of gemm_bf16_kernel that read them back once at the HBM rate. 5 GEMM units at (or near) the tensor-memory rate
+// instead of 7-8 (dQ 3 + fused dK/dV 4 with shared-memory A operands, or split dK 3 + dV 2), at the price of 8 B of
+// workspace traffic per score element (4 B written here at ~4.5 TB/s while the tensor core works, 4 B read by the GEMMs).
+template <int DH, bool SPILL>
 struct FaDqCfg {
   static constexpr int kCh = (DH + 63) / 64;
-  static constexpr int kStages = FaDqCfgBase::kStages;
+  static constexpr int kStages = SPILL ? 3 : 4;
   static constexpr int kBlkBytes = 64 * kCh * 128;     // 64-row streamed block (K or V)
-  static constexpr int kSBytes = 128 * 64 * 2;         // bf16 dS tile
-  static constexpr int kSmemBytes = 2 * kStages * kBlkBytes + 2 * kSBytes + 1024 + 512;
+  static constexpr int kSBytes = 128 * 64 * 2;         // bf16 dS (and Pd) tile
+  static constexpr int kSmemBytes = 2 * kStages * kBlkBytes + (SPILL ? 4 : 2) * kSBytes + 1024 + 512;
   static constexpr int kColS = DH, kColQ = DH + 128, kColdO = DH + 128 + DH / 2;
   static_assert(2 * DH + 128 <= 512, "TMEM budget");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <int DH, bool DROP>
-__global__ void __launch_bounds__(kFaBwdThreads, 1)
-fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfloat16* __restrict__ qbase,
+// CL = 2: the CTAs of two adjacent query tiles form a cluster and share every K / V block -- each loads half of its rows
+// and TMA-multicasts them into both shared memories (tma_kv64's box is then 32 rows), ring slots are released by a
+// multicast tcgen05.commit once BOTH CTAs' MMAs have consumed them. One 128-row tile re-reads 48 KB of K / V per 64 keys:
+// 55 GB of L2 -> SM traffic on the group_embed shape, which (with the 38 GB of spill stores) ran into the ~8.7 TB/s the
+// L2 delivers; sharing halves the load side.
+template <int DH, bool DROP, bool SPILL, int CL>
+__global__ void __launch_bounds__(kFaBwdThreads + (SPILL ? 32 : 0), 1)
+fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __grid_constant__ CUtensorMap tma_pd,
+                    const __grid_constant__ CUtensorMap tma_ds, const __nv_bfloat16* __restrict__ qbase,
                     const __nv_bfloat16* __restrict__ dobase, const FaBwdParams p) {
-  using Cfg = FaDqCfg<DH>;
+  using Cfg = FaDqCfg<DH, SPILL>;
   constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;                                // [NST][kCh][64][128B]
   uint8_t* sV = sK + NST * Cfg::kBlkBytes;           // [NST][kCh][64][128B]
   uint8_t* sdS = sV + NST * Cfg::kBlkBytes;          // [2][128][128B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * Cfg::kSBytes);
+  uint8_t* sPd = sdS + 2 * Cfg::kSBytes;             // [2][128][128B] (SPILL only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + (SPILL ? 4 : 2) * Cfg::kSBytes);
   uint64_t* k_full = bars;                 // [NST]
   uint64_t* v_full = bars + NST;           // [NST]
   uint64_t* kv_empty = bars + 2 * NST;     // [NST]
@@ -867,7 +890,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfl
     for (int i = 0; i < NST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], CL);  // one (multicast) commit from every CTA of the cluster
     }
     mbar_init(sp_full, 1);
     mbar_init(sp_free, kEwWarps);  // one arrive per element-wise warp
@@ -875,29 +898,43 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfl
     mbar_init(dq_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ds_full[i], kEwWarps);
-      mbar_init(&ds_free[i], 1);
+      mbar_init(&ds_free[i], SPILL ? 2 : 1);  // dQ MMAs retired (+ the tile's TMA stores have read it)
     }
     fence_barrier_init();
+    if (SPILL) {
+      tma_prefetch_desc(&tma_pd);
+      tma_prefetch_desc(&tma_ds);
+    }
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before any multicast can target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0) {
     if (lane == 0) {
+      constexpr int kRows = 64 / CL;  // rows of every 64-row chunk this CTA loads (and multicasts)
       for (int j = 0; j < nkv; ++j) {
         const int st = j % NST;
         mbar_wait(&kv_empty[st], ((j / NST) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], Cfg::kBlkBytes);
 #pragma unroll
-        for (int c = 0; c < Cfg::kCh; ++c)
-          tma_load_2d(sK + st * Cfg::kBlkBytes + c * (64 * 128), &tma_kv64, &k_full[st], ck + 64 * c, row_base + j * 64);
+        for (int c = 0; c < Cfg::kCh; ++c) {
+          uint8_t* dst = sK + st * Cfg::kBlkBytes + c * (64 * 128) + crank * kRows * 128;
+          if (CL > 1) tma_load_2d_mc(dst, &tma_kv64, &k_full[st], ck + 64 * c, row_base + j * 64 + crank * kRows, kMcMask);
+          else tma_load_2d(dst, &tma_kv64, &k_full[st], ck + 64 * c, row_base + j * 64);
+        }
         mbar_expect_tx(&v_full[st], Cfg::kBlkBytes);
 #pragma unroll
-        for (int c = 0; c < Cfg::kCh; ++c)
-          tma_load_2d(sV + st * Cfg::kBlkBytes + c * (64 * 128), &tma_kv64, &v_full[st], cv + 64 * c, row_base + j * 64);
+        for (int c = 0; c < Cfg::kCh; ++c) {
+          uint8_t* dst = sV + st * Cfg::kBlkBytes + c * (64 * 128) + crank * kRows * 128;
+          if (CL > 1) tma_load_2d_mc(dst, &tma_kv64, &v_full[st], cv + 64 * c, row_base + j * 64 + crank * kRows, kMcMask);
+          else tma_load_2d(dst, &tma_kv64, &v_full[st], cv + 64 * c, row_base + j * 64);
+        }
       }
     }
     __syncwarp();
@@ -910,16 +947,18 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfl
     const uint32_t ds_lo = smem_desc_lo(smem_u32(sdS), 16), kmn_lo = smem_desc_lo(smem_u32(sK), 64 * 128);
     const uint32_t t_s = tmem_base + Cfg::kColS, t_dp = t_s + 64;
     const uint32_t t_q = tmem_base + Cfg::kColQ, t_do = tmem_base + Cfg::kColdO;
+    auto leader = [&]() { return elect_one(); };
     auto issue_dq = [&](int j) {  // dQ += dS(j) K(j)
       const int u = j & 1, st = j % NST;
       mbar_wait(&ds_full[u], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t a = ds_lo + u * (Cfg::kSBytes >> 4), bb = kmn_lo + st * (Cfg::kBlkBytes >> 4);
-      if (elect_one()) {
+      if (leader()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_f16_ss2(tmem_base, a + ((kk * 32) >> 4), hi, bb + ((kk * 2048) >> 4), hi, idesc_q, (j > 0) || (kk != 0));
-        umma_commit(&kv_empty[st]);
+        if (CL > 1) umma_commit_mc(&kv_empty[st], kMcMask);
+        else umma_commit(&kv_empty[st]);
         umma_commit(&ds_free[u]);
         if (j + 1 == nkv) umma_commit(dq_full);
       }
@@ -933,7 +972,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfl
       if (j > 0) mbar_wait(sp_free, (j - 1) & 1);  // S / dP of block j-1 are in registers: the columns can be overwritten
       tc_fence_after();
       const uint32_t bk = k_lo + st * (Cfg::kBlkBytes >> 4), bv = v_lo + st * (Cfg::kBlkBytes >> 4);
-      if (elect_one()) {
+      if (leader()) {
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)  // S = Q K^T, A from tensor memory (8 columns per 16-element k-step)
           umma_f16_ts(t_s, t_q + kk * 8, ((uint64_t)hi << 32) | (bk + kstep_off<64>(kk)), idesc_s, kk != 0);
@@ -946,6 +985,25 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfl
       if (j > 0) issue_dq(j - 1);
     }
     issue_dq(nkv - 1);
+  } else if (SPILL && warp == 2 + kEwWarps) {
+    // ---- store warp: one TMA store per finished Pd / dS tile (the element-wise warps fenced their writes for the async
+    // proxy before arriving on ds_full); the tile is handed back once the store has read it AND the dQ MMAs retired
+    if (lane == 0) {
+      const int bh_i = b * p.H + h;
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      for (int j = 0; j < nkv; ++j) {
+        const int u = j & 1;
+        mbar_wait(&ds_full[u], (j >> 1) & 1);
+        if (!(p.dbg & 1)) fa_tma_store_4d(&tma_pd, sPd + u * Cfg::kSBytes, 0, q0, j, bh_i, policy);
+        if (!(p.dbg & 2)) fa_tma_store_4d(&tma_ds, sdS + u * Cfg::kSBytes, 0, q0, j, bh_i, policy);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&ds_free[u]);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
   } else {
     const int quad = warp & 3;
     const int part = (warp - 2) >> 2;  // which kEwCols of the 64 key columns of a block this thread handles
@@ -1004,6 +1062,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfl
       __syncwarp();
       if (lane == 0) mbar_arrive(sp_free);
       uint32_t w[kEwCols / 2];
+      uint32_t wp[kEwCols / 2];  // (dead code when !SPILL)
 #pragma unroll
       for (int i = 0; i < kEwCols / 2; ++i) {
         const float2 x = ffma2(make_float2(__uint_as_float(a0[2 * i]), __uint_as_float(a0[2 * i + 1])), c2, nlse2);
@@ -1012,6 +1071,10 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfl
         if (DROP) drop_zero2(dp.x, dp.y, z[i], thresh2);
         const float2 e = fmul2(pr, ffma2(dp, ks2, ndel2));
         w[i] = pack_bf16x2(e.x, e.y);
+        if (SPILL) {
+          wp[i] = pack_bf16x2(pr.x, pr.y);
+          if (DROP) wp[i] &= drop_andmask(z[i], thresh2);  // Pd = P o mask (the 1 / (1 - p) is the dV GEMM's alpha)
+        }
       }
       if (j * 64 + 64 > p.N) {  // last, partial key block
         const int key0 = j * 64 + part * kEwCols;
@@ -1019,10 +1082,15 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfl
         for (int i = 0; i < kEwCols / 2; ++i) {
           if (key0 + 2 * i >= p.N) w[i] = 0u;
           else if (key0 + 2 * i + 1 >= p.N) w[i] &= 0xffffu;
+          if (SPILL) {
+            if (key0 + 2 * i >= p.N) wp[i] = 0u;
+            else if (key0 + 2 * i + 1 >= p.N) wp[i] &= 0xffffu;
+          }
         }
       }
       if (j >= 2) mbar_wait(&ds_free[u], ((j >> 1) - 1) & 1);  // dQ MMAs of block j-2 no longer read this dS tile
       store_part_row_sw128(sdS + u * Cfg::kSBytes + r * 128, r, part, w);
+      if constexpr (SPILL) { if (!(p.dbg & 4)) store_part_row_sw128(sPd + u * Cfg::kSBytes + r * 128, r, part, wp); }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -1057,6 +1125,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __nv_bfl
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA exits while its peer may still multicast into it / signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -1923,17 +1992,18 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
   p.drop_site = a.drop_site;
   p.drop_thresh14 = a.drop_thresh14;
   p.drop_scale = a.drop_scale;
+  { const char* v = getenv("S3D_FA_DBG"); p.dbg = v == nullptr ? 0 : atoi(v); }
   {
     const long long rows = (long long)a.B * a.H * a.N;
     fa_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a.o, a.dout, a.delta, a.B, a.H, a.N, DH, a.o_bs, a.o_hs, a.o_rs);
     S3D_LAUNCH_OK();
   }
   p.o_rs_elems = a.o_rs;
-  auto kq = fa_bwd_dq_tc_kernel<DH, DROP>;
+  auto kq = fa_bwd_dq_tc_kernel<DH, DROP, false, 1>;
   auto kkv = fa_bwd_dkv_tc_kernel<DH, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
-    S3D_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDqCfg<DH>::kSmemBytes));
+    S3D_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDqCfg<DH, false>::kSmemBytes));
     S3D_CUDA_OK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -1941,6 +2011,92 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
       (reinterpret_cast<uintptr_t>(a.dout) & 15))
     return S3D_ERR_ALIGNMENT;  // 16-byte row loads of Q / dO
   dim3 grid((a.N + 127) / 128, a.H, a.B);
+  // ---- single score pass: dQ kernel spills Pd / dS (bf16 [B*H, N, Npad]) into the caller's workspace, dV / dK are GEMMs.
+  // Measured on the group_embed shape (B = 15, H = 4, S = 12544, dh = 192, p = 0.1): see profiles/ and DESIGN.md 4.
+  if (a.workspace != nullptr && a.workspace_bytes >= attn_bwd_workspace_bytes(a.B, a.H, a.N, DH) &&
+      attn_bwd_workspace_bytes(a.B, a.H, a.N, DH) > 0 && (a.qkv_bs % DH) == 0 && (a.o_bs % DH) == 0) {
+    const long long npad = (a.N + 63) / 64 * 64;
+    const long long BH = (long long)a.B * a.H;
+    // workspace layout: 64-key panels [B*H][Npad / 64][N queries][64 keys] -- a 128 x 64 tile store and a GEMM operand box
+    // are contiguous runs in HBM (row-major [N, Npad] matrices wrote 128-byte pieces 25 KB apart: 3 TB/s)
+    __nv_bfloat16* pd = reinterpret_cast<__nv_bfloat16*>(a.workspace);
+    __nv_bfloat16* ds = pd + ((2 * BH * a.N * npad + 1023) / 1024 * 1024) / 2;
+    CUtensorMap tpd, tds;
+    if ((rc = make_tmap_bf16_panel(&tpd, pd, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128))) return rc;
+    if ((rc = make_tmap_bf16_panel(&tds, ds, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128))) return rc;
+    // S3D_FA_CL=2: CTA pairs sharing the K / V blocks by multicast. Measured equal (10.9 ms both ways on the group_embed
+    // shape): this kernel is bound by its element-wise warps and, with the stores on, by ~3.5 TB/s of HBM writes -- not by
+    // the L2 -> SM operand traffic the pairs halve. Off by default.
+    static const bool no_cluster = []() { const char* v = getenv("S3D_FA_CL"); return v == nullptr || v[0] != '2'; }();
+    if (no_cluster) {
+      auto kqs = fa_bwd_dq_tc_kernel<DH, DROP, true, 1>;
+      static bool attr3_set = false;
+      if (!attr3_set) {
+        S3D_CUDA_OK(cudaFuncSetAttribute(kqs, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDqCfg<DH, true>::kSmemBytes));
+        attr3_set = true;
+      }
+      kqs<<<grid, kFaBwdThreads + 32, FaDqCfg<DH, true>::kSmemBytes, stream>>>(t64, tpd, tds, a.q, a.dout, p);
+      S3D_LAUNCH_OK();
+    } else {
+      auto kqs = fa_bwd_dq_tc_kernel<DH, DROP, true, 2>;
+      static bool attr4_set = false;
+      if (!attr4_set) {
+        S3D_CUDA_OK(cudaFuncSetAttribute(kqs, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDqCfg<DH, true>::kSmemBytes));
+        attr4_set = true;
+      }
+      CUtensorMap t32;  // half-chunk boxes: every CTA of a pair loads 32 of the 64 rows and multicasts them
+      if ((rc = make_tmap_bf16_2d(&t32, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 32))) return rc;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((grid.x + 1) / 2 * 2, grid.y, grid.z);  // an odd last tile gets an idle partner (all rows >= N)
+      cfg.blockDim = dim3(kFaBwdThreads + 32, 1, 1);
+      cfg.dynamicSmemBytes = FaDqCfg<DH, true>::kSmemBytes;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      S3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kqs, t32, tpd, tds, a.q, a.dout, p));
+    }
+    // dV[b,h] = Pd[b,h]^T dO[b,h] / (1 - p);  dK[b,h] = dS[b,h]^T Q[b,h] * scale: A = workspace matrix read MN-major
+    // (m = key contiguous), B = dO / Q read MN-major (n = head channel contiguous), contraction over the queries.
+    // A (batch, head) slice of qkv / dout sits at element offset b * batch_stride + h * DH = (b * batch_stride / DH + h) * DH.
+    GemmArgs g{};
+    g.a_mn = 1;
+    g.b_mn = 1;
+    g.batch = (int)BH;
+    g.batch_stride_b = DH;
+    g.batch_inner = a.H;
+    g.bmul_a = a.H;
+    g.p.M = a.N;
+    g.p.N = DH;
+    g.p.K = a.N;
+    g.p.out_fp32 = 0;
+    g.p.epilogue = EPI_NONE;
+    g.p.batched = 1;
+    g.p.a_panel = 1;
+    g.p.batch_stride_d = DH;
+    g.p.ldd = a.qkv_rs;
+    g.bmul_d = (int)(a.qkv_bs / DH);
+    // dV
+    g.A = pd;
+    g.B = a.dout;
+    g.ldb = a.o_rs;
+    g.bmul_b = (int)(a.o_bs / DH);
+    g.p.D = a.dv;
+    g.p.alpha = DROP ? a.drop_scale : 1.0f;
+    if ((rc = gemm_bf16(g, stream))) return rc;
+    // dK
+    g.A = ds;
+    g.B = a.q;
+    g.ldb = a.qkv_rs;
+    g.bmul_b = (int)(a.qkv_bs / DH);
+    g.p.D = a.dk;
+    g.p.alpha = a.scale;
+    return gemm_bf16(g, stream);
+  }
   // Split dK / dV kernels (all A operands in tensor memory) or the fused dK/dV kernel (K, V tiles in shared memory)?
   // Measured on the group_embed shape (B = 15, H = 4, S = 12544, dh = 192), dK + dV:
   //     without dropout   split 7.8 + 5.8 = 13.6 ms (tensor pipe 71 % / 62 %)    fused 15.4 ms (41 %)
@@ -1967,12 +2123,23 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
     kdv<<<grid, kFaBwdThreads, FaDvCfg<DH>::kSmemBytes, stream>>>(t64, d64, a.k, p);
     S3D_LAUNCH_OK();
   }
-  kq<<<grid, kFaBwdThreads, FaDqCfg<DH>::kSmemBytes, stream>>>(t64, a.q, a.dout, p);
+  kq<<<grid, kFaBwdThreads, FaDqCfg<DH, false>::kSmemBytes, stream>>>(t64, t64, t64, a.q, a.dout, p);
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
 
 bool attn_tc_supported(int DH) { return DH == 48 || DH == 64 || DH == 96 || DH == 192; }
+
+// Workspace of the single-score-pass backward: two bf16 [B*H, N, Npad] matrices. 0 = that path does not apply (head dims
+// whose 64-column operand boxes would read a neighbouring head, short sequences where the two-kernel form is faster).
+long long attn_bwd_workspace_bytes(int B, int H, int N, int DH) {
+  const char* v = getenv("S3D_FA_SPILL_MIN_N");  // read per call: the parity tests lower it to cover this path at small N
+  const int min_n = v == nullptr ? 2048 : atoi(v);
+  if (!attn_tc_supported(DH) || N < min_n || B <= 0 || H <= 0) return 0;
+  const long long npad = (N + 63) / 64 * 64;
+  const long long one = (2LL * B * H * N * npad + 1023) / 1024 * 1024;  // bytes of one matrix, 1 KiB aligned
+  return 2 * one;
+}
 bool attn_tc_fwd_supported(int DH) { return attn_tc_supported(DH) || DH == 256; }
 
 template <bool DROP>

@@ -155,6 +155,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 
 // multicast variants: the box lands at the same smem offset in every CTA of `mask`, each CTA's mbarrier gets the bytes
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -575,6 +582,12 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 // rank-3 (batched) variant: dims {inner, outer, batch}.
 int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t batch,
                       uint64_t pitch_elems, uint64_t batch_pitch_elems, uint32_t box_inner, uint32_t box_outer);
+
+// 64-column panel layout [batch][panel = col / 64][row][64] of a bf16 matrix (every 64 x rows panel contiguous, 128-byte
+// rows): dims {64, rows, panels, batch}, box {64, box_rows, 1, 1}, 128B swizzle. Used for the attention backward's
+// workspace matrices: a 128 x 64 tile store and a 64 x 64 operand load are single contiguous runs in HBM.
+int make_tmap_bf16_panel(CUtensorMap* map, const void* base, uint64_t rows, uint64_t panels, uint64_t batch,
+                         uint32_t box_rows);
 
 int num_sms();
 

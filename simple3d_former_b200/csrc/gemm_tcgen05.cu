@@ -248,7 +248,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int batch = blockIdx.y;
 
   static_assert(CL == 1 || (BN / 64) % CL == 0, "every CTA of the cluster loads BN / CL rows (whole 64-wide chunks)");
   const int num_m = (p.M + BM - 1) / BM;
@@ -257,7 +256,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int num_kb_total = (p.K + BK - 1) / BK;
   const int splits = p.splits;
   const int kb_per_split = (num_kb_total + splits - 1) / splits;
-  const int num_items = num_msuper * num_n * splits;
+  const int items_per_batch = num_msuper * num_n * splits;
+  const int num_items = items_per_batch * (p.batched ? p.batch : 1);  // batches are folded into the persistent item loop
   const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
@@ -290,7 +290,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   pdl_wait();
 
   // work item -> (m tile of this CTA, n tile, k-block range)
-  auto decode = [&](int item, int& m0, int& n0, int& kb0, int& kb1, int& split) {
+  // batch index -> tensor-map batch coordinate of an operand: (bt / inner) * mul + bt % inner (a two-level (batch, head)
+  // offset whose strides are both multiples of the head stride collapses into ONE coordinate of stride head_stride)
+  auto bcoord = [&](int bt, int mul) { return (bt / p.batch_inner) * mul + bt % p.batch_inner; };
+  auto decode = [&](int item, int& m0, int& n0, int& kb0, int& kb1, int& split, int& bt) {
+    bt = item / items_per_batch;
+    item -= bt * items_per_batch;
     split = item % splits;
     const int t = item / splits;
     n0 = (t % num_n) * BN;
@@ -305,8 +310,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters) {
-        int m0, n0, kb0, kb1, split;
-        decode(item, m0, n0, kb0, kb1, split);
+        int m0, n0, kb0, kb1, split, bt;
+        decode(item, m0, n0, kb0, kb1, split, bt);
+        const int batch = bcoord(bt, p.bmul_a), batch_b = bcoord(bt, p.bmul_b);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -317,7 +323,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (A_MN) {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i) {
-              if (p.batched) tma_load_3d(sa + i * 8192, &tma_a, &full_bar[stage], m0 + 64 * i, k0, batch);
+              if (p.a_panel) tma_load_4d(sa + i * 8192, &tma_a, &full_bar[stage], 0, k0, (m0 >> 6) + i, batch);
+              else if (p.batched) tma_load_3d(sa + i * 8192, &tma_a, &full_bar[stage], m0 + 64 * i, k0, batch);
               else tma_load_2d(sa + i * 8192, &tma_a, &full_bar[stage], m0 + 64 * i, k0);
             }
           } else {
@@ -330,10 +337,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int i = 0; i < BN / 64 / CL; ++i) {
               const int ch = crank * (BN / 64 / CL) + i;
               if (CL > 1) {
-                if (p.batched) tma_load_3d_mc(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0, batch, kMcMask);
+                if (p.batched) tma_load_3d_mc(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0, batch_b, kMcMask);
                 else tma_load_2d_mc(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0, kMcMask);
               } else {
-                if (p.batched) tma_load_3d(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0, batch);
+                if (p.batched) tma_load_3d(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0, batch_b);
                 else tma_load_2d(sb + ch * 8192, &tma_b, &full_bar[stage], n0 + 64 * ch, k0);
               }
             }
@@ -341,10 +348,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             uint8_t* dst = sb + crank * kBRowsPerCta * 128;
             const int nrow = n0 + crank * kBRowsPerCta;
             if (CL > 1) {
-              if (p.batched) tma_load_3d_mc(dst, &tma_b, &full_bar[stage], k0, nrow, batch, kMcMask);
+              if (p.batched) tma_load_3d_mc(dst, &tma_b, &full_bar[stage], k0, nrow, batch_b, kMcMask);
               else tma_load_2d_mc(dst, &tma_b, &full_bar[stage], k0, nrow, kMcMask);
             } else {
-              if (p.batched) tma_load_3d(dst, &tma_b, &full_bar[stage], k0, nrow, batch);
+              if (p.batched) tma_load_3d(dst, &tma_b, &full_bar[stage], k0, nrow, batch_b);
               else tma_load_2d(dst, &tma_b, &full_bar[stage], k0, nrow);
             }
           }
@@ -367,8 +374,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int as = 0;
       uint32_t aphase = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters) {
-        int m0, n0, kb0, kb1, split;
-        decode(item, m0, n0, kb0, kb1, split);
+        int m0, n0, kb0, kb1, split, bt;
+        decode(item, m0, n0, kb0, kb1, split, bt);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -403,11 +410,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     constexpr int kColsPerHalf = BN / EPW;
     int as = 0;
     uint32_t aphase = 0;
-    const long long boff_d = p.batched ? (long long)batch * p.batch_stride_d : 0;
-    const long long boff_r = p.batched ? (long long)batch * p.batch_stride_r : 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
-      int m0, n0, kb0, kb1, split;
-      decode(item, m0, n0, kb0, kb1, split);
+      int m0, n0, kb0, kb1, split, bt;
+      decode(item, m0, n0, kb0, kb1, split, bt);
+      const int batch = bcoord(bt, p.bmul_d);
+      const long long boff_d = p.batched ? (long long)batch * p.batch_stride_d : 0;
+      const long long boff_r = p.batched ? (long long)batch * p.batch_stride_r : 0;
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
       if (splits == 1 && row_ok) {
@@ -723,9 +731,24 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t inner, uint64
   return r == CUDA_SUCCESS ? S3D_OK : S3D_ERR_DRIVER;
 }
 
+int make_tmap_bf16_panel(CUtensorMap* map, const void* base, uint64_t rows, uint64_t panels, uint64_t batch,
+                         uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return S3D_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 1023) != 0) return S3D_ERR_ALIGNMENT;
+  cuuint64_t dims[4] = {64, rows, panels, batch};
+  cuuint64_t strides[3] = {128, rows * 128, panels * rows * 128};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? S3D_OK : S3D_ERR_DRIVER;
+}
+
 // rank-2 / rank-3 tensor map over the output (bf16 or fp32), box {box_inner, 32 rows}, 128B swizzle (staged epilogue)
 static int make_tmap_out(CUtensorMap* map, const void* base, int is_f32, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
-                         int batch, uint64_t batch_pitch_elems) {
+                         int batch, uint64_t batch_pitch_elems, bool rank3) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) return S3D_ERR_DRIVER;
   const uint64_t es = is_f32 ? 4 : 2;
@@ -735,7 +758,7 @@ static int make_tmap_out(CUtensorMap* map, const void* base, int is_f32, uint64_
   cuuint64_t strides[2] = {pitch_elems * es, batch_pitch_elems * es};
   cuuint32_t box[3] = {box_inner, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  const int rank = batch > 1 ? 3 : 2;
+  const int rank = rank3 ? 3 : 2;
   if (rank == 3 && (batch_pitch_elems * es) % 16 != 0) return S3D_ERR_ALIGNMENT;
   CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -765,12 +788,16 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   int rc;
   const GemmParams& p = g.p;
   constexpr int kBBoxRows = BN / CL;
-  if (g.batch > 1) {
-    if (A_MN) rc = make_tmap_bf16_3d(&ta, g.A, p.M, p.K, g.batch, g.lda, g.batch_stride_a, 64, 64);
-    else rc = make_tmap_bf16_3d(&ta, g.A, p.K, p.M, g.batch, g.lda, g.batch_stride_a, 64, BM);
+  // extent of an operand's batch dimension under the coordinate mapping of GemmParams
+  auto bdim = [&](int mul) { return (uint64_t)((g.batch / p.batch_inner - 1) * mul + p.batch_inner); };
+  if (p.a_panel && !A_MN) return S3D_ERR_UNSUPPORTED;
+  if (p.batched) {
+    if (A_MN && p.a_panel) rc = make_tmap_bf16_panel(&ta, g.A, p.K, (uint64_t)(p.M + 63) / 64, bdim(p.bmul_a), 64);
+    else if (A_MN) rc = make_tmap_bf16_3d(&ta, g.A, p.M, p.K, bdim(p.bmul_a), g.lda, g.batch_stride_a, 64, 64);
+    else rc = make_tmap_bf16_3d(&ta, g.A, p.K, p.M, bdim(p.bmul_a), g.lda, g.batch_stride_a, 64, BM);
     if (rc) return rc;
-    if (B_MN) rc = make_tmap_bf16_3d(&tb, g.B, p.N, p.K, g.batch, g.ldb, g.batch_stride_b, 64, 64);
-    else rc = make_tmap_bf16_3d(&tb, g.B, p.K, p.N, g.batch, g.ldb, g.batch_stride_b, 64, kBBoxRows);
+    if (B_MN) rc = make_tmap_bf16_3d(&tb, g.B, p.N, p.K, bdim(p.bmul_b), g.ldb, g.batch_stride_b, 64, 64);
+    else rc = make_tmap_bf16_3d(&tb, g.B, p.K, p.N, bdim(p.bmul_b), g.ldb, g.batch_stride_b, 64, kBBoxRows);
     if (rc) return rc;
   } else {
     if (A_MN) rc = make_tmap_bf16_2d(&ta, g.A, p.M, p.K, g.lda, 64, 64);
@@ -784,11 +811,12 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   memset(&td, 0, sizeof(td));
   memset(&taux, 0, sizeof(taux));
   if (BN >= 128 && p.splits == 1) {
-    rc = make_tmap_out(&td, p.D, p.out_fp32, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldd, g.batch, (uint64_t)p.batch_stride_d);
+    rc = make_tmap_out(&td, p.D, p.out_fp32, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldd, (int)bdim(p.bmul_d),
+                       (uint64_t)p.batch_stride_d, p.batched != 0);
     if (rc) return rc;
     if (p.aux_out != nullptr) {
       if (g.batch > 1) return S3D_ERR_UNSUPPORTED;
-      rc = make_tmap_out(&taux, p.aux_out, 0, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ld_aux_out, 1, 0);
+      rc = make_tmap_out(&taux, p.aux_out, 0, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ld_aux_out, 1, 0, false);
       if (rc) return rc;
     }
   }
@@ -799,14 +827,15 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     attr_set = true;
   }
   const int num_m = (p.M + BM - 1) / BM;
-  const int items = ((num_m + CL - 1) / CL) * ((p.N + BN - 1) / BN) * p.splits;
-  const int sms = num_sms();
   const int nb = g.batch > 1 ? g.batch : 1;
-  int max_clusters = (sms / nb) / CL;
+  const long long items = (long long)((num_m + CL - 1) / CL) * ((p.N + BN - 1) / BN) * p.splits * nb;
+  if (items > 0x7fffffffLL) return S3D_ERR_BAD_SHAPE;
+  const int sms = num_sms();
+  int max_clusters = sms / CL;
   if (max_clusters < 1) max_clusters = 1;
-  const int clusters = items < max_clusters ? items : max_clusters;
+  const int clusters = items < max_clusters ? (int)items : max_clusters;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(clusters * CL, nb, 1);
+  cfg.gridDim = dim3(clusters * CL, 1, 1);
   cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
@@ -861,6 +890,14 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   g.p.k_sbo = k_sbo;
   GemmParams& p = g.p;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return S3D_ERR_BAD_SHAPE;
+  p.batch = g.batch > 1 ? g.batch : 1;
+  p.batch_inner = g.batch_inner > 0 ? g.batch_inner : 1;
+  if (p.batch % p.batch_inner != 0) return S3D_ERR_BAD_SHAPE;
+  p.bmul_a = g.batch_inner > 0 ? g.bmul_a : 1;
+  p.bmul_b = g.batch_inner > 0 ? g.bmul_b : 1;
+  p.bmul_d = g.batch_inner > 0 ? g.bmul_d : 1;
+  if (p.a_panel) p.batched = 1;  // panel operands are addressed through rank-4 / rank-3 maps even for a single batch
+  if (p.batch > 1 && !p.batched) return S3D_ERR_BAD_SHAPE;
   if (g.A == nullptr || g.B == nullptr || p.D == nullptr) return S3D_ERR_NULL;
   if ((p.epilogue == EPI_DGELU || p.epilogue == EPI_DRELU) && p.aux_in == nullptr) return S3D_ERR_NULL;
   // vector epilogue accesses need 16-byte aligned rows

@@ -21,6 +21,10 @@ struct GemmParams {
   float alpha;
   long long batch_stride_d, batch_stride_r;
   int batched;
+  // batch count and the batch-index -> tensor-map coordinate mapping (bt / batch_inner) * bmul_x + bt % batch_inner of
+  // A, B and D / residual (plain batches: batch_inner = 1, bmul = 1); filled by gemm_bf16 from GemmArgs
+  int batch, batch_inner, bmul_a, bmul_b, bmul_d;
+  int a_panel;  // MN-major A stored as 64-column panels [batch][M / 64][K][64] (make_tmap_bf16_panel); needs batched = 1
   // UMMA smem-descriptor byte offsets (defaults: MN-major LBO 8192 / SBO 1024, K-major LBO 16 / SBO 1024);
   // overridable through S3D_DBG_* environment variables for bring-up on new silicon.
   unsigned mn_lbo, mn_sbo, k_lbo, k_sbo;
@@ -33,6 +37,9 @@ struct GemmArgs {
   int a_mn, b_mn;
   int batch;
   long long batch_stride_a, batch_stride_b;
+  // optional two-level batches (attention: batch = B * H, batch_inner = H): operand x of batch bt sits at tensor-map
+  // batch coordinate (bt / batch_inner) * bmul_x + bt % batch_inner, in units of its batch stride. 0 = plain batches.
+  int batch_inner, bmul_a, bmul_b, bmul_d;
   int force_bn;
   int force_cluster;  // 0 = auto
   int force_splits;   // 0 = auto
@@ -79,6 +86,9 @@ struct AttnParams {
   uint32_t drop_site;
   uint32_t drop_thresh14;  // keep <=> 14-bit draw >= thresh14 = round(p * 16384), see common.cuh
   float drop_scale;
+  // backward only: caller-owned scratch for the single-score-pass form (attn_bwd_workspace_bytes; nullptr = two-kernel form)
+  void* workspace;
+  long long workspace_bytes;
 };
 int attn_fwd(const AttnParams& p, int DH, cudaStream_t stream);
 int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream);
@@ -88,6 +98,7 @@ bool attn_tc_supported(int DH);      // forward and backward
 bool attn_tc_fwd_supported(int DH);  // forward only: additionally head_dim 256 (all A operands fit tensor memory)
 int attn_fwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
 int attn_bwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
+long long attn_bwd_workspace_bytes(int B, int H, int N, int DH);
 
 // pointops.cu
 int knn(const float* xyz, const float* query, long long* idx, float* dist, int B, int N, int S, int K,

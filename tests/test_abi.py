@@ -30,7 +30,7 @@ def test_header_symbols_exported_and_bound():
 def test_version_and_error_strings():
     from simple3d_former_b200 import _lib as L
     lib = L.lib()
-    assert lib.s3d_abi_version() == 3
+    assert lib.s3d_abi_version() == 4
     assert lib.s3d_error_string(0) == b"ok"
     assert b"aligned" in lib.s3d_error_string(-3)
     assert b"NULL" in lib.s3d_error_string(-4)

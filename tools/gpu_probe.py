@@ -11,7 +11,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-GROUPS = ["attn_tc", "gemm_epi_perf", "gemm_small", "gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
+GROUPS = ["attn_tc", "attn_spill", "gemm_epi_perf", "gemm_small", "gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
 
 
 def rel_err(a, b):
@@ -425,6 +425,88 @@ def g_attn_tc():
                                    drop_site=1, drop_p=0.1))
     print(f"  [PERF] attn bwd group_embed shape, dropout p=0.1: {ms:.2f} ms  {10.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s "
           f"(algorithmic)", flush=True)
+
+
+def g_attn_spill():
+    """Single-score-pass flash backward (dQ kernel spills P o mask / dS, dK / dV are batched GEMMs): against torch without
+    dropout, and against the recomputing two-kernel form with the SAME dropout mask; then the group_embed shape timed in
+    both forms."""
+    import torch
+    from simple3d_former_b200 import _lib as L
+    torch.manual_seed(12)
+    old = os.environ.get("S3D_FA_SPILL_MIN_N")
+    os.environ["S3D_FA_SPILL_MIN_N"] = "1"
+    try:
+        seed = torch.tensor([777], dtype=torch.int32, device="cuda")
+        for (B, N, H, dh, layout, p_drop) in [(2, 1024, 4, 192, "seqfirst", 0.0), (3, 700, 4, 192, "seqfirst", 0.1),
+                                              (1, 1088, 4, 192, "seqfirst", 0.0), (2, 1100, 3, 64, "timm", 0.0),
+                                              (3, 257, 3, 64, "timm", 0.1), (2, 700, 4, 96, "seqfirst", 0.0),
+                                              (2, 600, 4, 48, "seqfirst", 0.1), (1, 130, 1, 64, "timm", 0.25),
+                                              (3, 640, 2, 192, "timm", 0.1), (2, 2176, 4, 192, "seqfirst", 0.1)]:
+            assert L.lib().s3d_attn_bwd_workspace_bytes(B, H, N, dh) > 0
+            qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
+            lse = torch.empty(B, H, N, device="cuda")
+            delta = torch.empty(B, H, N, device="cuda")
+            scale = dh ** -0.5
+            kw = dict(drop_seed=seed, drop_site=1, drop_p=p_drop) if p_drop > 0 else {}
+            L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, scale, **kw)
+            dout = torch.randn_like(out.float()).bfloat16()
+            res = []
+            for ws in (True, False):
+                dqkv = torch.full_like(qkv, float("nan"))
+                dq, dk, dv = dqkv.select(2, 0), dqkv.select(2, 1), dqkv.select(2, 2)
+                L.attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out, dout, lse, delta, dq.data_ptr(), dk.data_ptr(),
+                           dv.data_ptr(), B, H, N, dh, qs, os_, scale, workspace=ws, **kw)
+                torch.cuda.synchronize()
+                res.append((perm(dq).float(), perm(dk).float(), perm(dv).float()))
+            tag = f"B{B} N{N} H{H} dh{dh} {layout} p{p_drop}"
+            for name, a, b in zip(("dq", "dk", "dv"), res[0], res[1]):
+                report(f"attn bwd spill vs two-kernel {name} {tag}", rel_err(a, b), 1e-2)
+            if p_drop == 0.0:
+                qr = perm(q).float().detach().requires_grad_(True)
+                kr = perm(k).float().detach().requires_grad_(True)
+                vr = perm(v).float().detach().requires_grad_(True)
+                s_ = (qr @ kr.transpose(-1, -2)) * scale
+                (s_.softmax(-1) @ vr).backward(perm(dout).float())
+                del s_
+                for name, a, b in zip(("dq", "dk", "dv"), res[0], (qr.grad, kr.grad, vr.grad)):
+                    report(f"attn bwd spill vs torch {name} {tag}", rel_err(a, b), 2e-2)
+                del qr, kr, vr
+    finally:
+        if old is None:
+            os.environ.pop("S3D_FA_SPILL_MIN_N", None)
+        else:
+            os.environ["S3D_FA_SPILL_MIN_N"] = old
+    if os.environ.get("S3D_PROBE_PERF", "1") == "0":
+        return
+    B, N, H, dh = 15, 12544, 4, 192
+    qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, "seqfirst")
+    lse = torch.empty(B, H, N, device="cuda")
+    delta = torch.empty(B, H, N, device="cuda")
+    dout = torch.randn_like(out.float()).bfloat16()
+    dqkv = torch.zeros_like(qkv)
+    dq, dk, dv = dqkv.select(2, 0), dqkv.select(2, 1), dqkv.select(2, 2)
+    seed = torch.tensor([20210915], dtype=torch.int32, device="cuda")
+
+    def timeit(fn, reps=4):
+        for _ in range(2):
+            fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+    for p_drop in (0.0, 0.1):
+        kw = dict(drop_seed=seed, drop_site=1, drop_p=p_drop) if p_drop > 0 else {}
+        L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, dh ** -0.5, **kw)
+        for ws in (True, False):
+            ms = timeit(lambda: L.attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out, dout, lse, delta, dq.data_ptr(),
+                                           dk.data_ptr(), dv.data_ptr(), B, H, N, dh, qs, os_, dh ** -0.5, workspace=ws, **kw))
+            print(f"  [PERF] attn bwd group_embed shape p={p_drop} {'single score pass + 2 GEMMs' if ws else 'two-kernel form'}: "
+                  f"{ms:.2f} ms  {10.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s (algorithmic)", flush=True)
 
 
 def g_attn_fwd():
