@@ -108,6 +108,14 @@ int s3d_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 int s3d_transpose_to_bf16(const void* in, int in_is_bf16, void* out, int R, int C, int64_t ld_in, int64_t ld_out,
                           void* stream);
 /* out[c] (+)= sum_t in[t, c]; Linear bias gradients */
+/* fp32 strided GEMM on the CUDA cores: C[M,N] (+)= alpha * sum_k A(m,k) B(k,n) [+ bias[n]] [ReLU] [zero where gate <= 0],
+ * A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn], C / gate row-major. The thin fp32 layers of the point models
+ * (fc1 / fc_pos_embed stem, reference models/3DViT/model.py:236-247,310-311) and the classification heads (model.py:232,
+ * vit_3d_2d_pretrain.py:366): y = x W^T + b, dx = dy W and dW = dy^T x are the same call with transposed strides. Long
+ * contractions with few output tiles are split and reduced with atomicAdd (C zeroed first unless accumulate). */
+int s3d_sgemm_f32(const float* A, const float* B, float* C, int M, int N, int K, int64_t sam, int64_t sak, int64_t sbk,
+                  int64_t sbn, int64_t ldc, float alpha, const float* bias, int relu, const float* gate, int64_t ld_gate,
+                  int accumulate, void* stream);
 int s3d_colsum_bf16(const void* in, float* out, int T, int C, int64_t ld, int accumulate, void* stream);
 /* Conv3d(k = s = cell) operand: x [B,1,V,V,V] -> P bf16 [B*p*p*(zsum?1:p), Kpad]; zsum sums the pz patches of a
  * column first (VoxelEmbed's mean over dim 4, embed_layer_3d_modality.py:38). in_dtype: 0 = f32, 1 = uint8/bool,

@@ -24,6 +24,8 @@ SIGNATURES = {
     "s3d_gemm_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float,
                               _P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_int64, c_int64, c_int64,
                               c_int64, c_int, c_int, c_int, _P]),
+    "s3d_sgemm_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, _P,
+                              c_int, _P, c_int64, c_int, _P]),
     "s3d_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "s3d_layernorm_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "s3d_attn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64,
@@ -180,6 +182,28 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, al
          a.stride(0) if batched else 0, b.stride(0) if batched else 0, out.stride(0) if batched else 0,
          residual.stride(0) if (batched and residual is not None) else 0, force_bn, force_cluster, force_splits,
          stream())
+    return out
+
+
+def sgemm(a, b, *, out=None, bias=None, relu=False, gate=None, accumulate=False, alpha=1.0):
+    """fp32 C[M,N] (+)= alpha * a[M,K] @ b[K,N] (+ bias) (ReLU) (zeroed where gate <= 0) on the CUDA cores; a and b may be
+    arbitrary 2-D strided views (x.t() costs nothing). The thin fp32 layers of the path (point stem, heads)."""
+    _need_cuda(a, b)
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
+    M, K = a.shape
+    K2, N = b.shape
+    assert K == K2
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.shape == (M, N) and out.stride(1) == 1
+    if gate is not None:
+        assert gate.dtype == torch.float32 and gate.shape == (M, N) and gate.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    call("s3d_sgemm_f32", ptr(a), ptr(b), ptr(out), M, N, K, a.stride(0), a.stride(1), b.stride(0), b.stride(1),
+         out.stride(0), float(alpha), ptr(bias), int(relu), ptr(gate), gate.stride(0) if gate is not None else 0,
+         int(accumulate), stream())
     return out
 
 

@@ -67,6 +67,13 @@ int s3d_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
   return s3d::gemm_bf16(g, as_stream(stream));
 }
 
+int s3d_sgemm_f32(const float* A, const float* B, float* C, int M, int N, int K, int64_t sam, int64_t sak, int64_t sbk,
+                  int64_t sbn, int64_t ldc, float alpha, const float* bias, int relu, const float* gate, int64_t ld_gate,
+                  int accumulate, void* stream) {
+  return s3d::sgemm_f32(A, B, C, M, N, K, sam, sak, sbk, sbn, ldc, alpha, bias, relu, gate, ld_gate, accumulate,
+                        as_stream(stream));
+}
+
 int s3d_layernorm_fwd(const float* x, const float* addend, float* sum_out, const float* gamma, const float* beta,
                       void* y_bf16, float* y_f32, float* mean, float* rstd, int T, int D, float eps, void* stream) {
   return s3d::layernorm_fwd(x, addend, sum_out, gamma, beta, y_bf16, y_f32, mean, rstd, T, D, eps, as_stream(stream));

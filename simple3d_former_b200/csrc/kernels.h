@@ -100,6 +100,11 @@ int attn_fwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
 int attn_bwd_tc(const AttnParams& p, int DH, cudaStream_t stream);
 long long attn_bwd_workspace_bytes(int B, int H, int N, int DH);
 
+// linear_f32.cu
+int sgemm_f32(const float* A, const float* B, float* C, int M, int N, int K, long long sam, long long sak, long long sbk,
+              long long sbn, long long ldc, float alpha, const float* bias, int relu, const float* gate, long long ld_gate,
+              int accumulate, cudaStream_t stream);
+
 // pointops.cu
 int knn(const float* xyz, const float* query, long long* idx, float* dist, int B, int N, int S, int K,
         cudaStream_t stream);

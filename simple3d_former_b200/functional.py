@@ -364,6 +364,103 @@ class BlockFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Thin fp32 layers (classification heads, the point models' stem): CUDA-core fp32 GEMM, no bf16 rounding
+# ----------------------------------------------------------------------------------------------------------------
+_ONES = {}
+
+
+def _ones_row(n, device):
+    key = (device.type, device.index)
+    t = _ONES.get(key)
+    if t is None or t.numel() < n:
+        t = torch.ones(max(n, 1 << 18), device=device, dtype=torch.float32)
+        _ONES[key] = t
+    return t[:n].view(1, n)
+
+
+def _wgrad_f32(w, dy2, x2):
+    """dW (+)= dy2^T @ x2 in fp32 (into the parameter's gradient sink when it has one)."""
+    sk = _sink(w)
+    if sk is None:
+        return L.sgemm(dy2.t(), x2).view(w.shape)
+    L.sgemm(dy2.t(), x2, out=sk.view(sk.shape[0], -1), accumulate=True)
+    w._s3d_owner.note_write(w)
+    return None
+
+
+def _bgrad_f32(b, dy2):
+    """db (+)= column sums of dy2 (fp32) as a [1, R] x [R, N] product of the same kernel."""
+    if b is None:
+        return None
+    ones = _ones_row(dy2.shape[0], dy2.device)
+    sk = _sink(b)
+    if sk is None:
+        return L.sgemm(ones, dy2).view(b.shape)
+    L.sgemm(ones, dy2, out=sk.view(1, -1), accumulate=True)
+    b._s3d_owner.note_write(b)
+    return None
+
+
+class LinearF32Fn(torch.autograd.Function):
+    """y = x W^T + b in fp32 (nn.Linear heads: vit_3d_2d_pretrain.py:366, models/3DViT/model.py:232)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K).float()
+        y = L.sgemm(x2, weight.detach().t(), bias=bias.detach() if bias is not None else None)
+        ctx.save_for_backward(x2, weight)
+        ctx.bias_ref = bias
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).float()
+        dx = L.sgemm(dy2, weight.detach()).view(ctx.in_shape) if ctx.needs_input_grad[0] else None
+        dw = _wgrad_f32(weight, dy2, x2) if ctx.needs_input_grad[1] else None
+        db = _bgrad_f32(ctx.bias_ref, dy2) if (ctx.bias_ref is not None and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+class PointStemFn(torch.autograd.Function):
+    """f = fc1(x) + fc_pos_embed(xyz), each Linear -> ReLU -> Linear (models/3DViT/model.py:236-247, 310-311) as one
+    node: four fp32 GEMM launches forward (the second branch accumulates onto the first), the ReLU masks applied inside
+    the backward GEMMs. The inputs are data (no input gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, xyz, w1a, b1a, w1b, b1b, w2a, b2a, w2b, b2b):
+        B, N, _ = x.shape
+        x2 = x.reshape(B * N, -1).float()
+        p2 = xyz.reshape(B * N, -1).float()
+        h1 = L.sgemm(x2, w1a.detach().t(), bias=b1a.detach(), relu=True)
+        h2 = L.sgemm(p2, w2a.detach().t(), bias=b2a.detach(), relu=True)
+        f = L.sgemm(h1, w1b.detach().t(), bias=b1b.detach())
+        L.sgemm(h2, w2b.detach().t(), bias=b2b.detach(), out=f, accumulate=True)
+        ctx.save_for_backward(x2, p2, h1, h2, w1a, w1b, w2a, w2b)
+        ctx.refs = (b1a, b1b, b2a, b2b)
+        return f.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, df):
+        x2, p2, h1, h2, w1a, w1b, w2a, w2b = ctx.saved_tensors
+        b1a, b1b, b2a, b2b = ctx.refs
+        df2 = df.reshape(h1.shape[0], -1).float()
+        if not df2.is_contiguous():
+            df2 = df2.contiguous()
+        out = []
+        for inp, h, wa, ba, wb, bb in ((x2, h1, w1a, b1a, w1b, b1b), (p2, h2, w2a, b2a, w2b, b2b)):
+            dwb = _wgrad_f32(wb, df2, h)
+            dbb = _bgrad_f32(bb, df2)
+            dh = L.sgemm(df2, wb.detach(), gate=h)  # gradient through the ReLU: zero where the activation was clipped
+            dwa = _wgrad_f32(wa, dh, inp)
+            dba = _bgrad_f32(ba, dh)
+            out += [dwa, dba, dwb, dbb]
+        return (None, None, *out)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # LayerNorm as its own node (VisionTransformer.norm on the fp32 residual stream)
 # ----------------------------------------------------------------------------------------------------------------
 class LayerNormFn(torch.autograd.Function):

@@ -166,7 +166,7 @@ class Feature3D_ViT2D_V2(VisionTransformer):
         x = self.pos_drop(x + self.pos_embed)
         for blk in self.blocks:
             x = blk(x)
-        return self.head(self.norm(x[:, 0]))
+        return Fn.LinearF32Fn.apply(self.norm(x[:, 0]), self.head.weight, self.head.bias)
 
     def _tokens(self, x):
         emb = self.voxel_embed
@@ -200,7 +200,7 @@ class Feature3D_ViT2D_V2(VisionTransformer):
         return self.norm(t[:, 0])
 
     def forward(self, x):
-        return self.voxel_head(self.forward_features(x))
+        return Fn.LinearF32Fn.apply(self.forward_features(x), self.voxel_head.weight, self.voxel_head.bias)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -333,7 +333,9 @@ class _PointTransformerBase(VisionTransformer):
 
     def forward_features(self, x):
         xyz = x[..., :3].contiguous()
-        f = self.pos_drop(self.fc1(x) + self.fc_pos_embed(xyz))
+        f = self.pos_drop(Fn.PointStemFn.apply(x, xyz, self.fc1[0].weight, self.fc1[0].bias, self.fc1[2].weight,
+                                               self.fc1[2].bias, self.fc_pos_embed[0].weight, self.fc_pos_embed[0].bias,
+                                               self.fc_pos_embed[2].weight, self.fc_pos_embed[2].bias))
         xyz_0, points_0 = self.transition_downs[0](xyz, f)
         xyz_1, points_1 = self.transition_downs[1](xyz_0, points_0)
         t = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), points_1), dim=1)
@@ -345,7 +347,7 @@ class _PointTransformerBase(VisionTransformer):
         return t if self._seg else t.mean(1)
 
     def forward(self, x):
-        return self.head(self.forward_features(x))
+        return Fn.LinearF32Fn.apply(self.forward_features(x), self.head.weight, self.head.bias)
 
 
 class PointTransformerCls(_PointTransformerBase):

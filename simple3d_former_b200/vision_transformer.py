@@ -206,7 +206,10 @@ class VisionTransformer(nn.Module):
         return self.norm(x)[:, 0]
 
     def forward(self, x):
-        return self.head(self.forward_features(x))
+        f = self.forward_features(x)
+        if isinstance(self.head, nn.Linear):  # fp32 head on our own CUDA-core GEMM (no cuBLAS on the path)
+            return Fn.LinearF32Fn.apply(f, self.head.weight, self.head.bias)
+        return self.head(f)
 
 
 # norm_layer used by every backbone of the reference (vit_3d_2d_pretrain.py:287): LayerNorm(eps=1e-6), fused kernel

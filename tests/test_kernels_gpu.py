@@ -16,7 +16,7 @@ probe = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(probe)
 
 
-@pytest.mark.parametrize("group", ["gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "attn_tc", "attn_spill",
+@pytest.mark.parametrize("group", ["gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "attn_tc", "attn_spill", "sgemm",
                                    "elementwise", "points"])
 def test_kernel_group(group):
     import torch

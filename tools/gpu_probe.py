@@ -11,7 +11,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-GROUPS = ["attn_tc", "attn_spill", "gemm_epi_perf", "gemm_small", "gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
+GROUPS = ["attn_tc", "attn_spill", "sgemm", "gemm_epi_perf", "gemm_small", "gemm_perf", "gemm_k", "gemm_mn", "gemm_epi", "gemm_batched", "ln", "attn_fwd", "attn_bwd", "elementwise", "points"]
 
 
 def rel_err(a, b):
@@ -507,6 +507,58 @@ def g_attn_spill():
                                            dk.data_ptr(), dv.data_ptr(), B, H, N, dh, qs, os_, dh ** -0.5, workspace=ws, **kw))
             print(f"  [PERF] attn bwd group_embed shape p={p_drop} {'single score pass + 2 GEMMs' if ws else 'two-kernel form'}: "
                   f"{ms:.2f} ms  {10.0 * B * H * N * N * dh / ms / 1e9:.1f} TFLOP/s (algorithmic)", flush=True)
+
+
+def g_sgemm():
+    """fp32 CUDA-core GEMM (point stem, heads) against torch fp32 (highest precision), strided views, split-K, epilogues;
+    then the two autograd nodes built on it against the nn modules they replace."""
+    import torch
+    import torch.nn as nn
+    from simple3d_former_b200 import _lib as L
+    from simple3d_former_b200 import functional as Fn
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(21)
+    dev = "cuda"
+    for (M, N, K) in [(131072, 48, 6), (1000, 48, 48), (64, 40, 768), (48, 48, 70000), (1, 48, 131072), (130, 70, 33)]:
+        a = torch.randn(M, K, device=dev)
+        b = torch.randn(K, N, device=dev)
+        bias = torch.randn(N, device=dev)
+        report(f"sgemm {M}x{N}x{K}", rel_err(L.sgemm(a, b, bias=bias), a @ b + bias), 2e-5)
+        at = torch.randn(K, M, device=dev)
+        bt = torch.randn(N, K, device=dev)
+        report(f"sgemm strided views {M}x{N}x{K}", rel_err(L.sgemm(at.t(), bt.t()), at.t() @ bt.t()), 2e-5)
+    a = torch.randn(300, 20, device=dev)
+    b = torch.randn(20, 50, device=dev)
+    g = torch.randn(300, 50, device=dev)
+    c0 = torch.randn(300, 50, device=dev)
+    report("sgemm relu", rel_err(L.sgemm(a, b, relu=True), (a @ b).relu()), 2e-5)
+    report("sgemm gate", rel_err(L.sgemm(a, b, gate=g), (a @ b) * (g > 0)), 2e-5)
+    c = c0.clone()
+    L.sgemm(a, b, out=c, accumulate=True, alpha=0.5)
+    report("sgemm accumulate", rel_err(c, c0 + 0.5 * (a @ b)), 2e-5)
+    a = torch.randn(50000, 24, device=dev)
+    b = torch.randn(50000, 48, device=dev)
+    c = c0[:24, :48].clone()
+    L.sgemm(a.t(), b, out=c, accumulate=True)
+    report("sgemm split-K accumulate", rel_err(c, c0[:24, :48] + a.t() @ b), 2e-5)
+    # autograd nodes
+    B, Np, dp, q, ncls = 4, 500, 6, 48, 40
+    fc1 = nn.Sequential(nn.Linear(dp, q), nn.ReLU(), nn.Linear(q, q)).to(dev)
+    fcp = nn.Sequential(nn.Linear(3, q), nn.ReLU(), nn.Linear(q, q)).to(dev)
+    head = nn.Linear(q, ncls).to(dev)
+    x = torch.randn(B, Np, dp, device=dev)
+    w = torch.randn(B, ncls, device=dev)
+    params = list(fc1.parameters()) + list(fcp.parameters()) + list(head.parameters())
+    (head((fc1(x) + fcp(x[..., :3])).mean(1)) * w).sum().backward()
+    want = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    f = Fn.PointStemFn.apply(x, x[..., :3].contiguous(), fc1[0].weight, fc1[0].bias, fc1[2].weight, fc1[2].bias,
+                             fcp[0].weight, fcp[0].bias, fcp[2].weight, fcp[2].bias)
+    report("PointStemFn forward", rel_err(f, fc1(x) + fcp(x[..., :3])), 2e-5)
+    (Fn.LinearF32Fn.apply(f.mean(1), head.weight, head.bias) * w).sum().backward()
+    for (n, p), g0 in zip(list(fc1.named_parameters()) + list(fcp.named_parameters()) + list(head.named_parameters()), want):
+        report(f"stem / head grad {n} {tuple(p.shape)}", rel_err(p.grad, g0), 5e-5)
 
 
 def g_attn_fwd():
