@@ -2134,7 +2134,7 @@ bool attn_tc_supported(int DH) { return DH == 48 || DH == 64 || DH == 96 || DH =
 // whose 64-column operand boxes would read a neighbouring head, short sequences where the two-kernel form is faster).
 long long attn_bwd_workspace_bytes(int B, int H, int N, int DH) {
   const char* v = getenv("S3D_FA_SPILL_MIN_N");  // read per call: the parity tests lower it to cover this path at small N
-  const int min_n = v == nullptr ? 2048 : atoi(v);
+  const int min_n = v == nullptr ? 128 : atoi(v);
   if (!attn_tc_supported(DH) || N < min_n || B <= 0 || H <= 0) return 0;
   const long long npad = (N + 63) / 64 * 64;
   const long long one = (2LL * B * H * N * npad + 1023) / 1024 * 1024;  // bytes of one matrix, 1 KiB aligned
