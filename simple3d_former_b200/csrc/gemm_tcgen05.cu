@@ -291,15 +291,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   // work item -> (m tile of this CTA, n tile, k-block range)
   // batch index -> tensor-map batch coordinate of an operand: (bt / inner) * mul + bt % inner (a two-level (batch, head)
-  // offset whose strides are both multiples of the head stride collapses into ONE coordinate of stride head_stride)
-  auto bcoord = [&](int bt, int mul) { return (bt / p.batch_inner) * mul + bt % p.batch_inner; };
+  // offset whose strides are both multiples of the head stride collapses into ONE coordinate of stride head_stride).
+  // Integer divisions cost ~40 issued instructions each and every role decodes every item: the common cases (no batch,
+  // no split-K) take none, the tile split takes one.
+  auto bcoord = [&](int bt, int mul) {
+    if (p.batch_inner == 1) return bt * mul;
+    const int hi = bt / p.batch_inner;
+    return hi * mul + (bt - hi * p.batch_inner);
+  };
   auto decode = [&](int item, int& m0, int& n0, int& kb0, int& kb1, int& split, int& bt) {
-    bt = item / items_per_batch;
-    item -= bt * items_per_batch;
-    split = item % splits;
-    const int t = item / splits;
-    n0 = (t % num_n) * BN;
-    m0 = ((t / num_n) * CL + crank) * BM;
+    bt = 0;
+    if (p.batched && p.batch > 1) {
+      bt = item / items_per_batch;
+      item -= bt * items_per_batch;
+    }
+    int t = item;
+    split = 0;
+    if (splits > 1) {
+      t = item / splits;
+      split = item - t * splits;
+    }
+    const int tq = t / num_n;
+    n0 = (t - tq * num_n) * BN;
+    m0 = (tq * CL + crank) * BM;
     kb0 = split * kb_per_split;
     kb1 = min(num_kb_total, kb0 + kb_per_split);
   };
@@ -453,21 +467,56 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int col0 = half * kColsPerHalf + c;
             const int n = n0 + col0;
             if (n >= p.N) break;  // warp-uniform
-            if (p.epilogue == EPI_GELU && p.aux_out != nullptr) {  // pre-activation (bf16) saved for the backward pass
+            if (p.epilogue == EPI_GELU && p.aux_out != nullptr && !p.out_fp32) {
+              // fc1 of the timm Mlp: the pre-activation (bf16, saved for the backward pass) and GELU(pre) leave through the
+              // same staging tile. The accumulator chunk is read from tensor memory ONCE: the pre-activation is staged
+              // at once, the activation waits as 32 packed registers until the first store has read the tile.
               if (lane == 0) tma_store_wait_read();
               __syncwarp();
-#pragma unroll 1
-              for (int hh = 0; hh < 2; ++hh) {
+              uint32_t act0[16], act1[16];
+              {
                 float f[32];
-                epi_load(p, trow + col0 + 32 * hh, n + 32 * hh, split, f);
-                stage_bf16(srow, lane, hh, f);
+                epi_load(p, trow + col0, n, split, f);
+                stage_bf16(srow, lane, 0, f);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  const float2 g2 = gelu_erf2(make_float2(f[j], f[j + 1]));
+                  act0[j >> 1] = pack_bf16x2(g2.x, g2.y);
+                }
+              }
+              {
+                float f[32];
+                epi_load(p, trow + col0 + 32, n + 32, split, f);
+                stage_bf16(srow, lane, 1, f);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  const float2 g2 = gelu_erf2(make_float2(f[j], f[j + 1]));
+                  act1[j >> 1] = pack_bf16x2(g2.x, g2.y);
+                }
               }
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
                 tma_store_2d(&tma_aux, stage, n, m_box);
                 tma_store_commit();
+                tma_store_wait_read();
               }
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                *reinterpret_cast<uint4*>(srow + ((q ^ (lane & 7)) << 4)) =
+                    make_uint4(act0[q * 4], act0[q * 4 + 1], act0[q * 4 + 2], act0[q * 4 + 3]);
+                *reinterpret_cast<uint4*>(srow + (((4 + q) ^ (lane & 7)) << 4)) =
+                    make_uint4(act1[q * 4], act1[q * 4 + 1], act1[q * 4 + 2], act1[q * 4 + 3]);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (p.batched) tma_store_3d(&tma_d, stage, n, m_box, batch);
+                else tma_store_2d(&tma_d, stage, n, m_box);
+                tma_store_commit();
+              }
+              continue;
             }
             // operand of this 128-byte-wide chunk through the staging tile (full chunks only; tails read directly)
             const bool grad_epi = (p.epilogue == EPI_DGELU || p.epilogue == EPI_DRELU);
