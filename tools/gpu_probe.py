@@ -630,6 +630,13 @@ def g_elementwise():
         else:
             ref = ref.flatten(2).transpose(1, 2).reshape(-1, D)
         report(f"patchify V{V} c{c} p{p} zsum{zsum}", rel_err(out, ref), 2e-3)
+        # the patch matrix itself, bit-exact, for every input dtype the loaders produce
+        cells = vox[:, 0, :p * c, :p * c, :p * c].reshape(B, p, c, p, c, p, c).permute(0, 1, 3, 5, 2, 4, 6)
+        want = (cells.sum(3) if zsum else cells).reshape(-1, K)
+        for dt in (torch.float32, torch.uint8, torch.int32):
+            Pd = L.voxel_patch_gather(vox.to(dt), c, p, kpad, zsum)
+            ok = torch.equal(Pd[:, :K].float(), want) and bool((Pd[:, K:] == 0).all())
+            report(f"patch matrix exact V{V} c{c} zsum{zsum} {str(dt)[6:]}", 0.0 if ok else 1.0, 0)
     # adam
     p0 = torch.randn(10001, device="cuda")
     g = torch.randn(10001, device="cuda")
