@@ -84,5 +84,43 @@ if which in ("all", "dropout"):
     db = dqkv.data_ptr()
     L.attn_bwd(base, base + 2 * E, base + 4 * E, out, rn(B, N, E).bfloat16(), lse, delta, db, db + 2 * E, db + 4 * E, B, H, N,
                dh, qs, os_, dh ** -0.5, drop_seed=seed, drop_site=1, drop_p=0.1)
+if which in ("all", "round2"):
+    # round 2: single-score-pass attention backward (spill stores through rank-4 tensor maps + batched panel GEMMs) at
+    # sizes with partial query tiles / key blocks, both layouts; fp32 strided GEMM; staged voxel gather; LN backward with
+    # the fused column sums
+    os.environ["S3D_FA_SPILL_MIN_N"] = "1"
+    seed = torch.tensor([5], dtype=torch.int32, device=dev)
+    for (B, H, N, dh, seqfirst, p_drop) in [(2, 2, 300, 64, False, 0.1), (3, 4, 130, 192, True, 0.0), (1, 3, 257, 64, False, 0.0),
+                                            (2, 4, 200, 96, True, 0.1), (2, 4, 129, 48, True, 0.0)]:
+        E = H * dh
+        if seqfirst:
+            qkv = (rn(N * B, 3 * E) * 0.5).bfloat16()
+            qs, os_ = (3 * E, dh, B * 3 * E), (E, dh, B * E)
+        else:
+            qkv = (rn(B * N, 3 * E) * 0.5).bfloat16()
+            qs, os_ = (N * 3 * E, dh, 3 * E), (N * E, dh, E)
+        out = torch.empty(B * N, E, device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, H, N, device=dev)
+        base = qkv.data_ptr()
+        kw = dict(drop_seed=seed, drop_site=1, drop_p=p_drop) if p_drop > 0 else {}
+        L.attn_fwd(base, base + 2 * E, base + 4 * E, out, lse, B, H, N, dh, qs, os_, dh ** -0.5, **kw)
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse)
+        db = dqkv.data_ptr()
+        assert L.lib().s3d_attn_bwd_workspace_bytes(B, H, N, dh) > 0
+        L.attn_bwd(base, base + 2 * E, base + 4 * E, out, rn(B * N, E).bfloat16(), lse, delta, db, db + 2 * E, db + 4 * E,
+                   B, H, N, dh, qs, os_, dh ** -0.5, workspace=True, **kw)
+    for (M, N, K) in [(1000, 48, 6), (130, 70, 33), (48, 48, 9000), (1, 48, 5000)]:
+        L.sgemm(rn(M, K), rn(K, N), bias=rn(N))
+        L.sgemm(rn(K, M).t(), rn(N, K).t(), relu=True)
+    L.sgemm(rn(300, 20), rn(20, 50), gate=rn(300, 50))
+    for (B, V, c, p, zsum, dt) in [(2, 30, 6, 5, True, torch.float32), (1, 128, 9, 14, False, torch.uint8),
+                                   (2, 30, 6, 5, False, torch.int32), (1, 33, 4, 8, False, torch.uint8)]:
+        vox = (torch.rand(B, 1, V, V, V, generator=g) < 0.1).to(dt).to(dev)
+        L.voxel_patch_gather(vox, c, p, (c ** 3 + 63) // 64 * 64, zsum)
+    for (T, D) in [(9500, 384), (333, 192)]:
+        x, gam, bet = rn(T, D), rn(D), rn(D)
+        _, _, _, mean, rstd = L.layernorm_fwd(x, gam, bet, 1e-6)
+        L.layernorm_bwd(rn(T, D).bfloat16(), x, gam, mean, rstd, dres=rn(T, D), want_bf16=True, want_dxsum=True)
 torch.cuda.synchronize()
 print("sanitizer targets done:", which)
