@@ -461,8 +461,25 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   p = ffma2(p, t2, bcast2(1.595679461e+00f / 4.0f));
   return fmul2(x, ffma2(p, t, bcast2(0.5f)));
 }
+// t already clamped to [-4.5, 4.5] (the GEMM epilogue clamps the packed bf16 pre-activations with two bf16x2 min / max
+// instructions per pair instead of four fp32 ones)
+__device__ __forceinline__ float2 gelu_erf_grad2_clamped(float2 t);
 __device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {
-  const float2 t = make_float2(fminf(fmaxf(x.x, -4.5f), 4.5f), fminf(fmaxf(x.y, -4.5f), 4.5f));
+  return gelu_erf_grad2_clamped(make_float2(fminf(fmaxf(x.x, -4.5f), 4.5f), fminf(fmaxf(x.y, -4.5f), 4.5f)));
+}
+__device__ __forceinline__ uint32_t clamp_bf16x2_4p5(uint32_t v) {
+  uint32_t d;
+  // 0x4090 = bf16(4.5), 0xC090 = bf16(-4.5)
+  asm("{\n"
+      ".reg .b32 t;\n"
+      "min.bf16x2 t, %1, %2;\n"
+      "max.bf16x2 %0, t, %3;\n"
+      "}\n"
+      : "=r"(d)
+      : "r"(v), "r"(0x40904090u), "r"(0xC090C090u));
+  return d;
+}
+__device__ __forceinline__ float2 gelu_erf_grad2_clamped(float2 t) {
   const float2 u = fmul2(t, bcast2(1.0f / 4.5f));  // coefficients of u^21 would underflow the fp32 range if folded
   const float2 u2 = fmul2(u, u);
   float2 p = bcast2(5.250829664e+01f);

@@ -83,8 +83,13 @@ __device__ __forceinline__ void epi_load(const GemmParams& p, uint32_t taddr, in
     }
     return;
   }
+  if (p.alpha == 1.0f) {  // warp-uniform: the activation-gradient GEMMs carry no scale
 #pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+  }
   if (p.bias != nullptr && split == 0 && n < p.N) {
     if (full) {
 #pragma unroll
@@ -164,6 +169,21 @@ __device__ __forceinline__ void epi_operand_to_stage(uint8_t* stage, const uint8
   __syncwarp();
 }
 __device__ __forceinline__ void epi_act_grad_smem(const GemmParams& p, const uint8_t* srow, int r, int hh, float (&f)[32]) {
+  if (p.epilogue == EPI_DGELU) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 u = *reinterpret_cast<const uint4*>(srow + (((hh * 4 + q) ^ (r & 7)) << 4));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = q * 8 + 2 * i;
+        const float2 g2 = fmul2(make_float2(f[j], f[j + 1]), gelu_erf_grad2_clamped(unpack_bf16x2(clamp_bf16x2_4p5(w[i]))));
+        f[j] = g2.x;
+        f[j + 1] = g2.y;
+      }
+    }
+    return;
+  }
   float a[32];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -172,14 +192,7 @@ __device__ __forceinline__ void epi_act_grad_smem(const GemmParams& p, const uin
     a[q * 8] = a0.x; a[q * 8 + 1] = a0.y; a[q * 8 + 2] = a1.x; a[q * 8 + 3] = a1.y;
     a[q * 8 + 4] = a2.x; a[q * 8 + 5] = a2.y; a[q * 8 + 6] = a3.x; a[q * 8 + 7] = a3.y;
   }
-  if (p.epilogue == EPI_DGELU) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      const float2 g2 = fmul2(make_float2(f[j], f[j + 1]), gelu_erf_grad2(make_float2(a[j], a[j + 1])));
-      f[j] = g2.x;
-      f[j + 1] = g2.y;
-    }
-  } else {
+  {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = a[j] > 0.f ? f[j] : 0.f;
   }
