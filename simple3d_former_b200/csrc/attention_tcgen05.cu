@@ -2022,8 +2022,8 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
     __nv_bfloat16* pd = reinterpret_cast<__nv_bfloat16*>(a.workspace);
     __nv_bfloat16* ds = pd + ((2 * BH * a.N * npad + 1023) / 1024 * 1024) / 2;
     CUtensorMap tpd, tds;
-    if ((rc = make_tmap_bf16_panel(&tpd, pd, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128))) return rc;
-    if ((rc = make_tmap_bf16_panel(&tds, ds, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128))) return rc;
+    if ((rc = make_tmap_bf16_panel(&tpd, pd, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128, 1))) return rc;
+    if ((rc = make_tmap_bf16_panel(&tds, ds, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128, 1))) return rc;
     // S3D_FA_CL=2: CTA pairs sharing the K / V blocks by multicast. Measured equal (10.9 ms both ways on the group_embed
     // shape): this kernel is bound by its element-wise warps and, with the stores on, by ~3.5 TB/s of HBM writes -- not by
     // the L2 -> SM operand traffic the pairs halve. Off by default.

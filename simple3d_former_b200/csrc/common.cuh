@@ -162,6 +162,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
 
 // multicast variants: the box lands at the same smem offset in every CTA of `mask`, each CTA's mbarrier gets the bytes
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -604,7 +612,12 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 // rows): dims {64, rows, panels, batch}, box {64, box_rows, 1, 1}, 128B swizzle. Used for the attention backward's
 // workspace matrices: a 128 x 64 tile store and a 64 x 64 operand load are single contiguous runs in HBM.
 int make_tmap_bf16_panel(CUtensorMap* map, const void* base, uint64_t rows, uint64_t panels, uint64_t batch,
-                         uint32_t box_rows);
+                         uint32_t box_rows, uint32_t box_panels);
+// "chunk view" of a row-major bf16 [rows, mn] matrix (mn a multiple of 64) read as an MN-major UMMA operand: dims
+// {64, rows, mn / 64, batch} with strides {pitch, 128 B, batch pitch}, box {64, 64, box_chunks, 1}: ONE TMA load brings
+// box_chunks 64-wide column chunks of 64 rows, chunk after chunk in shared memory (what the MN-major descriptors expect).
+int make_tmap_bf16_chunks(CUtensorMap* map, const void* base, uint64_t mn, uint64_t rows, uint64_t batch,
+                          uint64_t pitch_elems, uint64_t batch_pitch_elems, uint32_t box_chunks);
 
 int num_sms();
 

@@ -24,6 +24,7 @@ struct GemmParams {
   // batch count and the batch-index -> tensor-map coordinate mapping (bt / batch_inner) * bmul_x + bt % batch_inner of
   // A, B and D / residual (plain batches: batch_inner = 1, bmul = 1); filled by gemm_bf16 from GemmArgs
   int batch, batch_inner, bmul_a, bmul_b, bmul_d;
+  int chunk_a, chunk_b;  // MN-major operand read through a rank-4 chunk view (one TMA load per k-block); set by gemm_bf16
   int a_panel;  // MN-major A stored as 64-column panels [batch][M / 64][K][64] (make_tmap_bf16_panel); needs batched = 1
   // UMMA smem-descriptor byte offsets (defaults: MN-major LBO 8192 / SBO 1024, K-major LBO 16 / SBO 1024);
   // overridable through S3D_DBG_* environment variables for bring-up on new silicon.
