@@ -1016,16 +1016,18 @@ int attn_bwd(const AttnParams& p, int DH, cudaStream_t stream) {
     return S3D_ERR_NULL;
   static const bool tc_enabled = []() { const char* v = getenv("S3D_ATTN_TC"); return v == nullptr || v[0] != '0'; }();
   const bool tc_only = p.drop_seed != nullptr || (DH != 64 && DH != 192 && DH != 256);
-  if (tc_only) return attn_tc_supported(DH) ? attn_bwd_tc(p, DH, stream) : S3D_ERR_UNSUPPORTED;
+  const bool spill = p.workspace != nullptr && attn_bwd_workspace_bytes(p.B, p.H, p.N, DH) > 0 &&
+                     p.workspace_bytes >= attn_bwd_workspace_bytes(p.B, p.H, p.N, DH);
+  // head_dim 256 runs on tcgen05 only in the spill-only form (dQ as a third GEMM), i.e. only with a workspace
+  const bool tc_ok = attn_tc_supported(DH) || (DH == 256 && spill);
+  if (tc_only) return tc_ok ? attn_bwd_tc(p, DH, stream) : S3D_ERR_UNSUPPORTED;
   // Backward on tcgen05: with a workspace (single score pass: one flash kernel that also spills P o mask / dS, then two
   // batched GEMMs) from N = 128 -- measured in the cfg4 / cfg5 steps (N = 257 / 513, dh 64): 1.82 / 1.37 ms per step
   // against 2.12 / 1.62 ms for the mma.sync kernels. Without one it is three kernels (dK, dV, dQ) whose per-CTA prologue
   // (operand tile -> tensor memory, ring start-up) only amortises over long sequences (2.61 / 1.84 ms on the same
   // shapes): from N = 1024. head_dim 256 does not fit the TMEM budget of either form.
   static const int tc_min_n = []() { const char* v = getenv("S3D_ATTN_TC_BWD_MIN_N"); return v == nullptr ? 1024 : atoi(v); }();
-  const bool spill = p.workspace != nullptr && attn_bwd_workspace_bytes(p.B, p.H, p.N, DH) > 0 &&
-                     p.workspace_bytes >= attn_bwd_workspace_bytes(p.B, p.H, p.N, DH);
-  if (tc_enabled && attn_tc_supported(DH) && (p.N >= tc_min_n || spill)) {
+  if (tc_enabled && tc_ok && (spill || (DH != 256 && p.N >= tc_min_n))) {
     const int rc_tc = attn_bwd_tc(p, DH, stream);
     if (rc_tc != S3D_ERR_UNSUPPORTED) return rc_tc;
   }

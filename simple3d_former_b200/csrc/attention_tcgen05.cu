@@ -835,29 +835,29 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[32]) 
 // GEMMs of gemm_bf16_kernel that read them back once at the HBM rate. 5 GEMM units at (or near) the tensor-memory rate
 // instead of 7-8 (dQ 3 + fused dK/dV 4 with shared-memory A operands, or split dK 3 + dV 2), at the price of 8 B of
 // workspace traffic per score element (4 B written here at ~4.5 TB/s while the tensor core works, 4 B read by the GEMMs).
-template <int DH, bool SPILL>
+// MODE 0: recomputing form (dQ only). MODE 1: SPILL (dQ + workspace stores). MODE 2: spill ONLY -- no dQ accumulator, dQ
+// is a third GEMM over the spilled dS (its K-major A operand is a panel as it lies): the variant for head_dim 256 (timm
+// Blocks of deit_base), whose dQ accumulator + Q + dO + S + dP would need 640 TMEM columns.
+template <int DH, int MODE>
 struct FaDqCfg {
+  static constexpr bool kSpill = MODE > 0, kNoDq = MODE == 2;
   static constexpr int kCh = (DH + 63) / 64;
-  static constexpr int kStages = SPILL ? 3 : 4;
+  static constexpr int kStages = kSpill ? (DH > 192 ? 2 : 3) : 4;
   static constexpr int kBlkBytes = 64 * kCh * 128;     // 64-row streamed block (K or V)
   static constexpr int kSBytes = 128 * 64 * 2;         // bf16 dS (and Pd) tile
-  static constexpr int kSmemBytes = 2 * kStages * kBlkBytes + (SPILL ? 4 : 2) * kSBytes + 1024 + 512;
-  static constexpr int kColS = DH, kColQ = DH + 128, kColdO = DH + 128 + DH / 2;
-  static_assert(2 * DH + 128 <= 512, "TMEM budget");
+  static constexpr int kSmemBytes = 2 * kStages * kBlkBytes + (kSpill ? 4 : 2) * kSBytes + 1024 + 512;
+  static constexpr int kColS = kNoDq ? 0 : DH, kColQ = kColS + 128, kColdO = kColQ + DH / 2;
+  static_assert(kColdO + DH / 2 <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-// CL = 2: the CTAs of two adjacent query tiles form a cluster and share every K / V block -- each loads half of its rows
-// and TMA-multicasts them into both shared memories (tma_kv64's box is then 32 rows), ring slots are released by a
-// multicast tcgen05.commit once BOTH CTAs' MMAs have consumed them. One 128-row tile re-reads 48 KB of K / V per 64 keys:
-// 55 GB of L2 -> SM traffic on the group_embed shape, which (with the 38 GB of spill stores) ran into the ~8.7 TB/s the
-// L2 delivers; sharing halves the load side.
-template <int DH, bool DROP, bool SPILL, int CL>
-__global__ void __launch_bounds__(kFaBwdThreads + (SPILL ? 32 : 0), 1)
+template <int DH, bool DROP, int MODE, int CL>
+__global__ void __launch_bounds__(kFaBwdThreads + (MODE > 0 ? 32 : 0), 1)
 fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __grid_constant__ CUtensorMap tma_pd,
                     const __grid_constant__ CUtensorMap tma_ds, const __nv_bfloat16* __restrict__ qbase,
                     const __nv_bfloat16* __restrict__ dobase, const FaBwdParams p) {
-  using Cfg = FaDqCfg<DH, SPILL>;
+  using Cfg = FaDqCfg<DH, MODE>;
+  constexpr bool SPILL = Cfg::kSpill, NODQ = Cfg::kNoDq;
   constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -898,7 +898,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __grid_c
     mbar_init(dq_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ds_full[i], kEwWarps);
-      mbar_init(&ds_free[i], SPILL ? 2 : 1);  // dQ MMAs retired (+ the tile's TMA stores have read it)
+      mbar_init(&ds_free[i], (SPILL && !NODQ) ? 2 : 1);  // dQ MMAs retired and / or the tile's TMA stores have read it
     }
     fence_barrier_init();
     if (SPILL) {
@@ -980,11 +980,15 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __grid_c
         for (int kk = 0; kk < DH / 16; ++kk)  // dP = dO V^T
           umma_f16_ts(t_dp, t_do + kk * 8, ((uint64_t)hi << 32) | (bv + kstep_off<64>(kk)), idesc_s, kk != 0);
         umma_commit(sp_full);
+        if (NODQ) {  // no dQ MMAs will read this K / V block: the slot is free once S / dP retire
+          if (CL > 1) umma_commit_mc(&kv_empty[st], kMcMask);
+          else umma_commit(&kv_empty[st]);
+        }
       }
       __syncwarp();
-      if (j > 0) issue_dq(j - 1);
+      if (!NODQ && j > 0) issue_dq(j - 1);
     }
-    issue_dq(nkv - 1);
+    if (!NODQ) issue_dq(nkv - 1);
   } else if (SPILL && warp == 2 + kEwWarps) {
     // ---- store warp: one TMA store per finished Pd / dS tile (the element-wise warps fenced their writes for the async
     // proxy before arriving on ds_full); the tile is handed back once the store has read it AND the dQ MMAs retired
@@ -1101,6 +1105,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __grid_c
         for (int i = 0; i < kEwCols / 2; ++i) z[i] = drop_word(y0 + (uint32_t)i * kDropColMul);
       }
     }
+    if constexpr (!NODQ) {  // (MODE 2: dQ comes from the third GEMM)
     mbar_wait(dq_full, 0);
     tc_fence_after();
     __nv_bfloat16* orow = p.dq + (long long)b * p.qkv_bs + (long long)h * p.qkv_hs + (long long)row * p.qkv_rs;
@@ -1121,6 +1126,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tma_kv64, const __grid_c
           *reinterpret_cast<uint4*>(orow + cc + i) = wv;
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -1940,27 +1946,31 @@ __global__ void __launch_bounds__(256) fa_delta_kernel(const __nv_bfloat16* __re
   if (lane == 0) delta[warp] = s;
 }
 
-template <int DH, bool DROP>
-static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
-  using Cfg = FaBwdCfg<DH>;
+// Layout parse (timm [B, N, 3, H, dh] or sequence-first [S, Nb, 3E]), parameter block, alignment checks and the delta
+// kernel: shared by every form of the backward.
+struct FaBwdSetup {
+  FaBwdParams p;
+  long long rows_total, width, o_width;
+};
+static int fa_bwd_setup(const AttnParams& a, int DH, FaBwdSetup& st, cudaStream_t stream) {
   const long long E = (long long)a.H * DH;
   if (a.k - a.q != E || a.v - a.q != 2 * E || a.qkv_hs != DH || a.o_hs != DH) return S3D_ERR_UNSUPPORTED;
   if (a.dk - a.dq != E || a.dv - a.dq != 2 * E) return S3D_ERR_UNSUPPORTED;
-  FaBwdParams p{};
-  long long rows_total, width, o_width;
+  FaBwdParams& p = st.p;
+  p = FaBwdParams{};
   if (a.qkv_rs == 3 * E && (a.qkv_bs == (long long)a.N * 3 * E || a.B == 1) && a.o_rs == E &&
       (a.o_bs == (long long)a.N * E || a.B == 1)) {  // timm
-    rows_total = (long long)a.B * a.N;
-    width = 3 * E;
-    o_width = E;
+    st.rows_total = (long long)a.B * a.N;
+    st.width = 3 * E;
+    st.o_width = E;
     p.row_bs = a.N;
     p.col_bs = 0;
     p.o_row_bs = a.N;
     p.o_col_bs = 0;
   } else if (a.qkv_bs == 3 * E && a.qkv_rs == (long long)a.B * 3 * E && a.o_bs == E && a.o_rs == (long long)a.B * E) {
-    rows_total = a.N;  // sequence-first
-    width = (long long)a.B * 3 * E;
-    o_width = (long long)a.B * E;
+    st.rows_total = a.N;  // sequence-first
+    st.width = (long long)a.B * 3 * E;
+    st.o_width = (long long)a.B * E;
     p.row_bs = 0;
     p.col_bs = 3 * E;
     p.o_row_bs = 0;
@@ -1969,11 +1979,9 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
     return S3D_ERR_UNSUPPORTED;
   }
   if (a.B > 65535 || a.H > 65535) return S3D_ERR_BAD_SHAPE;
-  CUtensorMap t128, t64, d64;
-  int rc;
-  if ((rc = make_tmap_bf16_2d(&t128, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&t64, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&d64, a.dout, (uint64_t)o_width, (uint64_t)rows_total, (uint64_t)a.o_rs, 64, 64))) return rc;
+  if ((a.qkv_rs % 8) || (a.qkv_hs % 8) || (a.qkv_bs % 8) || (a.o_rs % 8) || (reinterpret_cast<uintptr_t>(a.q) & 15) ||
+      (reinterpret_cast<uintptr_t>(a.dout) & 15))
+    return S3D_ERR_ALIGNMENT;  // 16-byte row loads of Q / dO
   p.dq = a.dq;
   p.dk = a.dk;
   p.dv = a.dv;
@@ -1992,111 +2000,144 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
   p.drop_site = a.drop_site;
   p.drop_thresh14 = a.drop_thresh14;
   p.drop_scale = a.drop_scale;
-  { const char* v = getenv("S3D_FA_DBG"); p.dbg = v == nullptr ? 0 : atoi(v); }
-  {
-    const long long rows = (long long)a.B * a.H * a.N;
-    fa_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a.o, a.dout, a.delta, a.B, a.H, a.N, DH, a.o_bs, a.o_hs, a.o_rs);
-    S3D_LAUNCH_OK();
-  }
   p.o_rs_elems = a.o_rs;
-  auto kq = fa_bwd_dq_tc_kernel<DH, DROP, false, 1>;
+  { const char* v = getenv("S3D_FA_DBG"); p.dbg = v == nullptr ? 0 : atoi(v); }
+  const long long rows = (long long)a.B * a.H * a.N;
+  fa_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a.o, a.dout, a.delta, a.B, a.H, a.N, DH, a.o_bs, a.o_hs, a.o_rs);
+  S3D_LAUNCH_OK();
+  return S3D_OK;
+}
+
+static bool fa_spill_applies(const AttnParams& a, int DH) {
+  const long long need = attn_bwd_workspace_bytes(a.B, a.H, a.N, DH);
+  return a.workspace != nullptr && need > 0 && a.workspace_bytes >= need && (a.qkv_bs % DH) == 0 && (a.o_bs % DH) == 0;
+}
+
+// ---- single score pass: the dQ kernel spills Pd / dS (bf16 64-key panels) into the caller's workspace, dV / dK (and, in
+// MODE 2, dQ) are batched GEMMs over them. Measured on the group_embed shape: DESIGN.md 4.4, profiles/ncu_table.json.
+template <int DH, bool DROP, int MODE>
+static int fa_bwd_spill_launch(const AttnParams& a, const FaBwdSetup& st, cudaStream_t stream) {
+  using QCfg = FaDqCfg<DH, MODE>;
+  const FaBwdParams& p = st.p;
+  int rc;
+  CUtensorMap t64;
+  if ((rc = make_tmap_bf16_2d(&t64, a.q, (uint64_t)st.width, (uint64_t)st.rows_total, (uint64_t)a.qkv_rs, 64, 64))) return rc;
+  dim3 grid((a.N + 127) / 128, a.H, a.B);
+  const long long npad = (a.N + 63) / 64 * 64;
+  const long long BH = (long long)a.B * a.H;
+  // workspace layout: 64-key panels [B*H][Npad / 64][N queries][64 keys] -- a 128 x 64 tile store and a GEMM operand box
+  // are contiguous runs in HBM (row-major [N, Npad] matrices wrote 128-byte pieces 25 KB apart: 3 TB/s)
+  __nv_bfloat16* pd = reinterpret_cast<__nv_bfloat16*>(a.workspace);
+  __nv_bfloat16* ds = pd + ((2 * BH * a.N * npad + 1023) / 1024 * 1024) / 2;
+  CUtensorMap tpd, tds;
+  if ((rc = make_tmap_bf16_panel(&tpd, pd, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128, 1))) return rc;
+  if ((rc = make_tmap_bf16_panel(&tds, ds, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128, 1))) return rc;
+  // S3D_FA_CL=2: CTA pairs sharing the K / V blocks by multicast. Measured equal (10.9 ms both ways on the group_embed
+  // shape): this kernel is bound by its element-wise warps and, with the stores on, by ~3.5 TB/s of HBM writes -- not by
+  // the L2 -> SM operand traffic the pairs halve. Off by default.
+  static const bool no_cluster = []() { const char* v = getenv("S3D_FA_CL"); return v == nullptr || v[0] != '2'; }();
+  if (no_cluster) {
+    auto kqs = fa_bwd_dq_tc_kernel<DH, DROP, MODE, 1>;
+    static bool attr3_set = false;
+    if (!attr3_set) {
+      S3D_CUDA_OK(cudaFuncSetAttribute(kqs, cudaFuncAttributeMaxDynamicSharedMemorySize, QCfg::kSmemBytes));
+      attr3_set = true;
+    }
+    kqs<<<grid, kFaBwdThreads + 32, QCfg::kSmemBytes, stream>>>(t64, tpd, tds, a.q, a.dout, p);
+    S3D_LAUNCH_OK();
+  } else {
+    auto kqs = fa_bwd_dq_tc_kernel<DH, DROP, MODE, 2>;
+    static bool attr4_set = false;
+    if (!attr4_set) {
+      S3D_CUDA_OK(cudaFuncSetAttribute(kqs, cudaFuncAttributeMaxDynamicSharedMemorySize, QCfg::kSmemBytes));
+      attr4_set = true;
+    }
+    CUtensorMap t32;  // half-chunk boxes: every CTA of a pair loads 32 of the 64 rows and multicasts them
+    if ((rc = make_tmap_bf16_2d(&t32, a.q, (uint64_t)st.width, (uint64_t)st.rows_total, (uint64_t)a.qkv_rs, 64, 32))) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((grid.x + 1) / 2 * 2, grid.y, grid.z);  // an odd last tile gets an idle partner (all rows >= N)
+    cfg.blockDim = dim3(kFaBwdThreads + 32, 1, 1);
+    cfg.dynamicSmemBytes = QCfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    S3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kqs, t32, tpd, tds, a.q, a.dout, p));
+  }
+  // dV[b,h] = Pd[b,h]^T dO[b,h] / (1 - p);  dK[b,h] = dS[b,h]^T Q[b,h] * scale: A = workspace matrix read MN-major
+  // (m = key contiguous), B = dO / Q read MN-major (n = head channel contiguous), contraction over the queries.
+  // A (batch, head) slice of qkv / dout sits at element offset b * batch_stride + h * DH = (b * batch_stride / DH + h) * DH.
+  GemmArgs g{};
+  g.a_mn = 1;
+  g.b_mn = 1;
+  g.batch = (int)BH;
+  g.batch_stride_b = DH;
+  g.batch_inner = a.H;
+  g.bmul_a = a.H;
+  g.p.M = a.N;
+  g.p.N = DH;
+  g.p.K = a.N;
+  g.p.out_fp32 = 0;
+  g.p.epilogue = EPI_NONE;
+  g.p.batched = 1;
+  g.p.a_panel = 1;
+  g.p.batch_stride_d = DH;
+  g.p.ldd = a.qkv_rs;
+  g.bmul_d = (int)(a.qkv_bs / DH);
+  // dV
+  g.A = pd;
+  g.B = a.dout;
+  g.ldb = a.o_rs;
+  g.bmul_b = (int)(a.o_bs / DH);
+  g.p.D = a.dv;
+  g.p.alpha = DROP ? a.drop_scale : 1.0f;
+  if ((rc = gemm_bf16(g, stream))) return rc;
+  // dK
+  g.A = ds;
+  g.B = a.q;
+  g.ldb = a.qkv_rs;
+  g.bmul_b = (int)(a.qkv_bs / DH);
+  g.p.D = a.dk;
+  g.p.alpha = a.scale;
+  if ((rc = gemm_bf16(g, stream))) return rc;
+  if (MODE == 2) {
+    // dQ[b,h] = dS[b,h] K[b,h] * scale: A = dS read K-major straight from its panels (panel = 64-key k-block), B = K read
+    // MN-major, contraction over the keys (keys >= N hold zeros in dS and are zero-filled in K by the tensor map)
+    g.a_mn = 0;
+    g.p.a_panel = 2;
+    g.B = a.k;
+    g.p.D = a.dq;
+    return gemm_bf16(g, stream);
+  }
+  return S3D_OK;
+}
+
+template <int DH, bool DROP>
+static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
+  using Cfg = FaBwdCfg<DH>;
+  FaBwdSetup st;
+  int rc;
+  if ((rc = fa_bwd_setup(a, DH, st, stream))) return rc;
+  if (fa_spill_applies(a, DH)) return fa_bwd_spill_launch<DH, DROP, 1>(a, st, stream);
+  const FaBwdParams& p = st.p;
+  const long long rows_total = st.rows_total, width = st.width, o_width = st.o_width;
+  CUtensorMap t128, t64, d64;
+  if ((rc = make_tmap_bf16_2d(&t128, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&t64, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&d64, a.dout, (uint64_t)o_width, (uint64_t)rows_total, (uint64_t)a.o_rs, 64, 64))) return rc;
+  auto kq = fa_bwd_dq_tc_kernel<DH, DROP, 0, 1>;
   auto kkv = fa_bwd_dkv_tc_kernel<DH, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
-    S3D_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDqCfg<DH, false>::kSmemBytes));
+    S3D_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDqCfg<DH, 0>::kSmemBytes));
     S3D_CUDA_OK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  if ((a.qkv_rs % 8) || (a.qkv_hs % 8) || (a.qkv_bs % 8) || (a.o_rs % 8) || (reinterpret_cast<uintptr_t>(a.q) & 15) ||
-      (reinterpret_cast<uintptr_t>(a.dout) & 15))
-    return S3D_ERR_ALIGNMENT;  // 16-byte row loads of Q / dO
   dim3 grid((a.N + 127) / 128, a.H, a.B);
-  // ---- single score pass: dQ kernel spills Pd / dS (bf16 [B*H, N, Npad]) into the caller's workspace, dV / dK are GEMMs.
-  // Measured on the group_embed shape (B = 15, H = 4, S = 12544, dh = 192, p = 0.1): see profiles/ and DESIGN.md 4.
-  if (a.workspace != nullptr && a.workspace_bytes >= attn_bwd_workspace_bytes(a.B, a.H, a.N, DH) &&
-      attn_bwd_workspace_bytes(a.B, a.H, a.N, DH) > 0 && (a.qkv_bs % DH) == 0 && (a.o_bs % DH) == 0) {
-    const long long npad = (a.N + 63) / 64 * 64;
-    const long long BH = (long long)a.B * a.H;
-    // workspace layout: 64-key panels [B*H][Npad / 64][N queries][64 keys] -- a 128 x 64 tile store and a GEMM operand box
-    // are contiguous runs in HBM (row-major [N, Npad] matrices wrote 128-byte pieces 25 KB apart: 3 TB/s)
-    __nv_bfloat16* pd = reinterpret_cast<__nv_bfloat16*>(a.workspace);
-    __nv_bfloat16* ds = pd + ((2 * BH * a.N * npad + 1023) / 1024 * 1024) / 2;
-    CUtensorMap tpd, tds;
-    if ((rc = make_tmap_bf16_panel(&tpd, pd, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128, 1))) return rc;
-    if ((rc = make_tmap_bf16_panel(&tds, ds, (uint64_t)a.N, (uint64_t)(npad / 64), (uint64_t)BH, 128, 1))) return rc;
-    // S3D_FA_CL=2: CTA pairs sharing the K / V blocks by multicast. Measured equal (10.9 ms both ways on the group_embed
-    // shape): this kernel is bound by its element-wise warps and, with the stores on, by ~3.5 TB/s of HBM writes -- not by
-    // the L2 -> SM operand traffic the pairs halve. Off by default.
-    static const bool no_cluster = []() { const char* v = getenv("S3D_FA_CL"); return v == nullptr || v[0] != '2'; }();
-    if (no_cluster) {
-      auto kqs = fa_bwd_dq_tc_kernel<DH, DROP, true, 1>;
-      static bool attr3_set = false;
-      if (!attr3_set) {
-        S3D_CUDA_OK(cudaFuncSetAttribute(kqs, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDqCfg<DH, true>::kSmemBytes));
-        attr3_set = true;
-      }
-      kqs<<<grid, kFaBwdThreads + 32, FaDqCfg<DH, true>::kSmemBytes, stream>>>(t64, tpd, tds, a.q, a.dout, p);
-      S3D_LAUNCH_OK();
-    } else {
-      auto kqs = fa_bwd_dq_tc_kernel<DH, DROP, true, 2>;
-      static bool attr4_set = false;
-      if (!attr4_set) {
-        S3D_CUDA_OK(cudaFuncSetAttribute(kqs, cudaFuncAttributeMaxDynamicSharedMemorySize, FaDqCfg<DH, true>::kSmemBytes));
-        attr4_set = true;
-      }
-      CUtensorMap t32;  // half-chunk boxes: every CTA of a pair loads 32 of the 64 rows and multicasts them
-      if ((rc = make_tmap_bf16_2d(&t32, a.q, (uint64_t)width, (uint64_t)rows_total, (uint64_t)a.qkv_rs, 64, 32))) return rc;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((grid.x + 1) / 2 * 2, grid.y, grid.z);  // an odd last tile gets an idle partner (all rows >= N)
-      cfg.blockDim = dim3(kFaBwdThreads + 32, 1, 1);
-      cfg.dynamicSmemBytes = FaDqCfg<DH, true>::kSmemBytes;
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      S3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kqs, t32, tpd, tds, a.q, a.dout, p));
-    }
-    // dV[b,h] = Pd[b,h]^T dO[b,h] / (1 - p);  dK[b,h] = dS[b,h]^T Q[b,h] * scale: A = workspace matrix read MN-major
-    // (m = key contiguous), B = dO / Q read MN-major (n = head channel contiguous), contraction over the queries.
-    // A (batch, head) slice of qkv / dout sits at element offset b * batch_stride + h * DH = (b * batch_stride / DH + h) * DH.
-    GemmArgs g{};
-    g.a_mn = 1;
-    g.b_mn = 1;
-    g.batch = (int)BH;
-    g.batch_stride_b = DH;
-    g.batch_inner = a.H;
-    g.bmul_a = a.H;
-    g.p.M = a.N;
-    g.p.N = DH;
-    g.p.K = a.N;
-    g.p.out_fp32 = 0;
-    g.p.epilogue = EPI_NONE;
-    g.p.batched = 1;
-    g.p.a_panel = 1;
-    g.p.batch_stride_d = DH;
-    g.p.ldd = a.qkv_rs;
-    g.bmul_d = (int)(a.qkv_bs / DH);
-    // dV
-    g.A = pd;
-    g.B = a.dout;
-    g.ldb = a.o_rs;
-    g.bmul_b = (int)(a.o_bs / DH);
-    g.p.D = a.dv;
-    g.p.alpha = DROP ? a.drop_scale : 1.0f;
-    if ((rc = gemm_bf16(g, stream))) return rc;
-    // dK
-    g.A = ds;
-    g.B = a.q;
-    g.ldb = a.qkv_rs;
-    g.bmul_b = (int)(a.qkv_bs / DH);
-    g.p.D = a.dk;
-    g.p.alpha = a.scale;
-    return gemm_bf16(g, stream);
-  }
   // Split dK / dV kernels (all A operands in tensor memory) or the fused dK/dV kernel (K, V tiles in shared memory)?
   // Measured on the group_embed shape (B = 15, H = 4, S = 12544, dh = 192), dK + dV:
   //     without dropout   split 7.8 + 5.8 = 13.6 ms (tensor pipe 71 % / 62 %)    fused 15.4 ms (41 %)
@@ -2123,7 +2164,7 @@ static int fa_bwd_launch(const AttnParams& a, cudaStream_t stream) {
     kdv<<<grid, kFaBwdThreads, FaDvCfg<DH>::kSmemBytes, stream>>>(t64, d64, a.k, p);
     S3D_LAUNCH_OK();
   }
-  kq<<<grid, kFaBwdThreads, FaDqCfg<DH, false>::kSmemBytes, stream>>>(t64, t64, t64, a.q, a.dout, p);
+  kq<<<grid, kFaBwdThreads, FaDqCfg<DH, 0>::kSmemBytes, stream>>>(t64, t64, t64, a.q, a.dout, p);
   S3D_LAUNCH_OK();
   return S3D_OK;
 }
@@ -2135,16 +2176,27 @@ bool attn_tc_supported(int DH) { return DH == 48 || DH == 64 || DH == 96 || DH =
 long long attn_bwd_workspace_bytes(int B, int H, int N, int DH) {
   const char* v = getenv("S3D_FA_SPILL_MIN_N");  // read per call: the parity tests lower it to cover this path at small N
   const int min_n = v == nullptr ? 128 : atoi(v);
-  if (!attn_tc_supported(DH) || N < min_n || B <= 0 || H <= 0) return 0;
+  if (!attn_tc_fwd_supported(DH) || N < min_n || B <= 0 || H <= 0) return 0;
   const long long npad = (N + 63) / 64 * 64;
   const long long one = (2LL * B * H * N * npad + 1023) / 1024 * 1024;  // bytes of one matrix, 1 KiB aligned
   return 2 * one;
 }
 bool attn_tc_fwd_supported(int DH) { return attn_tc_supported(DH) || DH == 256; }
 
+// head_dim 256 (timm Blocks of deit_base, N = 197): only the spill-ONLY form fits tensor memory; without a workspace the
+// caller falls back to the mma.sync kernels
+template <bool DROP>
+static int fa_bwd_256(const AttnParams& a, cudaStream_t stream) {
+  if (!fa_spill_applies(a, 256)) return S3D_ERR_UNSUPPORTED;
+  FaBwdSetup st;
+  if (int rc = fa_bwd_setup(a, 256, st, stream)) return rc;
+  return fa_bwd_spill_launch<256, DROP, 2>(a, st, stream);
+}
+
 template <bool DROP>
 static int fa_bwd_dispatch(const AttnParams& p, int DH, cudaStream_t stream) {
   switch (DH) {
+    case 256: return fa_bwd_256<DROP>(p, stream);
     case 192: return fa_bwd_launch<192, DROP>(p, stream);
     case 96: return fa_bwd_launch<96, DROP>(p, stream);
     case 64: return fa_bwd_launch<64, DROP>(p, stream);

@@ -338,10 +338,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // 8 KB boxes per k-block and ran 10 % slower when every load picked its tensor-map rank at run time (0.675 against
     // 0.613 ms on M = 3072, N = 768, K = 188160). All operand maps are rank 3 (batch extent 1 when there is none); the
     // panel layout of the attention workspace (rank 4) is a compile-time variant of the whole loop.
-    auto produce = [&](auto a_tag, auto b_tag) {
+    auto produce = [&](auto a_tag, auto b_tag, auto pk_tag) {
       // MN-major operands through a rank-4 "chunk view" (make_tmap_bf16_chunks / _panel): ONE load brings all the
       // 64-wide chunks of the tile instead of one 8 KB box per chunk
       constexpr bool kChunkA = decltype(a_tag)::value, kChunkB = decltype(b_tag)::value;
+      constexpr bool kPanelK = decltype(pk_tag)::value;  // K-major A read from 64-column panels (panel index = k-block)
       int stage = 0;
       uint32_t phase = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters) {
@@ -362,6 +363,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
               for (int i = 0; i < BM / 64; ++i) tma_load_3d(sa + i * 8192, &tma_a, &full_bar[stage], m0 + 64 * i, k0, batch);
             }
+          } else if (kPanelK) {
+            tma_load_4d(sa, &tma_a, &full_bar[stage], 0, m0, kb, batch);
           } else {
             tma_load_3d(sa, &tma_a, &full_bar[stage], k0, m0, batch);
           }
@@ -392,10 +395,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     };
     if (lane == 0) {
       // chunk views need whole 64-wide chunks (M / N multiples of 64); both flags are set together by the host
-      if (A_MN && B_MN && p.chunk_a && p.chunk_b) produce(std::true_type{}, std::true_type{});
-      else if (A_MN && p.chunk_a) produce(std::true_type{}, std::false_type{});
-      else if (B_MN && p.chunk_b) produce(std::false_type{}, std::true_type{});
-      else produce(std::false_type{}, std::false_type{});
+      using T = std::true_type;
+      using F = std::false_type;
+      if (!A_MN && p.a_panel == 2) {
+        if (B_MN && p.chunk_b) produce(F{}, T{}, T{});
+        else produce(F{}, F{}, T{});
+      } else if (A_MN && B_MN && p.chunk_a && p.chunk_b) produce(T{}, T{}, F{});
+      else if (A_MN && p.chunk_a) produce(T{}, F{}, F{});
+      else if (B_MN && p.chunk_b) produce(F{}, T{}, F{});
+      else produce(F{}, F{}, F{});
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -878,13 +886,14 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   constexpr int kBBoxRows = BN / CL;
   // extent of an operand's batch dimension under the coordinate mapping of GemmParams
   auto bdim = [&](int mul) { return (uint64_t)((g.batch / p.batch_inner - 1) * mul + p.batch_inner); };
-  if (p.a_panel && !A_MN) return S3D_ERR_UNSUPPORTED;
+  if ((p.a_panel == 1 && !A_MN) || (p.a_panel == 2 && A_MN)) return S3D_ERR_UNSUPPORTED;
   {
     // rank-3 maps always (see the producer): without batches the third extent is 1 and its stride is the matrix size
     const uint64_t ba = g.batch > 1 ? bdim(p.bmul_a) : 1, bb = g.batch > 1 ? bdim(p.bmul_b) : 1;
     const uint64_t sa = g.batch > 1 ? (uint64_t)g.batch_stride_a : (uint64_t)g.lda * (uint64_t)(A_MN ? p.K : p.M);
     const uint64_t sb = g.batch > 1 ? (uint64_t)g.batch_stride_b : (uint64_t)g.ldb * (uint64_t)(B_MN ? p.K : p.N);
     if (A_MN && p.a_panel) rc = make_tmap_bf16_panel(&ta, g.A, p.K, (uint64_t)(p.M + 63) / 64, ba, 64, BM / 64);
+    else if (p.a_panel == 2) rc = make_tmap_bf16_panel(&ta, g.A, p.M, (uint64_t)(p.K + 63) / 64, ba, BM, 1);
     else if (A_MN && p.chunk_a) rc = make_tmap_bf16_chunks(&ta, g.A, p.M, p.K, ba, g.lda, sa, BM / 64);
     else if (A_MN) rc = make_tmap_bf16_3d(&ta, g.A, p.M, p.K, ba, g.lda, sa, 64, 64);
     else rc = make_tmap_bf16_3d(&ta, g.A, p.K, p.M, ba, g.lda, sa, 64, BM);
@@ -986,7 +995,7 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   p.bmul_d = g.batch_inner > 0 ? g.bmul_d : 1;
   if (p.a_panel) p.batched = 1;  // panel operands are addressed through rank-4 / rank-3 maps even for a single batch
   static const bool no_chunks = getenv("S3D_GEMM_NO_CHUNK_VIEW") != nullptr;
-  p.chunk_a = (g.a_mn && (p.a_panel || (!no_chunks && p.M % 64 == 0))) ? 1 : 0;
+  p.chunk_a = (g.a_mn && (p.a_panel == 1 || (!no_chunks && p.M % 64 == 0))) ? 1 : 0;
   p.chunk_b = (g.b_mn && !no_chunks && p.N % 64 == 0) ? 1 : 0;
   if (p.batch > 1 && !p.batched) return S3D_ERR_BAD_SHAPE;
   if (g.A == nullptr || g.B == nullptr || p.D == nullptr) return S3D_ERR_NULL;

@@ -25,7 +25,8 @@ struct GemmParams {
   // A, B and D / residual (plain batches: batch_inner = 1, bmul = 1); filled by gemm_bf16 from GemmArgs
   int batch, batch_inner, bmul_a, bmul_b, bmul_d;
   int chunk_a, chunk_b;  // MN-major operand read through a rank-4 chunk view (one TMA load per k-block); set by gemm_bf16
-  int a_panel;  // MN-major A stored as 64-column panels [batch][M / 64][K][64] (make_tmap_bf16_panel); needs batched = 1
+  int a_panel;  // A stored as 64-column panels (make_tmap_bf16_panel), addressed through rank-4 maps. 1: MN-major A, panels
+                // [batch][M / 64][K][64]; 2: K-major A, panels [batch][K / 64][M][64] (the panel index is the k-block)
   // UMMA smem-descriptor byte offsets (defaults: MN-major LBO 8192 / SBO 1024, K-major LBO 16 / SBO 1024);
   // overridable through S3D_DBG_* environment variables for bring-up on new silicon.
   unsigned mn_lbo, mn_sbo, k_lbo, k_sbo;

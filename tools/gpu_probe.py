@@ -442,7 +442,9 @@ def g_attn_spill():
                                               (1, 1088, 4, 192, "seqfirst", 0.0), (2, 1100, 3, 64, "timm", 0.0),
                                               (3, 257, 3, 64, "timm", 0.1), (2, 700, 4, 96, "seqfirst", 0.0),
                                               (2, 600, 4, 48, "seqfirst", 0.1), (1, 130, 1, 64, "timm", 0.25),
-                                              (3, 640, 2, 192, "timm", 0.1), (2, 2176, 4, 192, "seqfirst", 0.1)]:
+                                              (3, 640, 2, 192, "timm", 0.1), (2, 2176, 4, 192, "seqfirst", 0.1),
+                                              (4, 197, 3, 256, "timm", 0.0), (2, 300, 2, 256, "seqfirst", 0.0),
+                                              (1, 128, 1, 256, "timm", 0.0)]:
             assert L.lib().s3d_attn_bwd_workspace_bytes(B, H, N, dh) > 0
             qkv, q, k, v, qs, os_, out, perm = _make_qkv(B, N, H, dh, layout)
             lse = torch.empty(B, H, N, device="cuda")
@@ -499,6 +501,19 @@ def g_attn_spill():
         torch.cuda.synchronize()
         return s.elapsed_time(e) / reps
 
+    Bs, Ns, Hs, ds = 64, 197, 3, 256  # stage 2 of cfg3: head_dim 256 -> spill-only form (dQ as a third GEMM) vs mma.sync
+    qkv2, q2, k2, v2, qs2, os2, out2, _ = _make_qkv(Bs, Ns, Hs, ds, "timm")
+    lse2 = torch.empty(Bs, Hs, Ns, device="cuda")
+    delta2 = torch.empty(Bs, Hs, Ns, device="cuda")
+    do2 = torch.randn_like(out2.float()).bfloat16()
+    dqkv2 = torch.zeros_like(qkv2)
+    L.attn_fwd(q2, k2, v2, out2, lse2, Bs, Hs, Ns, ds, qs2, os2, ds ** -0.5)
+    for ws in (True, False):
+        ms = timeit(lambda: L.attn_bwd(q2.data_ptr(), k2.data_ptr(), v2.data_ptr(), out2, do2, lse2, delta2,
+                                       dqkv2.select(2, 0).data_ptr(), dqkv2.select(2, 1).data_ptr(),
+                                       dqkv2.select(2, 2).data_ptr(), Bs, Hs, Ns, ds, qs2, os2, ds ** -0.5, workspace=ws), reps=20)
+        print(f"  [PERF] attn bwd timm B{Bs} N{Ns} H{Hs} dh{ds} {'tcgen05 spill-only + 3 GEMMs' if ws else 'mma.sync'}: "
+              f"{ms * 1e3:.1f} us  {10.0 * Bs * Hs * Ns * Ns * ds / ms / 1e9:.1f} TFLOP/s", flush=True)
     for p_drop in (0.0, 0.1):
         kw = dict(drop_seed=seed, drop_site=1, drop_p=p_drop) if p_drop > 0 else {}
         L.attn_fwd(q, k, v, out, lse, B, H, N, dh, qs, os_, dh ** -0.5, **kw)
