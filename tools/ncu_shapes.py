@@ -87,16 +87,16 @@ def attn(B, N, H, dh, seqfirst, drop):
     kw = dict(drop_seed=seed, drop_site=1, drop_p=0.1) if drop else {}
     L.attn_fwd(b, b + 2 * E, b + 4 * E, o, lse, B, H, N, dh, qs, os_, dh ** -0.5, **kw)
     tc_f = drop or N >= 64          # forward: tcgen05 for every sequence of at least one 64-key block
-    # backward: single score pass (flash dQ kernel that spills P o mask / dS + two batched GEMMs) from N = 128;
-    # head_dim 256 does not fit the TMEM budget and the 15-token sequences keep the warp-per-sequence kernel
-    tc = dh != 256 and (drop or N >= 128)
+    # backward: single score pass (flash dQ kernel that spills P o mask / dS + two batched GEMMs; head_dim 256: spill-only
+    # kernel + three GEMMs) from N = 128; the 15-token sequences keep the warp-per-sequence kernel
+    tc = drop or N >= 128
     order.append((f"s3d_attn_fwd[B={B},H={H},N={N},dh={dh},drop={int(drop)}]", ["fa_fwd" if tc_f else "attn_fwd"]))
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
     db = dqkv.data_ptr()
     L.attn_bwd(b, b + 2 * E, b + 4 * E, o, rn(B * N, E), lse, delta, db, db + 2 * E, db + 4 * E, B, H, N, dh, qs, os_,
                dh ** -0.5, **kw)
-    pats = ["fa_delta", "fa_bwd_dq", "gemm_bf16_kernel", "gemm_bf16_kernel"] if tc else (
+    pats = (["fa_delta", "fa_bwd_dq", "gemm_bf16_kernel", "gemm_bf16_kernel"] + (["gemm_bf16_kernel"] if dh == 256 else [])) if tc else (
         ["attn_bwd_small"] if N <= 16 else ["attn_delta", "attn_bwd_dq", "attn_bwd_dkv"])
     order.append((f"s3d_attn_bwd[B={B},H={H},N={N},dh={dh},drop={int(drop)}]", pats))
     torch.cuda.synchronize()
