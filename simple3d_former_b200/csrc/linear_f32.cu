@@ -97,8 +97,8 @@ int sgemm_f32(const float* A, const float* B, float* C, int M, int N, int K, lon
   int splits = 1;
   const long long tiles = (long long)tm * tn;
   if (!relu && gate == nullptr && tiles < num_sms() && K >= 4096) {
-    splits = (int)((2LL * num_sms() + tiles - 1) / tiles);
-    const int max_splits = K / 1024;
+    splits = (int)((4LL * num_sms() + tiles - 1) / tiles);  // measured on [48, 131072] x [131072, 48]: 72 -> 54 us
+    const int max_splits = K / 128;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }

@@ -68,7 +68,7 @@ def main():
     tot = collections.Counter()
     cnt = collections.Counter()
     for e in evs:
-        key = e.name.split("(")[0][-70:]
+        key = e.name.replace("(anonymous namespace)::", "").split("(")[0][-70:]
         tot[key] += e.time_range.end - e.time_range.start
         cnt[key] += 1
     print(f"{name}: span {(t1 - t0) / 1e3:.2f} ms, device busy {busy / 1e3:.2f} ms, idle {(t1 - t0 - busy) / 1e3:.2f} ms in "
