@@ -309,17 +309,19 @@ class BlockFn(torch.autograd.Function):
         dy2 = dy.reshape(T, D).contiguous()
         # the downstream block's backward leaves a bf16 copy of this gradient on the tensor object (see below); autograd
         # hands the same object through when it did not have to accumulate, which saves one cast pass per block
-        dy16 = getattr(dy, "_s3d_bf16", None)
-        if dy16 is None or dy16.shape != (T, D) or getattr(dy, "_s3d_bf16_src", None) != dy.data_ptr():
+        # The side products are only valid for the very tensor they were computed from: same storage AND same version
+        # (autograd's input buffer may add another consumer's gradient IN PLACE into the tensor it was handed first,
+        # which keeps the Python object and its data pointer but bumps the version counter).
+        fresh = (getattr(dy, "_s3d_bf16_src", None) == dy.data_ptr() and getattr(dy, "_s3d_ver", None) == dy._version)
+        dy16 = getattr(dy, "_s3d_bf16", None) if fresh else None
+        if dy16 is None or dy16.shape != (T, D):
             dy16 = L.cast_bf16(dy2)
         n1b, qkv_b, proj_b, n2b, fc1_b, fc2_b = ctx.refs
         pg = _ParamGradStream(dy.device, T * D <= _OVERLAP_LIMIT)  # weight / bias gradients off the critical chain
         # MLP
         # bias gradient of fc2 = column sums of dy: the LayerNorm backward that PRODUCED dy (the downstream block's norm1)
         # has accumulated them on the way (see the end of this function); otherwise one pass over dy
-        dy_colsum = getattr(dy, "_s3d_colsum", None)
-        if dy_colsum is not None and getattr(dy, "_s3d_bf16_src", None) != dy.data_ptr():
-            dy_colsum = None
+        dy_colsum = getattr(dy, "_s3d_colsum", None) if fresh else None
         with pg.fork():
             dfc2_w = _wgrad(fc2_w, dy16, a16)
             if fc2_b is None:
@@ -359,6 +361,7 @@ class BlockFn(torch.autograd.Function):
         dx._s3d_bf16 = dx16
         dx._s3d_bf16_src = dx.data_ptr()
         dx._s3d_colsum = dx_colsum
+        dx._s3d_ver = dx._version
         return (dx, dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w,
                 dfc2_b, None, None, None, None)
 

@@ -226,3 +226,34 @@ def test_trainer_sgd_matches_torch_on_point_model(golden):
             assert float(upd.norm()) < 1e-3 * 0.01 * upd_ref.numel() ** 0.5, n
             continue
         assert float((upd - upd_ref).norm()) <= 5e-2 * scale + 1e-7, (n, float((upd - upd_ref).norm()), scale)
+
+
+def test_block_gradient_side_products_with_two_consumers():
+    """A Block's backward leaves a bf16 copy and the column sums of its input gradient on the tensor for the upstream
+    Block. When that activation has a SECOND consumer, autograd adds the other gradient (possibly in place, same Python
+    object and data pointer): the side products must then be ignored. By linearity the parameter gradients of
+    loss1 + loss2 equal the sum of the gradients of two single-consumer graphs."""
+    from simple3d_former_b200.vision_transformer import Block
+    torch.manual_seed(4)
+    dev = _dev()
+    B, N, D, H = 4, 50, 192, 3
+    blk1 = Block(D, H, mlp_ratio=4.0, qkv_bias=True).to(dev)
+    blk2 = Block(D, H, mlp_ratio=4.0, qkv_bias=True).to(dev)
+    x = torch.randn(B, N, D, device=dev)
+    w = torch.randn(B, N, D, device=dev) * 30.0  # the side branch dominates: a stale side product cannot hide
+    params = list(blk1.parameters())
+
+    def grads(loss_fn):
+        for p in params:
+            p.grad = None
+        h = blk1(x)
+        loss_fn(h).backward()
+        return [p.grad.detach().clone() for p in params]
+
+    g_chain = grads(lambda h: blk2(h).sum())
+    g_side = grads(lambda h: (h * w).sum())
+    for order in (lambda h: blk2(h).sum() + (h * w).sum(), lambda h: (h * w).sum() + blk2(h).sum()):
+        g_both = grads(order)
+        for (n, _), a, b, c in zip(blk1.named_parameters(), g_both, g_chain, g_side):
+            want = b + c
+            assert float((a - want).norm()) <= 2e-2 * float(want.norm()) + 1e-6, (n, float((a - want).norm()), float(want.norm()))
