@@ -531,7 +531,11 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_dkv_kernel(const AttnPar
 // sequences of the group-embed model (12544 x 3 heads x 15 tokens x 12 layers): these are HBM-bound, so reading the
 // operands once instead of twice is the whole win.
 // ================================================================================================
-template <int DH, int NWARPS>
+// NST = 2: each warp double-buffers its four operand tiles (the next pair's loads fly while this one is multiplied).
+// NST = 1: one set of tiles per warp and twice the warps per SM -- at head_dim 256 a set is 32 KB, so 3 double-buffered
+// warps were all an SM could hold and their dependent ldmatrix -> MMA -> store chains left HBM at 62 % of the copy peak;
+// six single-buffered warps keep as many bytes in flight and hide each other's chains.
+template <int DH, int NWARPS, int NST>
 __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnParams p) {
   pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem_attn[];
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   const long long BH = (long long)p.B * p.H;
   const long long gw = (long long)blockIdx.x * NWARPS + warp;
   const long long gstride = (long long)gridDim.x * NWARPS;
-  const uint32_t wbase = smem_u32(smem_attn) + warp * 8 * kTile;
+  const uint32_t wbase = smem_u32(smem_attn) + warp * NST * 4 * kTile;
   // one tile = 16 rows x DH bf16; lane l copies 16-byte chunk l (+32, ...) of every VALID row: the source pointer
   // advances by one row stride per row, the swizzled smem offsets (chunk ^ (row & 7)) are 8 per-lane constants.
   // Rows >= N are never written by cp.async; they are zeroed once here (P = 0 must not meet NaN garbage).
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   for (int c = 0; c < (CH + 31) / 32; ++c)
 #pragma unroll
     for (int k = 0; k < 8; ++k) xs[c][k] = (uint32_t)(((c * 32 + lane) ^ k) << 4);
-  for (int i = lane; i < 8 * 16 * CH; i += 32) {
+  for (int i = lane; i < NST * 4 * 16 * CH; i += 32) {
     const int t = i / (16 * CH), r = (i / CH) % 16, ch = i % CH;
     if (r >= p.N) {
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tile_addr<DH>(wbase + t * kTile, r, ch)), "r"(0));
@@ -584,14 +588,20 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
     load16(sb + 2 * kTile, p.v + tq, p.qkv_rs);
     load16(sb + 3 * kTile, p.dout + to, p.o_rs);
   };
-  if (gw < BH) prefetch(gw, 0);
-  cp_async_commit();
+  if (NST == 2) {
+    if (gw < BH) prefetch(gw, 0);
+    cp_async_commit();
+  }
   int it = 0;
   for (long long bh = gw; bh < BH; bh += gstride, ++it) {
-  if (bh + gstride < BH) prefetch(bh + gstride, (it + 1) & 1);
+  if (NST == 2) {
+    if (bh + gstride < BH) prefetch(bh + gstride, (it + 1) & 1);
+  } else {
+    prefetch(bh, 0);  // the previous pair's reads of these tiles ended at the __syncwarp closing its iteration
+  }
   cp_async_commit();
   const int b = (int)(bh / p.H), h = (int)(bh % p.H);
-  const uint32_t sbase = wbase + (it & 1) * 4 * kTile;
+  const uint32_t sbase = wbase + (NST == 2 ? (it & 1) : 0) * 4 * kTile;
   const uint32_t sQ = sbase, sK = sbase + kTile, sV = sbase + 2 * kTile, sdO = sbase + 3 * kTile;
   const long long qoff = (long long)b * p.qkv_bs + (long long)h * p.qkv_hs;
 
@@ -604,7 +614,8 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_small_kernel(const AttnP
   // padded rows / columns: lse = +inf makes P = 0
   const float lse_r0 = r0 < p.N ? glse[r0] * kLog2e : INFINITY, lse_r1 = r1 < p.N ? glse[r1] * kLog2e : INFINITY;
   const float sc = p.scale * kLog2e;
-  cp_async_wait<1>();
+  if (NST == 2) cp_async_wait<1>();
+  else cp_async_wait<0>();
   __syncwarp();
 
   // ---- S = Q K^T, dP = dO V^T (rows = queries)
@@ -904,9 +915,25 @@ template <int DH>
 static int attn_bwd_dh(const AttnParams& p, cudaStream_t stream) {
   const long long BH = (long long)p.B * p.H;
   if (p.N <= 16) {  // fused delta + dQ + dK + dV, one warp per (batch, head)
+    static const bool two_stage = []() { const char* v = getenv("S3D_ATTN_SMALL_BWD_STAGES"); return v != nullptr && v[0] == '2'; }();
+    if (DH == 256 && !two_stage) {  // single-buffered warps (see the kernel): measured 0.475 ms (3 x 2 stages) -> 0.407 ms
+      // (6 warps, 5.7 TB/s) / 0.414 ms (7 warps) on the stage-1 shape of cfg3 (12544 x 3 heads x 15 tokens)
+      static const bool six = []() { const char* v = getenv("S3D_ATTN_SMALL_BWD_WARPS"); return v == nullptr || v[0] != '7'; }();
+      auto launch1 = [&](auto kern, int nw) -> int {
+        const int smem = nw * 4 * 16 * DH * 2;
+        int rc = set_smem(kern, smem);
+        if (rc) return rc;
+        long long ctas = (BH + nw - 1) / nw;
+        if (ctas > num_sms()) ctas = num_sms();
+        S3D_CUDA_OK(launch_pdl(kern, dim3((unsigned)ctas), dim3(nw * 32), (size_t)(smem), stream, p));
+        S3D_LAUNCH_OK();
+        return S3D_OK;
+      };
+      return six ? launch1(attn_bwd_small_kernel<DH, 6, 1>, 6) : launch1(attn_bwd_small_kernel<DH, 7, 1>, 7);
+    }
     constexpr int NW = (DH == 64) ? 8 : (DH == 192 ? 4 : 3);
     constexpr int smem = NW * 2 * 4 * 16 * DH * 2;  // two stages of {Q, K, V, dO} per warp
-    auto kern = attn_bwd_small_kernel<DH, NW>;
+    auto kern = attn_bwd_small_kernel<DH, NW, 2>;
     int rc = set_smem(kern, smem);
     if (rc) return rc;
     long long ctas = (BH + NW - 1) / NW;
