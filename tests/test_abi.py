@@ -66,3 +66,17 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dp, f)).read()
                 assert "s3d_oracle" not in text and "reference_harness" not in text, os.path.join(dp, f)
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), os.path.join(dp, f)
+
+
+def test_attn_bwd_workspace_bytes_host_side():
+    """s3d_attn_bwd_workspace_bytes is pure host arithmetic (no CUDA call): two bf16 score matrices in 64-key panels,
+    each rounded up to 1 KiB; 0 when the single-score-pass backward does not apply."""
+    from simple3d_former_b200 import _lib as L
+    f = L.lib().s3d_attn_bwd_workspace_bytes
+    B, H, N, dh = 15, 4, 12544, 192
+    one = (2 * B * H * N * ((N + 63) // 64 * 64) + 1023) // 1024 * 1024
+    assert f(B, H, N, dh) == 2 * one
+    assert f(64, 3, 197, 256) == 2 * ((2 * 64 * 3 * 197 * 256 + 1023) // 1024 * 1024)  # head_dim 256: spill-only form
+    assert f(12544, 3, 15, 256) == 0      # 15-token sequences keep the warp-per-sequence kernels
+    assert f(2, 4, 1024, 100) == 0        # head_dim without a tcgen05 kernel
+    assert f(0, 4, 1024, 64) == 0
