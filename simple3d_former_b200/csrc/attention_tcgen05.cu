@@ -747,7 +747,8 @@ static int fa_fwd1_launch(const AttnParams& a, cudaStream_t stream) {
 }
 
 // ================================================================================================
-// Backward on tcgen05. Two kernels (no atomics, no dQ round trips through HBM):
+// Backward on tcgen05. Recomputing form (callers without a workspace) = two kernels (no atomics, no round trips through
+// HBM); the single-score-pass form built on the dQ kernel is described at FaDqCfg below:
 //   dQ   : CTA = 128 query rows; per 64-key block  S = Q K^T, dP = dO V^T (TMEM, double buffered),
 //          dS = P o (dP - delta) -> bf16 smem,  dQ += dS K  (K block re-read as an MN-major B operand)
 //   dKdV : CTA = 128 key rows; per 64-query block S^T = K Q^T, dP^T = V dO^T,  P^T / dS^T -> bf16 smem,
@@ -827,14 +828,14 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[32]) 
 // S / dP are single-buffered: the element-wise warps pull them into registers and hand the columns back at once
 // (sp_free), so S/dP(j+1) runs on the tensor core while dS(j) is computed; dS tiles are double-buffered in smem.
 //
-// SPILL variant (long sequences, see fa_bwd_launch): this kernel is then the ONLY pass over the score matrix of the
+// SPILL variant (N >= 128 with a caller workspace, see fa_bwd_spill_launch): this kernel is then the ONLY pass over the score matrix of the
 // backward. Besides dQ it writes the two bf16 [query, key] matrices the key-side gradients contract over queries,
 //     Pd = P o mask          (dV = Pd^T dO / (1 - p))          dS = P o (mask o dP / (1 - p) - delta)     (dK = dS^T Q scale)
 // tile by tile (the dS tile is the A operand of the dQ MMAs and sits in shared memory anyway; the Pd tile gets a buffer
 // of its own, paid for with one K/V stage) with one TMA store per tile, and dK / dV become two batched MN-major x MN-major
 // GEMMs of gemm_bf16_kernel that read them back once at the HBM rate. 5 GEMM units at (or near) the tensor-memory rate
 // instead of 7-8 (dQ 3 + fused dK/dV 4 with shared-memory A operands, or split dK 3 + dV 2), at the price of 8 B of
-// workspace traffic per score element (4 B written here at ~4.5 TB/s while the tensor core works, 4 B read by the GEMMs).
+// workspace traffic per score element (4 B written here at ~3.5 TB/s while the tensor core works, 4 B read by the GEMMs at ~4.9 TB/s).
 // MODE 0: recomputing form (dQ only). MODE 1: SPILL (dQ + workspace stores). MODE 2: spill ONLY -- no dQ accumulator, dQ
 // is a third GEMM over the spilled dS (its K-major A operand is a panel as it lies): the variant for head_dim 256 (timm
 // Blocks of deit_base), whose dQ accumulator + Q + dO + S + dP would need 640 TMEM columns.
